@@ -1,0 +1,290 @@
+"""CPU restatement (torch CPU fp32) of the reference GAN-step hot path.  TEST INFRASTRUCTURE.
+
+Each function cites the reference file:line it follows (reference = r9y9/gantts @ fb1e75f).  The
+reference itself is Python and cannot travel to the GPU box, so this port is what the ``-m gpu``
+parity tests, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference``
+leg run there.  It is PINNED: ``tests/golden/make_golden.py`` runs the unmodified reference
+(``oracle.reference_loader``) and this port on the same seeded inputs in the build container and
+commits the reference outputs under ``tests/golden/``; ``tests/test_oracle_golden.py`` checks the
+port against those vectors (bit-exact for masks/indexing, <=1e-6 relative for float outputs: the
+port issues the same torch CPU ops in the same order as the reference).
+
+Written as plain functions over explicit weight lists (no nn.Module copies of the reference
+classes): parameters are passed as ``[(W0, b0), (W1, b1), ...]`` with ``W`` laid out ``[out, in]``
+exactly like the reference's ``nn.Linear`` state_dict entries.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import nnmnkwii_port as nn_port
+
+LEAKY_SLOPE = 0.01          # nn.LeakyReLU() default, reference gantts/models.py:37,132
+BCE_EPS = 1e-20             # reference train.py:246,285
+
+
+# ----------------------------------------------------------------------------- seqloss.py
+def sequence_mask(lengths, max_len=None):
+    """reference gantts/seqloss.py:9-20 -- ``arange(max_len)[None] < len[:, None]`` as float."""
+    lengths = torch.as_tensor(lengths).long().view(-1)
+    if max_len is None:
+        max_len = int(lengths.max())
+    rng = torch.arange(0, int(max_len)).long().unsqueeze(0).expand(lengths.numel(), int(max_len))
+    return (rng < lengths.unsqueeze(1)).float()
+
+
+def masked_mse(inp, target, lengths=None, mask=None, max_len=None):
+    """reference gantts/seqloss.py:27-43 -- sum(((in - tgt) * m)^2) / sum(m), m is (B,T,1)."""
+    if lengths is None and mask is None:
+        raise RuntimeError("Should provide either lengths or mask")
+    if mask is None:
+        mask = sequence_mask(lengths, max_len).unsqueeze(-1)
+    m = mask.expand_as(inp)
+    loss = F.mse_loss(inp * m, target * m, reduction="sum")
+    return loss / mask.sum()
+
+
+# ------------------------------------------------------------------------- multistream.py
+def get_static_stream_sizes(stream_sizes, has_dynamic_features, num_windows):
+    """reference gantts/multistream.py:46-53."""
+    out = np.array(stream_sizes)
+    sel = np.asarray(has_dynamic_features, dtype=bool)
+    out[sel] = out[sel] / num_windows
+    return out
+
+
+def select_streams(inputs, stream_sizes=(60, 1, 1, 1), streams=(True, True, True, True)):
+    """reference gantts/multistream.py:33-43 -- column gather of enabled streams."""
+    starts = np.hstack(([0], np.cumsum(stream_sizes)[:-1]))
+    parts = [inputs[:, :, int(s):int(s) + int(n)]
+             for s, n, on in zip(starts, stream_sizes, streams) if on]
+    return torch.cat(parts, dim=-1)
+
+
+def get_static_features(inputs, num_windows, stream_sizes=(180, 3, 1, 3),
+                        has_dynamic_features=(True, True, False, True),
+                        streams=(True, True, True, True)):
+    """reference gantts/multistream.py:56-79 -- static columns of a static+delta tensor."""
+    D = inputs.size(-1)
+    if stream_sizes is None or (len(stream_sizes) == 1 and has_dynamic_features[0]):
+        return inputs[:, :, :D // num_windows]
+    if len(stream_sizes) == 1 and not has_dynamic_features[0]:
+        return inputs
+    starts = np.hstack(([0], np.cumsum(stream_sizes)[:-1]))
+    parts = []
+    for s, n, dyn, on in zip(starts, stream_sizes, has_dynamic_features, streams):
+        if not on:
+            continue
+        width = int(n) // num_windows if dyn else int(n)
+        parts.append(inputs[:, :, int(s):int(s) + width])
+    return torch.cat(parts, dim=-1)
+
+
+def multi_stream_mlpg(inputs, R, stream_sizes=(180, 3, 1, 3),
+                      has_dynamic_features=(True, True, False, True),
+                      streams=(True, True, True, True)):
+    """reference gantts/multistream.py:82-123 -- per-stream dense-R MLPG, static streams copied."""
+    if inputs.size(-1) != sum(stream_sizes):
+        raise RuntimeError("You probably have specified wrong dimention params.")
+    starts = np.hstack(([0], np.cumsum(stream_sizes)[:-1]))
+    ends = np.cumsum(stream_sizes)
+    parts = []
+    for s, e, dyn, on in zip(starts, ends, has_dynamic_features, streams):
+        if not on:
+            continue
+        x = inputs[:, :, int(s):int(e)]
+        parts.append(nn_port.unit_variance_mlpg(R, x) if dyn else x)
+    return torch.cat(parts, dim=-1)
+
+
+# ------------------------------------------------------------------------------ models.py
+def mlp_forward(x, layers, dropout_p=0.0, training=False, last_sigmoid=False):
+    """reference gantts/models.py:137-141 -- x = Dropout(LeakyReLU(Linear(x))) per hidden
+    layer, then last_linear (+ sigmoid).  ``layers`` = [(W, b), ...]; the last pair is
+    ``last_linear``."""
+    for W, b in layers[:-1]:
+        x = F.dropout(F.leaky_relu(F.linear(x, W, b), LEAKY_SLOPE), dropout_p, training)
+    W, b = layers[-1]
+    x = F.linear(x, W, b)
+    return torch.sigmoid(x) if last_sigmoid else x
+
+
+def in2out_highway_forward(x, R, gate, layers, static_dim, dropout_p=0.0, training=False):
+    """reference gantts/models.py:54-69 -- returns (y_hat, x_static + sigmoid(T x_static) * MLPG(y_hat))."""
+    x = x.unsqueeze(0) if x.dim() == 2 else x
+    x_static = x[:, :, :static_dim]
+    Tx = torch.sigmoid(F.linear(x_static, gate[0], gate[1]))
+    h = mlp_forward(x, layers, dropout_p, training, last_sigmoid=False)
+    Gx = nn_port.unit_variance_mlpg(R, h)
+    return h, x_static + Tx * Gx
+
+
+def lstm_forward(x, lengths, lstm, hidden2out, last_sigmoid=False):
+    """reference gantts/models.py:204-213 (LSTMRNN) / :181-190 (GRURNN, also an nn.LSTM):
+    pack -> nn.LSTM -> pad -> Linear (-> sigmoid).  ``lstm`` is a torch ``nn.LSTM`` (the oracle
+    for the recurrent kernel is torch's own CPU LSTM, as in the reference)."""
+    lengths = [int(l) for l in lengths]
+    packed = torch.nn.utils.rnn.pack_padded_sequence(x, lengths, batch_first=True)
+    out, _ = lstm(packed)
+    out, _ = torch.nn.utils.rnn.pad_packed_sequence(out, batch_first=True)
+    out = F.linear(out, hidden2out[0], hidden2out[1])
+    return torch.sigmoid(out) if last_sigmoid else out
+
+
+# ------------------------------------------------------------------- train.py step functions
+def get_selected_static_stream(y_static, hp):
+    """reference train.py:232-242 -- adversarial streams, first ``mask_nth`` mgc columns dropped."""
+    sizes = get_static_stream_sizes(hp["stream_sizes"], hp["has_dynamic_features"],
+                                    hp["num_windows"])
+    sel = select_streams(y_static, sizes, streams=hp["adversarial_streams"])
+    if hp.get("mask_nth_mgc_for_adv_loss", 0) > 0:
+        sel = sel[:, :, hp["mask_nth_mgc_for_adv_loss"]:]
+    return sel
+
+
+def bce_real(D, mask, T, eps=BCE_EPS):
+    """reference train.py:269 -- -(log(D + eps) * m).sum() / T."""
+    return -(torch.log(D + eps) * mask).sum() / T
+
+
+def bce_fake(D, mask, T, eps=BCE_EPS):
+    """reference train.py:270 -- -(log(1 - D + eps) * m).sum() / T."""
+    return -(torch.log(1 - D + eps) * mask).sum() / T
+
+
+def clip_grad_norm(grads, max_norm=1.0):
+    """torch.nn.utils.clip_grad_norm_ semantics (reference train.py:275,317)."""
+    total = torch.sqrt(sum((g.detach() ** 2).sum() for g in grads))
+    coef = torch.clamp(max_norm / (total + 1e-6), max=1.0)
+    for g in grads:
+        g.mul_(coef)
+    return total
+
+
+def adagrad_step(params, grads, state_sums, lr=0.01, weight_decay=1e-7, eps=1e-10):
+    """torch.optim.Adagrad (lr_decay=0, initial_accumulator_value=0) as configured in reference
+    hparams.py:223-227,240-244 and stepped at train.py:276,318."""
+    with torch.no_grad():
+        for p, g, s in zip(params, grads, state_sums):
+            g = g + weight_decay * p
+            s.addcmul_(g, g, value=1.0)
+            p.addcdiv_(g, s.sqrt() + eps, value=-lr)
+
+
+class GanStepState(object):
+    """Weights + Adagrad accumulators for one MLP-G / MLP-D pair (plain tensors)."""
+
+    def __init__(self, g_layers, d_layers):
+        self.g = [(W.clone().requires_grad_(True), b.clone().requires_grad_(True)) for W, b in g_layers]
+        self.d = [(W.clone().requires_grad_(True), b.clone().requires_grad_(True)) for W, b in d_layers]
+        self.g_sum = [torch.zeros_like(t) for pair in self.g for t in pair]
+        self.d_sum = [torch.zeros_like(t) for pair in self.d for t in pair]
+
+    def g_params(self):
+        return [t for pair in self.g for t in pair]
+
+    def d_params(self):
+        return [t for pair in self.d for t in pair]
+
+
+def gan_step_mlp(state, x, y, lengths, R, hp, w_d=1.0, mse_w=0.0, mge_w=1.0, adv_w=1.0,
+                 dropout_g=0.0, dropout_d=0.0, training=True, lr=0.01, weight_decay=1e-7,
+                 update=True):
+    """One mini-batch of the reference train_loop body (train.py:528-580) for an MLP generator
+    and MLP discriminator, restated with explicit tensors.
+
+    Order of operations and quirks preserved: single zero_grad at the
+    top; y_hat_static is NOT detached in the discriminator update, so ``loss_d.backward`` also
+    deposits the fake-term gradient on the generator; the discriminator steps before the third
+    D forward used by the adversarial loss; gradients of both backwards accumulate on G before
+    its clip + Adagrad step.  Returns a dict of python floats and the generator outputs.
+    """
+    nw = hp["num_windows"]
+    y_static = get_static_features(y, nw, hp["stream_sizes"], hp["has_dynamic_features"])   # :528-529
+    mask = sequence_mask(lengths, x.size(1)).unsqueeze(-1)                                   # :535
+    for p in state.g_params() + state.d_params():                                            # :538-539
+        p.grad = None
+    # apply_generator, train.py:336-355
+    y_hat = mlp_forward(x, state.g, dropout_g, training, last_sigmoid=False)
+    y_hat_static = multi_stream_mlpg(y_hat, R, hp["stream_sizes"], hp["has_dynamic_features"])
+    out = {}
+    T = mask.sum().item()
+    cond = hp.get("discriminator_linguistic_condition", False)
+    if w_d > 0:
+        # update_discriminator, train.py:245-279
+        real_in = get_selected_static_stream(y_static, hp)
+        fake_in = get_selected_static_stream(y_hat_static, hp)
+        if cond:
+            real_in = torch.cat((x, real_in), -1)
+            fake_in = torch.cat((x, fake_in), -1)
+        D_real = mlp_forward(real_in, state.d, dropout_d, training, last_sigmoid=True)
+        out["real_correct"] = ((D_real > 0.5).float() * mask).sum().item()
+        D_fake = mlp_forward(fake_in, state.d, dropout_d, training, last_sigmoid=True)
+        out["fake_correct"] = ((D_fake < 0.5).float() * mask).sum().item()
+        loss_real = bce_real(D_real, mask, T)
+        loss_fake = bce_fake(D_fake, mask, T)
+        loss_d = loss_real + loss_fake
+        if update:
+            loss_d.backward(retain_graph=True)
+            dg = [p.grad for p in state.d_params()]
+            out["d_grad_norm"] = float(clip_grad_norm(dg, 1.0))
+            adagrad_step(state.d_params(), dg, state.d_sum, lr, weight_decay)
+        out.update(loss_d=loss_d.item(), loss_fake_d=loss_fake.item(), loss_real_d=loss_real.item())
+    # update_generator, train.py:282-320
+    loss_mge = masked_mse(y_hat_static, y_static, mask=mask)
+    loss_mse = masked_mse(y_hat, y, mask=mask)
+    if adv_w > 0 and w_d > 0:
+        fake_in = get_selected_static_stream(y_hat_static, hp)
+        if cond:
+            fake_in = torch.cat((x, fake_in), -1)
+        D_adv = mlp_forward(fake_in, state.d, dropout_d, training, last_sigmoid=True)
+        loss_adv = bce_real(D_adv, mask, T)
+    else:
+        loss_adv = y.new_zeros(1)
+        adv_w = 0.0
+    loss_g = (mse_w * loss_mse + mge_w * loss_mge) + adv_w * loss_adv
+    if update:
+        loss_g.backward()
+        gg = [p.grad for p in state.g_params()]
+        out["g_grad_norm"] = float(clip_grad_norm(gg, 1.0))
+        adagrad_step(state.g_params(), gg, state.g_sum, lr, weight_decay)
+    out.update(loss_mse=loss_mse.item(), loss_mge=loss_mge.item(), loss_adv=float(loss_adv.detach()),
+               loss_g=float(loss_g.detach()))
+    return out, y_hat.detach(), y_hat_static.detach()
+
+
+# ------------------------------------------------------------------------------ SRU (unpinned)
+def sru_layer_forward(x, W, b, bidirectional=False, use_tanh=False, use_relu=True):
+    """SRU v1 layer (Lei et al. 2017, github.com/taolei87/sru ``cuda_functional.py``; NOT vendored
+    in the reference tree -- restated from the published recurrence, **parity unpinned**):
+
+        U = x W ; per direction and hidden unit j, with k = 3 (n_in == n_out) or 4 gates
+        f_t = sigmoid(U_f + b_f) ; r_t = sigmoid(U_r + b_r)
+        c_t = f_t * c_{t-1} + (1 - f_t) * U_x
+        h_t = r_t * g(c_t) + (1 - r_t) * x'_t     (x' = x if k == 3 else U_x')
+
+    ``x``: (T, B, n_in); ``W``: (n_in, dirs*k*d) laid out ``[..., dir, d, k]`` (k fastest) as in
+    the upstream kernel; ``b``: (dirs*2*d,) = [f-bias | r-bias] per direction."""
+    T, B, n_in = x.shape
+    dirs = 2 if bidirectional else 1
+    d = b.numel() // (2 * dirs)
+    k = W.shape[1] // (d * dirs)
+    U = (x.reshape(-1, n_in) @ W).view(T, B, dirs, d, k)
+    bias = b.view(dirs, 2, d)
+    act = torch.tanh if use_tanh else (torch.relu if use_relu else (lambda v: v))
+    outs = []
+    for di in range(dirs):
+        c = x.new_zeros(B, d)
+        hs = [None] * T
+        order = range(T) if di == 0 else range(T - 1, -1, -1)
+        for t in order:
+            u = U[t, :, di]
+            f = torch.sigmoid(u[..., 1] + bias[di, 0])
+            r = torch.sigmoid(u[..., 2] + bias[di, 1])
+            c = f * c + (1 - f) * u[..., 0]
+            xp = x[t] if k == 3 else u[..., 3]
+            hs[t] = r * act(c) + (1 - r) * xp
+        outs.append(torch.stack(hs, 0))
+    return torch.cat(outs, -1)

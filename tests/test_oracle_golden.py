@@ -1,0 +1,156 @@
+"""Pin the CPU oracle (oracle/gantts_port.py + oracle/nnmnkwii_port.py) against golden vectors
+produced by the unmodified reference (tests/golden/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import WINDOWS, TTS_HP, rel_err
+from oracle import gantts_port as gp
+from oracle import nnmnkwii_port as nnp
+
+F32_TOL = 2e-6   # same torch CPU ops in the same order; allow for thread-count dependent reductions
+
+
+def T(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def test_sequence_mask_bit_exact(golden_ops):
+    lengths = T(golden_ops["mask_lengths"])
+    assert np.array_equal(gp.sequence_mask(lengths).numpy(), golden_ops["mask"])
+    assert np.array_equal(gp.sequence_mask(lengths, 30).numpy(), golden_ops["mask_maxlen30"])
+
+
+def test_masked_mse(golden_ops):
+    a = T(golden_ops["mse_in"]).requires_grad_(True)
+    b = T(golden_ops["mse_tgt"])
+    lengths = T(golden_ops["mask_lengths"])
+    loss = gp.masked_mse(a, b, lengths=lengths)
+    loss.backward()
+    assert rel_err(loss.detach().numpy(), golden_ops["mse_loss"]) < F32_TOL
+    assert rel_err(a.grad.numpy(), golden_ops["mse_grad"]) < F32_TOL
+    m = gp.sequence_mask(lengths).unsqueeze(-1)
+    assert rel_err(gp.masked_mse(a, b, mask=m).detach().numpy(), golden_ops["mse_loss_mask"]) < F32_TOL
+    with pytest.raises(RuntimeError):
+        gp.masked_mse(a, b)
+
+
+def test_stream_indexing_bit_exact(golden_ops):
+    x = torch.arange(0, 63).float().expand(2, 4, 63)
+    for name in ("1111", "1000", "1001", "0010", "0101"):
+        streams = [c == "1" for c in name]
+        assert np.array_equal(gp.select_streams(x, [60, 1, 1, 1], streams).numpy(),
+                              golden_ops["select_" + name])
+    assert np.array_equal(gp.get_static_stream_sizes([180, 3, 1, 3], [True, True, False, True], 3),
+                          golden_ops["static_sizes"])
+    y = T(golden_ops["ms_in"])
+    assert np.array_equal(gp.get_static_features(y, 3).numpy(), golden_ops["static_all"])
+    assert np.array_equal(
+        gp.get_static_features(y, 3, streams=[True, False, False, True]).numpy(),
+        golden_ops["static_1001"])
+
+
+def test_multi_stream_mlpg(golden_ops):
+    y = T(golden_ops["ms_in"]).requires_grad_(True)
+    R = T(nnp.unit_variance_mlpg_matrix(WINDOWS, y.shape[1]))
+    z = gp.multi_stream_mlpg(y, R)
+    z.backward(T(golden_ops["mlpg_gout"]))
+    assert rel_err(z.detach().numpy(), golden_ops["mlpg_out"]) < F32_TOL
+    assert rel_err(y.grad.numpy(), golden_ops["mlpg_gin"]) < F32_TOL
+    # vuv stream is copied through bit-exactly (reference tests/test_gantts.py:158)
+    assert np.array_equal(z.detach().numpy()[:, :, 61], golden_ops["ms_in"][:, :, 183])
+    z2 = gp.multi_stream_mlpg(y.detach(), R, streams=[True, False, True, False])
+    assert rel_err(z2.numpy(), golden_ops["mlpg_out_1010"]) < F32_TOL
+    with pytest.raises(RuntimeError):
+        gp.multi_stream_mlpg(y.detach()[:, :, :100], R)
+
+
+def test_mlpg_dense_vs_banded_f64(golden_ops):
+    """The reference arithmetic (dense fp32 R matmul) against the independent fp64 banded solve."""
+    y = golden_ops["ms_in"][:, :, :180]
+    ref64 = nnp.mlpg_solve_f64(WINDOWS, y)
+    assert rel_err(golden_ops["mlpg_out"][:, :, :60], ref64) < 5e-6
+    v = golden_ops["vc_in"]
+    assert rel_err(golden_ops["vc_out"], nnp.mlpg_solve_f64(WINDOWS, v)) < 5e-6
+    assert rel_err(golden_ops["w2_out"], nnp.mlpg_solve_f64(WINDOWS[:2], golden_ops["w2_in"])) < 5e-6
+
+
+def test_normal_matrix_is_pentadiagonal():
+    """P interior [0.75,-4,7.5,-4,0.75], corners 6.25."""
+    P = nnp.normal_matrix(WINDOWS, 12)
+    assert np.allclose(np.diagonal(P)[1:-1], 7.5) and P[0, 0] == 6.25 and P[-1, -1] == 6.25
+    assert np.allclose(np.diagonal(P, 1), -4.0) and np.allclose(np.diagonal(P, 2), 0.75)
+    assert np.count_nonzero(np.triu(P, 3)) == 0
+
+
+def _layers(g, prefix, n_hidden):
+    ls = [(T(g[prefix + "layers.%d.weight" % i]), T(g[prefix + "layers.%d.bias" % i]))
+          for i in range(n_hidden)]
+    ls.append((T(g[prefix + "last_linear.weight"]), T(g[prefix + "last_linear.bias"])))
+    return ls
+
+
+def test_mlp_forward_backward(golden_models):
+    g = golden_models
+    layers = [(W.requires_grad_(True), b.requires_grad_(True)) for W, b in _layers(g, "mlpg_", 3)]
+    x = T(g["mlp_g_x"]).requires_grad_(True)
+    y = gp.mlp_forward(x, layers)
+    y.backward(T(g["mlp_g_gy"]))
+    assert rel_err(y.detach().numpy(), g["mlp_g_y"]) < F32_TOL
+    assert rel_err(x.grad.numpy(), g["mlp_g_gx"]) < F32_TOL
+    for i, (W, b) in enumerate(layers[:-1]):
+        assert rel_err(W.grad.numpy(), g["mlp_g_grad_layers.%d.weight" % i]) < F32_TOL
+        assert rel_err(b.grad.numpy(), g["mlp_g_grad_layers.%d.bias" % i]) < F32_TOL
+    yd = gp.mlp_forward(T(g["mlp_d_x"]), _layers(g, "mlpd_", 3), last_sigmoid=True)
+    assert rel_err(yd.numpy(), g["mlp_d_y"]) < F32_TOL
+
+
+def test_in2out_highway(golden_models):
+    g = golden_models
+    layers = [(T(g["hw_H.%d.weight" % i]), T(g["hw_H.%d.bias" % i])) for i in range(2)]
+    layers.append((T(g["hw_last_linear.weight"]), T(g["hw_last_linear.bias"])))
+    gate = (T(g["hw_T.weight"]), T(g["hw_T.bias"]))
+    x = T(g["hw_x"])
+    R = T(nnp.unit_variance_mlpg_matrix(WINDOWS, x.shape[1]))
+    y, ys = gp.in2out_highway_forward(x, R, gate, layers, static_dim=10)
+    assert rel_err(y.numpy(), g["hw_y"]) < F32_TOL
+    assert rel_err(ys.numpy(), g["hw_ystatic"]) < F32_TOL
+
+
+def test_lstm(golden_models):
+    g = golden_models
+    lstm = torch.nn.LSTM(12, 16, 2, batch_first=True, bidirectional=True)
+    lstm.load_state_dict({k[len("lstm_lstm."):]: T(g[k]) for k in g.files if k.startswith("lstm_lstm.")})
+    lstm.eval()
+    h2o = (T(g["lstm_hidden2out.weight"]), T(g["lstm_hidden2out.bias"]))
+    with torch.no_grad():
+        y = gp.lstm_forward(T(g["lstm_x"]), g["lstm_lengths"], lstm, h2o)
+    assert rel_err(y.numpy(), g["lstm_y"]) < F32_TOL
+
+
+@pytest.mark.parametrize("tag,cond", [("u_", False), ("c_", True)])
+def test_gan_step_two_iterations(golden_step, tag, cond):
+    """Losses, generator outputs and post-step weights of two consecutive reference mini-batches."""
+    g = golden_step
+    state = gp.GanStepState(_layers(g, tag + "g0_", 3), _layers(g, tag + "d0_", 3))
+    hp = dict(TTS_HP, discriminator_linguistic_condition=cond)
+    R = T(nnp.unit_variance_mlpg_matrix(WINDOWS, 30))
+    for it in range(2):
+        p = "%sit%d_" % (tag, it)
+        out, y_hat, y_hat_static = gp.gan_step_mlp(
+            state, T(g[p + "x"]), T(g[p + "y"]), g[p + "lengths"], R, hp,
+            w_d=1.0, mse_w=0.0, mge_w=1.0, adv_w=1.0)
+        ref = g[p + "losses"]
+        got = [out["loss_d"], out["loss_fake_d"], out["loss_real_d"], out["loss_mse"],
+               out["loss_mge"], out["loss_adv"], out["loss_g"]]
+        assert np.allclose(got, ref, rtol=2e-6, atol=0), (got, ref)
+        assert [out["real_correct"], out["fake_correct"]] == list(g[p + "counts"])
+        assert rel_err(y_hat.numpy(), g[p + "y_hat"]) < F32_TOL
+        assert rel_err(y_hat_static.numpy(), g[p + "y_hat_static"]) < F32_TOL
+        names = ["layers.0", "layers.1", "layers.2", "last_linear"]
+        for (W, b), n in zip(state.g, names):
+            assert rel_err(W.detach().numpy(), g[p + "g_" + n + ".weight"]) < 1e-5
+            assert rel_err(b.detach().numpy(), g[p + "g_" + n + ".bias"]) < 1e-5
+        for (W, b), n in zip(state.d, names):
+            assert rel_err(W.detach().numpy(), g[p + "d_" + n + ".weight"]) < 1e-5
+            assert rel_err(b.detach().numpy(), g[p + "d_" + n + ".bias"]) < 1e-5
