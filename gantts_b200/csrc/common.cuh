@@ -1,0 +1,82 @@
+// Shared helpers for libgantts_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/gantts_b200.h"
+
+namespace gantts {
+
+// Thread-local last-error message (gantts_last_error_string()).
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define GANTTS_CHECK_ARG(cond, ...)            \
+  do {                                         \
+    if (!(cond)) {                             \
+      ::gantts::set_error(__VA_ARGS__);        \
+      return GANTTS_E_BADARG;                  \
+    }                                          \
+  } while (0)
+
+#define GANTTS_CUDA(call)                                        \
+  do {                                                           \
+    cudaError_t _e = (call);                                     \
+    if (_e != cudaSuccess) return ::gantts::cuda_fail(_e, #call); \
+  } while (0)
+
+#define GANTTS_LAUNCH_CHECK(name)                                     \
+  do {                                                                \
+    cudaError_t _e = cudaGetLastError();                              \
+    if (_e != cudaSuccess) return ::gantts::cuda_fail(_e, "launch " name); \
+  } while (0)
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide sum of up to 4 values; result valid in thread 0.  smem: float[4][32].
+template <int NV>
+__device__ __forceinline__ void block_sum(float (&v)[NV], float* smem) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) smem[i * 32 + warp] = v[i];
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float x = lane < nwarp ? smem[i * 32 + lane] : 0.f;
+      v[i] = warp_sum(x);
+    }
+  }
+}
+
+// Counter-based keep decision for dropout: 32-bit mix of (seed, element index), two elements per
+// hash (16-bit thresholds).  Not torch's Philox stream (hard part 4).
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ uint32_t dropout_bits(uint64_t seed, uint64_t pair_index) {
+  uint32_t lo = static_cast<uint32_t>(pair_index), hi = static_cast<uint32_t>(pair_index >> 32);
+  uint32_t s0 = static_cast<uint32_t>(seed), s1 = static_cast<uint32_t>(seed >> 32);
+  return mix32(mix32(lo ^ s0) + (hi ^ s1) * 0x9e3779b9U + 0x85ebca6bU);
+}
+// keep iff 16-bit field >= thresh, thresh = round(p * 65536).
+__device__ __forceinline__ bool dropout_keep(uint64_t seed, uint64_t elem_index, uint32_t thresh) {
+  uint32_t bits = dropout_bits(seed, elem_index >> 1);
+  uint32_t f = (elem_index & 1) ? (bits >> 16) : (bits & 0xffffu);
+  return f >= thresh;
+}
+
+}  // namespace gantts

@@ -1,0 +1,339 @@
+// MLPG trajectory generation as stencil + row-variant FIR (see include/gantts_b200.h).
+//
+// Reference path replaced: nnmnkwii.paramgen.unit_variance_mlpg_matrix (train.py:510-513, a dense
+// (T x 3T) matrix rebuilt on the CPU per batch) + nnmnkwii.autograd.unit_variance_mlpg (a dense fp32
+// matmul, gantts/multistream.py:120, gantts/models.py:66,115).  y = R mu with R = P^-1 W^T is
+// evaluated as  b = W^T mu  (<=5-tap stencil per window)  followed by  y_t = sum_j G[t][j] b_{t-K+j},
+// G = rows of P^-1 truncated at +-K (entries beyond are < 3e-10 of the diagonal for the hparams
+// windows).  Per-column arithmetic does not depend on which other columns are in the launch nor on
+// the launch geometry (tiles depend on T only), which the reference test
+// tests/test_gantts.py:156-159 (bitwise whole-vs-slice equality) requires.
+//
+// HBM-bound by design: algorithmic bytes per (b,t) = 4 * (sum of stream widths + output columns).
+#include <math.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace gantts {
+
+constexpr int K_HALF = GANTTS_MLPG_HALF_TAPS;     // 24
+constexpr int NTAPS = 2 * K_HALF + 1;             // 49
+constexpr int GROW = 52;                          // taps padded to a float4 multiple
+constexpr int TT = 64;                            // frames per block
+constexpr int TC = 64;                            // columns per block
+constexpr int HALO = 2;                           // max(l,u)
+constexpr int MLPG_THREADS = 256;
+
+struct ColInfo {
+  int in_col;   // column of the window-0 component, -1 when the column is out of range
+  int sd;
+  int dyn;
+};
+
+__device__ __forceinline__ ColInfo find_col(const gantts_streams_t& st, int oc) {
+  ColInfo ci{-1, 0, 0};
+#pragma unroll 1
+  for (int s = 0; s < st.n; ++s) {
+    int d = oc - st.out_start[s];
+    if (d >= 0 && d < st.sd[s]) {
+      ci.in_col = st.in_start[s] + d;
+      ci.sd = st.sd[s];
+      ci.dyn = st.dyn[s];
+    }
+  }
+  return ci;
+}
+
+// acc[i] = sum_j G[row0+i][j] * win[i+j], 8 rows at a time, window held in registers.
+__device__ __forceinline__ void fir8(const float* __restrict__ gs, int grow0, const float* win,
+                                     float* acc) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4* g4 = reinterpret_cast<const float4*>(gs + (grow0 + i) * GROW);
+    float a = 0.f;
+#pragma unroll
+    for (int q = 0; q < GROW / 4; ++q) {
+      float4 g = g4[q];
+      if (4 * q + 0 < NTAPS) a = fmaf(g.x, win[i + 4 * q + 0], a);
+      if (4 * q + 1 < NTAPS) a = fmaf(g.y, win[i + 4 * q + 1], a);
+      if (4 * q + 2 < NTAPS) a = fmaf(g.z, win[i + 4 * q + 2], a);
+      if (4 * q + 3 < NTAPS) a = fmaf(g.w, win[i + 4 * q + 3], a);
+    }
+    acc[i] = a;
+  }
+}
+
+__global__ void __launch_bounds__(MLPG_THREADS)
+mlpg_fwd_kernel(const float* __restrict__ in, int64_t in_bs, int64_t in_ts,
+                float* __restrict__ out, int64_t out_bs, int64_t out_ts,
+                const float* __restrict__ table, gantts_streams_t st, gantts_windows_t win,
+                int T, int ncols) {
+  extern __shared__ __align__(16) float smem[];
+  float* bv = smem;                                   // [(TT + 2K)][TC]
+  float* gs = smem + (TT + 2 * K_HALF) * TC;          // [TT][GROW]
+  const int b = blockIdx.z, t0 = blockIdx.y * TT, c0 = blockIdx.x * TC;
+  const float* inb = in + (int64_t)b * in_bs;
+
+  for (int i = threadIdx.x; i < TT * GROW; i += MLPG_THREADS) {
+    int r = i / GROW, j = i - r * GROW, t = t0 + r;
+    gs[i] = (t < T && j < NTAPS) ? table[(int64_t)t * NTAPS + j] : 0.f;
+  }
+  // Phase 1: b = W^T mu over [t0-K, t0+TT+K) (or the raw input for static streams).
+  for (int i = threadIdx.x; i < (TT + 2 * K_HALF) * TC; i += MLPG_THREADS) {
+    int r = i / TC, c = i - r * TC, t = t0 - K_HALF + r;
+    float v = 0.f;
+    ColInfo ci = find_col(st, c0 + c);
+    if (ci.in_col >= 0 && t >= 0 && t < T) {
+      if (!ci.dyn) {
+        v = inb[(int64_t)t * in_ts + ci.in_col];
+      } else {
+#pragma unroll 1
+        for (int w = 0; w < win.n; ++w) {
+          const int l = win.l[w], u = win.u[w];
+          const float* colp = inb + ci.in_col + w * ci.sd;
+          for (int k = -l; k <= u; ++k) {
+            int tt = t - k;
+            float cf = win.coef[w][k + l];
+            if (tt >= 0 && tt < T && cf != 0.f) v = fmaf(cf, colp[(int64_t)tt * in_ts], v);
+          }
+        }
+      }
+    }
+    bv[i] = v;
+  }
+  __syncthreads();
+  // Phase 2: FIR with the rows of P^-1.
+  const int cx = threadIdx.x & (TC - 1), rg = threadIdx.x / TC;
+  const int oc = c0 + cx;
+  ColInfo ci = find_col(st, oc);
+  if (ci.in_col < 0 || oc >= ncols) return;
+  float* outb = out + (int64_t)b * out_bs + oc;
+#pragma unroll 1
+  for (int pass = 0; pass < TT / 32; ++pass) {
+    const int r0 = rg * (TT / 4) + pass * 8;
+    if (t0 + r0 >= T) break;
+    if (!ci.dyn) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (t0 + r0 + i < T) outb[(int64_t)(t0 + r0 + i) * out_ts] = bv[(K_HALF + r0 + i) * TC + cx];
+      continue;
+    }
+    float w[8 + 2 * K_HALF], acc[8];
+#pragma unroll
+    for (int j = 0; j < 8 + 2 * K_HALF; ++j) w[j] = bv[(r0 + j) * TC + cx];
+    fir8(gs, r0, w, acc);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (t0 + r0 + i < T) outb[(int64_t)(t0 + r0 + i) * out_ts] = acc[i];
+  }
+}
+
+constexpr int ZROWS = TT + 2 * HALO;                  // 68 rows of z per block
+constexpr int GIN_ROWS = ZROWS + 2 * K_HALF;          // 116 rows of upstream gradient
+
+__global__ void __launch_bounds__(MLPG_THREADS)
+mlpg_bwd_kernel(const float* __restrict__ go, int64_t go_bs, int64_t go_ts,
+                float* __restrict__ gi, int64_t gi_bs, int64_t gi_ts,
+                const float* __restrict__ table, gantts_streams_t st, gantts_windows_t win,
+                int T, int ncols, int accumulate) {
+  extern __shared__ __align__(16) float smem[];
+  float* gv = smem;                                   // [GIN_ROWS][TC]   upstream gradient tile
+  float* gs = gv + GIN_ROWS * TC;                     // [ZROWS (pad 72)][GROW]
+  float* zs = gs + 72 * GROW;                         // [ZROWS (pad 72)][TC]
+  const int b = blockIdx.z, t0 = blockIdx.y * TT, c0 = blockIdx.x * TC;
+  const float* gob = go + (int64_t)b * go_bs;
+
+  for (int i = threadIdx.x; i < 72 * GROW; i += MLPG_THREADS) {
+    int r = i / GROW, j = i - r * GROW, t = t0 - HALO + r;
+    gs[i] = (t >= 0 && t < T && j < NTAPS && r < ZROWS) ? table[(int64_t)t * NTAPS + j] : 0.f;
+  }
+  for (int i = threadIdx.x; i < GIN_ROWS * TC; i += MLPG_THREADS) {
+    int r = i / TC, c = i - r * TC, t = t0 - HALO - K_HALF + r, oc = c0 + c;
+    float v = 0.f;
+    if (oc < ncols && t >= 0 && t < T) v = gob[(int64_t)t * go_ts + oc];
+    gv[i] = v;
+  }
+  __syncthreads();
+  // Phase 2: z = P^-1 g on rows [t0-HALO, t0+TT+HALO); rows outside [0,T) have all-zero taps.
+  {
+    const int cx = threadIdx.x & (TC - 1), rg = threadIdx.x / TC;
+#pragma unroll 1
+    for (int q = rg; q < 72 / 8; q += MLPG_THREADS / TC) {
+      const int r0 = q * 8;
+      float w[8 + 2 * K_HALF], acc[8];
+#pragma unroll
+      for (int j = 0; j < 8 + 2 * K_HALF; ++j) {
+        int rr = r0 + j;
+        w[j] = rr < GIN_ROWS ? gv[rr * TC + cx] : 0.f;
+      }
+      fir8(gs, r0, w, acc);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) zs[(r0 + i) * TC + cx] = acc[i];
+    }
+  }
+  __syncthreads();
+  // Phase 3: grad wrt window w of stream column = sum_k coef_w[k+l] z_{t+k}; static: copy g.
+  float* gib = gi + (int64_t)b * gi_bs;
+  const int nw = win.n;
+  for (int i = threadIdx.x; i < nw * TT * TC; i += MLPG_THREADS) {
+    int c = i % TC, r = (i / TC) % TT, w = i / (TC * TT);
+    int t = t0 + r, oc = c0 + c;
+    if (t >= T || oc >= ncols) continue;
+    ColInfo ci = find_col(st, oc);
+    if (ci.in_col < 0) continue;
+    float v;
+    if (!ci.dyn) {
+      if (w != 0) continue;
+      v = gv[(HALO + K_HALF + r) * TC + c];
+    } else {
+      const int l = win.l[w], u = win.u[w];
+      v = 0.f;
+      for (int k = -l; k <= u; ++k) v = fmaf(win.coef[w][k + l], zs[(HALO + r + k) * TC + c], v);
+    }
+    float* p = gib + (int64_t)t * gi_ts + ci.in_col + w * ci.sd;
+    *p = accumulate ? (*p + v) : v;
+  }
+}
+
+static int check_layout(const gantts_streams_t* st, const gantts_windows_t* win, int* ncols) {
+  GANTTS_CHECK_ARG(st && win, "mlpg: null stream/window table");
+  GANTTS_CHECK_ARG(st->n >= 1 && st->n <= GANTTS_MAX_STREAMS, "mlpg: bad stream count %d", st->n);
+  GANTTS_CHECK_ARG(win->n >= 1 && win->n <= GANTTS_MAX_WINDOWS, "mlpg: bad window count %d", win->n);
+  int nc = 0;
+  for (int s = 0; s < st->n; ++s) {
+    GANTTS_CHECK_ARG(st->sd[s] > 0 && st->in_start[s] >= 0 && st->out_start[s] >= 0,
+                     "mlpg: bad stream %d", s);
+    nc = st->out_start[s] + st->sd[s] > nc ? st->out_start[s] + st->sd[s] : nc;
+  }
+  for (int w = 0; w < win->n; ++w)
+    GANTTS_CHECK_ARG(win->l[w] >= 0 && win->l[w] <= HALO && win->u[w] >= 0 && win->u[w] <= HALO,
+                     "mlpg: window %d taps out of range (l,u <= %d)", w, HALO);
+  *ncols = nc;
+  return GANTTS_OK;
+}
+
+}  // namespace gantts
+
+using namespace gantts;
+
+extern "C" int gantts_mlpg_table(const gantts_windows_t* win, int T, float* table_host) {
+  GANTTS_CHECK_ARG(win && table_host && T >= 1, "mlpg_table: bad arguments");
+  GANTTS_CHECK_ARG(win->n >= 1 && win->n <= GANTTS_MAX_WINDOWS, "mlpg_table: bad window count");
+  int hb = 0;
+  for (int w = 0; w < win->n; ++w) {
+    GANTTS_CHECK_ARG(win->l[w] >= 0 && win->l[w] <= HALO && win->u[w] >= 0 && win->u[w] <= HALO,
+                     "mlpg_table: window %d taps out of range", w);
+    hb = win->l[w] + win->u[w] > hb ? win->l[w] + win->u[w] : hb;
+  }
+  // Lower band of P = sum_w W_w^T W_w:  band[d][j] = P[j+d][j], d = 0..hb.
+  std::vector<double> band((size_t)(hb + 1) * T, 0.0);
+  for (int w = 0; w < win->n; ++w) {
+    const int l = win->l[w], u = win->u[w];
+    for (int r = 0; r < T; ++r)
+      for (int k1 = -l; k1 <= u; ++k1)
+        for (int k2 = -l; k2 <= k1; ++k2) {          // column j = r+k2 <= i = r+k1
+          int i = r + k1, j = r + k2;
+          if (i < 0 || i >= T || j < 0 || j >= T) continue;
+          band[(size_t)(i - j) * T + j] += (double)win->coef[w][k1 + l] * (double)win->coef[w][k2 + l];
+        }
+  }
+  // Banded Cholesky P = L L^T, L stored in the same band layout.
+  std::vector<double>& L = band;
+  for (int j = 0; j < T; ++j) {
+    double d = L[j];
+    for (int k = 1; k <= hb && j - k >= 0; ++k) {
+      double v = L[(size_t)k * T + (j - k)];
+      d -= v * v;
+    }
+    if (!(d > 0.0)) {
+      set_error("mlpg_table: normal matrix not positive definite at row %d", j);
+      return GANTTS_E_UNSUPPORTED;
+    }
+    d = sqrt(d);
+    L[j] = d;
+    for (int i = j + 1; i <= j + hb && i < T; ++i) {
+      double s = L[(size_t)(i - j) * T + j];
+      for (int k = 1; k <= hb; ++k) {
+        int c = j - k;
+        if (c < 0 || i - c > hb) continue;
+        s -= L[(size_t)(i - c) * T + c] * L[(size_t)(j - c) * T + c];
+      }
+      L[(size_t)(i - j) * T + j] = s / d;
+    }
+  }
+  std::vector<double> x(T);
+  double worst_tail = 0.0;
+  for (int t = 0; t < T; ++t) {
+    // Solve P x = e_t restricted to where x can be non-negligible is not needed: full O(T*hb) solve.
+    for (int i = 0; i < T; ++i) x[i] = 0.0;
+    x[t] = 1.0;
+    for (int i = t; i < T; ++i) {                     // forward substitution (zeros before t)
+      double s = x[i];
+      for (int k = 1; k <= hb && i - k >= t; ++k) s -= L[(size_t)k * T + (i - k)] * x[i - k];
+      x[i] = s / L[i];
+    }
+    for (int i = T - 1; i >= 0; --i) {                // backward substitution
+      double s = x[i];
+      for (int k = 1; k <= hb && i + k < T; ++k) s -= L[(size_t)k * T + i] * x[i + k];
+      x[i] = s / L[i];
+    }
+    for (int j = 0; j < NTAPS; ++j) {
+      int c = t + j - K_HALF;
+      table_host[(size_t)t * NTAPS + j] = (c >= 0 && c < T) ? (float)x[c] : 0.f;
+    }
+    double tail = 0.0;
+    if (t - K_HALF - 1 >= 0) tail = fabs(x[t - K_HALF - 1]);
+    if (t + K_HALF + 1 < T && fabs(x[t + K_HALF + 1]) > tail) tail = fabs(x[t + K_HALF + 1]);
+    if (tail / x[t] > worst_tail) worst_tail = tail / x[t];
+  }
+  if (worst_tail > 1e-8) {
+    set_error("mlpg_table: P^-1 decays too slowly for these windows (%.3g at lag %d)", worst_tail,
+              K_HALF + 1);
+    return GANTTS_E_UNSUPPORTED;
+  }
+  return GANTTS_OK;
+}
+
+extern "C" int gantts_mlpg_fwd(const float* in, int64_t in_bs, int64_t in_ts, float* out,
+                               int64_t out_bs, int64_t out_ts, const float* table_dev,
+                               const gantts_streams_t* st, const gantts_windows_t* win, int B, int T,
+                               void* stream) {
+  int ncols = 0;
+  int rc = check_layout(st, win, &ncols);
+  if (rc) return rc;
+  GANTTS_CHECK_ARG(in && out && table_dev && B >= 1 && T >= 1, "mlpg_fwd: bad arguments");
+  const size_t smem = ((TT + 2 * K_HALF) * TC + TT * GROW) * sizeof(float);
+  static bool attr_done = false;
+  if (!attr_done) {
+    GANTTS_CUDA(cudaFuncSetAttribute(mlpg_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    attr_done = true;
+  }
+  dim3 grid((ncols + TC - 1) / TC, (T + TT - 1) / TT, B);
+  mlpg_fwd_kernel<<<grid, MLPG_THREADS, smem, as_stream(stream)>>>(in, in_bs, in_ts, out, out_bs, out_ts,
+                                                                  table_dev, *st, *win, T, ncols);
+  GANTTS_LAUNCH_CHECK("mlpg_fwd_kernel");
+  return GANTTS_OK;
+}
+
+extern "C" int gantts_mlpg_bwd(const float* go, int64_t go_bs, int64_t go_ts, float* gi,
+                               int64_t gi_bs, int64_t gi_ts, const float* table_dev,
+                               const gantts_streams_t* st, const gantts_windows_t* win, int B, int T,
+                               int accumulate, void* stream) {
+  int ncols = 0;
+  int rc = check_layout(st, win, &ncols);
+  if (rc) return rc;
+  GANTTS_CHECK_ARG(go && gi && table_dev && B >= 1 && T >= 1, "mlpg_bwd: bad arguments");
+  const size_t smem = (GIN_ROWS * TC + 72 * GROW + 72 * TC) * sizeof(float);
+  static bool attr_done = false;
+  if (!attr_done) {
+    GANTTS_CUDA(cudaFuncSetAttribute(mlpg_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    attr_done = true;
+  }
+  dim3 grid((ncols + TC - 1) / TC, (T + TT - 1) / TT, B);
+  mlpg_bwd_kernel<<<grid, MLPG_THREADS, smem, as_stream(stream)>>>(go, go_bs, go_ts, gi, gi_bs, gi_ts,
+                                                                  table_dev, *st, *win, T, ncols, accumulate);
+  GANTTS_LAUNCH_CHECK("mlpg_bwd_kernel");
+  return GANTTS_OK;
+}

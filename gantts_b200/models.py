@@ -1,0 +1,77 @@
+"""Drop-in for reference ``gantts/models.py``: same class names, constructor signatures, forward
+signatures and ``state_dict`` keys, with the arithmetic in hand-written sm_100a CUDA."""
+import torch
+from torch import nn
+
+from . import _lib
+from . import ops
+
+
+class AbstractModel(object):
+    """Interface for VC and TTS models (reference gantts/models.py:11-18)."""
+
+    def include_parameter_generation(self):
+        """Whether model includes parameter generation or not."""
+        return False
+
+
+def _hidden_stack(x, layers, p, training, engine=None):
+    for layer in layers:
+        x = ops.linear_act(x, layer.weight, layer.bias, _lib.ACT_LEAKY_DROPOUT, p=p, training=training,
+                           engine=engine)
+    return x
+
+
+class MLP(AbstractModel, nn.Module):
+    """Generator or discriminator MLP (reference gantts/models.py:121-141):
+    ``x = Dropout(LeakyReLU_0.01(Linear(x)))`` per hidden layer, ``last_linear``, optional sigmoid.
+    state_dict keys: ``layers.{i}.weight/bias``, ``last_linear.weight/bias``."""
+
+    def __init__(self, in_dim=118, out_dim=1, num_hidden=2, hidden_dim=256,
+                 dropout=0.5, last_sigmoid=True, bidirectional=None):
+        # bidirectional is dummy
+        super(MLP, self).__init__()
+        in_sizes = [in_dim] + [hidden_dim] * (num_hidden - 1)
+        out_sizes = [hidden_dim] * num_hidden
+        self.layers = nn.ModuleList(
+            [nn.Linear(in_size, out_size) for (in_size, out_size) in zip(in_sizes, out_sizes)])
+        self.last_linear = nn.Linear(hidden_dim, out_dim)
+        self.dropout_p = float(dropout)
+        self.last_sigmoid = last_sigmoid
+        self.engine = None          # None -> gantts_b200.config.engine
+
+    def forward(self, x, lengths=None):
+        x = _hidden_stack(x, self.layers, self.dropout_p, self.training, self.engine)
+        act = _lib.ACT_SIGMOID if self.last_sigmoid else _lib.ACT_NONE
+        return ops.linear_act(x, self.last_linear.weight, self.last_linear.bias, act, engine=self.engine)
+
+
+class In2OutHighwayNet(AbstractModel, nn.Module):
+    """Input-to-output highway network for VC (reference gantts/models.py:21-69): returns
+    ``(y_hat, x_static + sigmoid(T(x_static)) * MLPG(R, y_hat))``.
+    state_dict keys: ``T.*``, ``H.{i}.*``, ``last_linear.*``."""
+
+    def __init__(self, in_dim=118, out_dim=118, static_dim=118 // 2,
+                 num_hidden=3, hidden_dim=512, dropout=0.5):
+        super(In2OutHighwayNet, self).__init__()
+        self.static_dim = static_dim
+        self.T = nn.Linear(static_dim, static_dim)
+        in_sizes = [in_dim] + [hidden_dim] * (num_hidden - 1)
+        out_sizes = [hidden_dim] * num_hidden
+        self.H = nn.ModuleList(
+            [nn.Linear(in_size, out_size) for (in_size, out_size) in zip(in_sizes, out_sizes)])
+        self.last_linear = nn.Linear(hidden_dim, out_dim)
+        self.dropout_p = float(dropout)
+        self.engine = None
+
+    def include_parameter_generation(self):
+        return True
+
+    def forward(self, x, R, lengths=None):
+        x = x.unsqueeze(0) if x.dim() == 2 else x
+        x_static = x[:, :, :self.static_dim]
+        Tx = ops.linear_act(x_static, self.T.weight, self.T.bias, _lib.ACT_SIGMOID, engine=self.engine)
+        h = _hidden_stack(x, self.H, self.dropout_p, self.training, self.engine)
+        h = ops.linear_act(h, self.last_linear.weight, self.last_linear.bias, _lib.ACT_NONE, engine=self.engine)
+        Gx = ops.unit_variance_mlpg(R, h)
+        return h, ops.highway_combine(x_static, Tx, Gx)

@@ -1,0 +1,392 @@
+"""torch.autograd bindings of the C-ABI ops.  Every op requires CUDA float32 tensors; there is no
+CPU path (the product must fail loudly rather than fall back)."""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import config
+
+LEAKY_SLOPE = 0.01          # nn.LeakyReLU() default used by the reference (gantts/models.py:37,132)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("gantts_b200: CUDA tensor required (got a %s tensor); this package has "
+                               "no CPU fallback" % t.device.type)
+        if t.dtype != torch.float32:
+            raise RuntimeError("gantts_b200: float32 tensor required (got %s)" % t.dtype)
+
+
+def _rows2d(x):
+    """View (…, D) as (rows, D) with unit column stride; returns (tensor2d, row_stride)."""
+    D = x.shape[-1]
+    x2 = x.reshape(-1, D)
+    if x2.stride(1) != 1 or (x2.shape[0] > 1 and x2.stride(0) < D):
+        x2 = x2.contiguous()
+    return x2, (x2.stride(0) if x2.shape[0] > 1 else D)
+
+
+_ws_cache = {}
+
+
+def workspace(nbytes, device, tag="ws"):
+    """Cached per-(device, tag) scratch buffer, grown geometrically (stream-ordered reuse on the
+    current stream only)."""
+    key = (device.index, tag)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes * 1.25), 1 << 20), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+# ------------------------------------------------------------------------------------- MLPG
+STANDARD_WINDOWS = {
+    1: [(0, 0, (1.0,))],
+    2: [(0, 0, (1.0,)), (1, 1, (-0.5, 0.0, 0.5))],
+    3: [(0, 0, (1.0,)), (1, 1, (-0.5, 0.0, 0.5)), (1, 1, (1.0, -2.0, 1.0))],
+}
+_registered_windows = {}
+_table_cache = {}
+_validated_R = set()
+
+
+def windows_key(windows):
+    return tuple((int(l), int(u), tuple(float(c) for c in coef)) for l, u, coef in windows)
+
+
+def register_windows(windows):
+    """Declare the delta windows behind the R matrices of a given window count (the defaults are
+    the reference's hparams windows, hparams.py:22-26,183-187)."""
+    _registered_windows[len(windows)] = windows_key(windows)
+
+
+def windows_for(num_windows):
+    w = _registered_windows.get(num_windows)
+    if w is None:
+        if num_windows not in STANDARD_WINDOWS:
+            raise RuntimeError("gantts_b200: no windows registered for num_windows=%d" % num_windows)
+        w = windows_key(STANDARD_WINDOWS[num_windows])
+    return w
+
+
+def mlpg_table_host(windows, T):
+    """Rows of P^-1 within +-24 taps, float32 (T, 49); host computation inside the C library."""
+    lib = _lib.load()
+    w = _lib.make_windows(windows)
+    tab = np.zeros((int(T), _lib.MLPG_NTAPS), dtype=np.float32)
+    _lib.check(lib.gantts_mlpg_table(ctypes.byref(w), int(T), tab.ctypes.data))
+    return tab
+
+
+def mlpg_table(windows, T, device):
+    key = (windows_key(windows), int(T), device.index)
+    t = _table_cache.get(key)
+    if t is None:
+        t = torch.from_numpy(mlpg_table_host(windows, T)).to(device)
+        _table_cache[key] = t
+    return t
+
+
+def _validate_R(R, windows, T):
+    """One-time check per (num_windows, T) that a dense R handed in by the caller really is
+    (W^T W)^-1 W^T for the registered windows (the kernels never read R on the hot path)."""
+    key = (windows, int(T))
+    if key in _validated_R:
+        return
+    tab = mlpg_table_host(windows, T)
+    t = int(T) // 2
+    row = R[t].detach().float().cpu().numpy()
+    K = _lib.MLPG_HALF_TAPS
+    worst = 0.0
+    for w, (l, u, coef) in enumerate(windows):
+        for r in range(max(0, t - K + 2), min(int(T), t + K - 1)):
+            exp = 0.0
+            for k in range(-l, u + 1):
+                c = r + k
+                j = c - t + K
+                if 0 <= c < T and 0 <= j < _lib.MLPG_NTAPS:
+                    exp += tab[t, j] * coef[k + l]
+            worst = max(worst, abs(exp - row[w * int(T) + r]))
+    if worst > 1e-4:
+        raise RuntimeError("gantts_b200: the R matrix does not match the registered delta windows "
+                           "(max deviation %.3g); call gantts_b200.ops.register_windows(...)" % worst)
+    _validated_R.add(key)
+
+
+def windows_from_R(R):
+    """(windows, T) for a dense MLPG matrix R of shape (T, num_windows*T) (reference train.py:511)."""
+    T = int(R.shape[0])
+    nw = int(R.shape[1]) // T
+    if nw * T != int(R.shape[1]):
+        raise RuntimeError("gantts_b200: R must have shape (T, num_windows*T)")
+    windows = windows_for(nw)
+    _validate_R(R, windows, T)
+    return windows, T
+
+
+class _MLPG(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, table, streams, windows, ncols_out):
+        require_cuda(x, table)
+        lib = _lib.load()
+        B, T, D = x.shape
+        if x.stride(2) != 1:
+            x = x.contiguous()
+        out = torch.empty(B, T, ncols_out, dtype=torch.float32, device=x.device)
+        _lib.check(lib.gantts_mlpg_fwd(x.data_ptr(), x.stride(0), x.stride(1), out.data_ptr(),
+                                       out.stride(0), out.stride(1), table.data_ptr(),
+                                       ctypes.byref(streams), ctypes.byref(windows), B, T, _stream()))
+        ctx.table, ctx.streams, ctx.windows = table, streams, windows
+        ctx.in_shape = (B, T, D)
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        require_cuda(go)
+        lib = _lib.load()
+        B, T, D = ctx.in_shape
+        if go.stride(2) != 1:
+            go = go.contiguous()
+        gi = torch.zeros(B, T, D, dtype=torch.float32, device=go.device)
+        _lib.check(lib.gantts_mlpg_bwd(go.data_ptr(), go.stride(0), go.stride(1), gi.data_ptr(),
+                                       gi.stride(0), gi.stride(1), ctx.table.data_ptr(),
+                                       ctypes.byref(ctx.streams), ctypes.byref(ctx.windows), B, T, 0,
+                                       _stream()))
+        return gi, None, None, None, None
+
+
+def mlpg(x, windows, stream_entries, ncols_out):
+    """x: (B, T, D) CUDA float32.  stream_entries: [(in_start, sd, dyn, out_start)]."""
+    squeeze = x.dim() == 2
+    if squeeze:
+        x = x.unsqueeze(0)
+    table = mlpg_table(windows, x.shape[1], x.device)
+    out = _MLPG.apply(x, table, _lib.make_streams(stream_entries), _lib.make_windows(windows), ncols_out)
+    return out.squeeze(0) if squeeze else out
+
+
+def unit_variance_mlpg(R, means):
+    """Drop-in for nnmnkwii.autograd.unit_variance_mlpg(R, means) (reference
+    gantts/multistream.py:120, gantts/models.py:66,115): means (B, T, nw*sd) or (T, nw*sd)."""
+    windows, T = windows_from_R(R)
+    if means.shape[-2] != T:
+        raise RuntimeError("gantts_b200: means has %d frames but R was built for T=%d" % (means.shape[-2], T))
+    nw = len(windows)
+    D = means.shape[-1]
+    if D % nw:
+        raise RuntimeError("gantts_b200: feature dim %d not divisible by num_windows %d" % (D, nw))
+    sd = D // nw
+    return mlpg(means, windows, [(0, sd, True, 0)], sd)
+
+
+# ---------------------------------------------------------------------------- column gather
+_cols_cache = {}
+
+
+def _cols_tensor(cols, device):
+    key = (tuple(cols), device.index)
+    t = _cols_cache.get(key)
+    if t is None:
+        t = torch.tensor(list(cols), dtype=torch.int32, device=device)
+        _cols_cache[key] = t
+    return t
+
+
+class _GatherCols(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, cols):
+        require_cuda(x)
+        lib = _lib.load()
+        x2, rs = _rows2d(x)
+        rows = x2.shape[0]
+        out = torch.empty(x.shape[:-1] + (len(cols),), dtype=torch.float32, device=x.device)
+        ct = _cols_tensor(cols, x.device)
+        _lib.check(lib.gantts_gather_cols(x2.data_ptr(), rs, out.data_ptr(), len(cols), ct.data_ptr(),
+                                          len(cols), rows, _stream()))
+        ctx.cols, ctx.in_shape = cols, tuple(x.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        lib = _lib.load()
+        go = go.contiguous()
+        gi = torch.zeros(ctx.in_shape, dtype=torch.float32, device=go.device)
+        rows = gi.numel() // ctx.in_shape[-1]
+        ct = _cols_tensor(ctx.cols, go.device)
+        _lib.check(lib.gantts_scatter_cols_add(go.data_ptr(), len(ctx.cols), gi.data_ptr(),
+                                               ctx.in_shape[-1], ct.data_ptr(), len(ctx.cols), rows,
+                                               _stream()))
+        return gi, None
+
+
+def gather_cols(x, cols):
+    cols = tuple(int(c) for c in cols)
+    if len(cols) == 0:
+        raise RuntimeError("gantts_b200: empty column selection")
+    return _GatherCols.apply(x, cols)
+
+
+# ------------------------------------------------------------------------------ masks/losses
+def sequence_mask(lengths, max_len):
+    lib = _lib.load()
+    if not lengths.is_cuda:
+        raise RuntimeError("gantts_b200: CUDA lengths tensor required; this package has no CPU fallback")
+    lengths = lengths.long().contiguous().view(-1)
+    B = lengths.numel()
+    mask = torch.empty(B, int(max_len), dtype=torch.float32, device=lengths.device)
+    _lib.check(lib.gantts_sequence_mask(lengths.data_ptr(), mask.data_ptr(), B, int(max_len), _stream()))
+    return mask
+
+
+class _MaskedSSE(torch.autograd.Function):
+    """sums = [sum(((a-b)*m)^2), sum(m)]"""
+
+    @staticmethod
+    def forward(ctx, a, b, mask):
+        require_cuda(a, b, mask)
+        lib = _lib.load()
+        a2, ars = _rows2d(a)
+        b2, brs = _rows2d(b)
+        m = mask.reshape(-1).contiguous()
+        rows, D = a2.shape
+        if m.numel() != rows or b2.shape != a2.shape:
+            raise RuntimeError("gantts_b200: masked MSE shape mismatch")
+        sums = torch.empty(2, dtype=torch.float32, device=a.device)
+        nb = lib.gantts_masked_sse_workspace_bytes()
+        ws = workspace(nb, a.device, "red")
+        _lib.check(lib.gantts_masked_sse_fwd(a2.data_ptr(), ars, b2.data_ptr(), brs, m.data_ptr(), rows, D,
+                                             sums.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+        ctx.save_for_backward(a2, b2, m)
+        ctx.strides = (ars, brs)
+        ctx.shape = tuple(a.shape)
+        return sums
+
+    @staticmethod
+    def backward(ctx, gsums):
+        lib = _lib.load()
+        a2, b2, m = ctx.saved_tensors
+        rows, D = a2.shape
+        scale = gsums[0:1].contiguous()
+        ga = torch.empty(rows, D, dtype=torch.float32, device=a2.device)
+        _lib.check(lib.gantts_masked_sse_bwd(a2.data_ptr(), ctx.strides[0], b2.data_ptr(), ctx.strides[1],
+                                             m.data_ptr(), rows, D, scale.data_ptr(), ga.data_ptr(), D, 0,
+                                             _stream()))
+        return ga.view(ctx.shape), None, None
+
+
+def masked_mse(inp, target, mask):
+    """reference gantts/seqloss.py:41-43: sum((in*m - tgt*m)^2) / sum(m), m of shape (B, T, 1)."""
+    sums = _MaskedSSE.apply(inp, target, mask)
+    return sums[0] / sums[1]
+
+
+class _MaskedBCE(torch.autograd.Function):
+    """out = [-(log(arg) * m).sum(), count, sum(m)], arg = D+1e-20 (kind 0) or 1-D+1e-20 (kind 1)."""
+
+    @staticmethod
+    def forward(ctx, D, mask, kind):
+        require_cuda(D, mask)
+        lib = _lib.load()
+        d = D.reshape(-1).contiguous()
+        m = mask.reshape(-1).contiguous()
+        if d.numel() != m.numel():
+            raise RuntimeError("gantts_b200: masked BCE shape mismatch")
+        out = torch.empty(3, dtype=torch.float32, device=D.device)
+        ws = workspace(lib.gantts_masked_sse_workspace_bytes(), D.device, "red")
+        _lib.check(lib.gantts_masked_bce_fwd(d.data_ptr(), m.data_ptr(), d.numel(), int(kind), out.data_ptr(),
+                                             ws.data_ptr(), ws.numel(), _stream()))
+        ctx.save_for_backward(d, m)
+        ctx.kind, ctx.shape = int(kind), tuple(D.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        lib = _lib.load()
+        d, m = ctx.saved_tensors
+        scale = gout[0:1].contiguous()
+        gD = torch.empty_like(d)
+        _lib.check(lib.gantts_masked_bce_bwd(d.data_ptr(), m.data_ptr(), d.numel(), ctx.kind, scale.data_ptr(),
+                                             gD.data_ptr(), _stream()))
+        return gD.view(ctx.shape), None, None
+
+
+def masked_bce(D, mask, kind):
+    """Un-normalised adversarial BCE sum, correct-count and sum(mask) (reference train.py:258-271)."""
+    return _MaskedBCE.apply(D, mask, kind)
+
+
+# --------------------------------------------------------------------------- fused linear
+class _LinearAct(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, W, b, act, slope, p, seed, engine):
+        require_cuda(x, W, b)
+        lib = _lib.load()
+        x2, xrs = _rows2d(x)
+        M, K = x2.shape
+        N = W.shape[0]
+        if W.shape[1] != K:
+            raise RuntimeError("gantts_b200: linear shape mismatch (x has %d features, W expects %d)" % (K, W.shape[1]))
+        Wc = W.contiguous()
+        bc = b.contiguous() if b is not None else None
+        y = torch.empty(M, N, dtype=torch.float32, device=x.device)
+        nb = lib.gantts_linear_workspace_bytes(M, N, K, engine)
+        ws = workspace(nb, x.device)
+        _lib.check(lib.gantts_linear_fwd(x2.data_ptr(), xrs, Wc.data_ptr(), bc.data_ptr() if bc is not None else None,
+                                         y.data_ptr(), N, M, N, K, act, slope, p, seed, engine,
+                                         ws.data_ptr(), ws.numel(), _stream()))
+        ctx.save_for_backward(x2, Wc, y)
+        ctx.cfg = (xrs, act, slope, p, engine, b is not None, tuple(x.shape))
+        return y.view(x.shape[:-1] + (N,))
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = _lib.load()
+        x2, W, y = ctx.saved_tensors
+        xrs, act, slope, p, engine, has_bias, xshape = ctx.cfg
+        M, K = x2.shape
+        N = W.shape[0]
+        gy2, gyrs = _rows2d(gy)
+        need_gx, need_gW, need_gb = ctx.needs_input_grad[0], ctx.needs_input_grad[1], (has_bias and ctx.needs_input_grad[2])
+        gz = torch.empty(M, N, dtype=torch.float32, device=gy.device)
+        gx = torch.empty(M, K, dtype=torch.float32, device=gy.device) if need_gx else None
+        gW = torch.empty(N, K, dtype=torch.float32, device=gy.device) if need_gW else None
+        gb = torch.empty(N, dtype=torch.float32, device=gy.device) if need_gb else None
+        nb = lib.gantts_linear_workspace_bytes(M, N, K, engine)
+        ws = workspace(nb, gy.device)
+        _lib.check(lib.gantts_linear_bwd(gy2.data_ptr(), gyrs, y.data_ptr(), N, x2.data_ptr(), xrs, W.data_ptr(),
+                                         gz.data_ptr(), gx.data_ptr() if gx is not None else None, K,
+                                         gW.data_ptr() if gW is not None else None,
+                                         gb.data_ptr() if gb is not None else None,
+                                         M, N, K, act, slope, p, 0, engine, ws.data_ptr(), ws.numel(), _stream()))
+        return (gx.view(xshape) if gx is not None else None), gW, gb, None, None, None, None, None
+
+
+def draw_seed():
+    """64-bit dropout seed from torch's CPU generator (reproducible under torch.manual_seed)."""
+    return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+
+
+def linear_act(x, W, b, act=_lib.ACT_NONE, p=0.0, training=False, slope=LEAKY_SLOPE, engine=None, seed=None):
+    """act(x W^T + b): the reference's Linear -> LeakyReLU(0.01) -> Dropout(p) hidden layer
+    (gantts/models.py:137-139), ``last_linear`` (act NONE) or Linear -> Sigmoid."""
+    eng = config.engine_id(engine)
+    p_eff = float(p) if (training and act == _lib.ACT_LEAKY_DROPOUT) else 0.0
+    if p_eff > 0.0 and seed is None:
+        seed = draw_seed()
+    return _LinearAct.apply(x, W, b, int(act), float(slope), p_eff, int(seed or 0), eng)
+
+
+def highway_combine(x_static, Tx, Gx):
+    """y = x_static + Tx * Gx (reference gantts/models.py:69)."""
+    require_cuda(x_static, Tx, Gx)
+    return torch.addcmul(x_static, Tx, Gx)

@@ -1,0 +1,197 @@
+/*
+ * gantts_b200.h -- C ABI of libgantts_b200.so: the B200 (sm_100a) GAN-step hot path of r9y9/gantts.
+ *
+ * Every entry point takes plain device/host pointers and sizes; no torch types.  All work is
+ * enqueued on the caller's `stream` (a cudaStream_t passed as void*), nothing synchronises
+ * internally unless stated.  Return value: 0 on success, otherwise a GANTTS_E_* code; the message
+ * for the calling thread's last failure is available from gantts_last_error_string().  The library
+ * owns no device memory: every buffer, including workspaces, is the caller's.
+ *
+ * Each declaration cites the reference interface (r9y9/gantts @ fb1e75f, file:line) it replaces.
+ * The reference-side binding is shown in INTEGRATION.md (ctypes, since the reference is Python).
+ */
+#ifndef GANTTS_B200_H_
+#define GANTTS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GANTTS_OK 0
+#define GANTTS_E_BADARG 1   /* shape / pointer / enum out of contract */
+#define GANTTS_E_CUDA 2     /* a CUDA runtime or driver call failed */
+#define GANTTS_E_UNSUPPORTED 3
+#define GANTTS_E_WORKSPACE 4 /* caller workspace too small */
+
+#define GANTTS_MAX_STREAMS 8
+#define GANTTS_MAX_WINDOWS 4
+#define GANTTS_MAX_WINDOW_TAPS 5 /* l, u <= 2 */
+#define GANTTS_MLPG_HALF_TAPS 24 /* FIR half width K: P^-1 decays to 2.6e-10 at lag 24 */
+#define GANTTS_MAX_LAYERS 8
+
+int gantts_version(void);                       /* 100 * major + minor */
+const char* gantts_last_error_string(void);     /* thread-local, never NULL */
+/* 1 when the current device is compute capability 10.x (the kernels are sm_100a only). */
+int gantts_device_supported(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Feature-stream layout (reference hparams.py:196-206: stream_sizes / has_dynamic_features).
+ * Stream s occupies input columns [in_start, in_start + width) laid out window-major
+ * [static sd | delta sd | delta-delta sd] when dyn != 0 (width = num_windows * sd), or sd plain
+ * columns when dyn == 0; its static part lands in output columns [out_start, out_start + sd).
+ * Disabled streams are simply left out of the table.
+ */
+typedef struct {
+  int n;
+  int in_start[GANTTS_MAX_STREAMS];
+  int sd[GANTTS_MAX_STREAMS];
+  int dyn[GANTTS_MAX_STREAMS];
+  int out_start[GANTTS_MAX_STREAMS];
+} gantts_streams_t;
+
+/* Delta windows (reference hparams.py:22-26,183-187): window w has taps coef[w][0..l+u]. */
+typedef struct {
+  int n;
+  int l[GANTTS_MAX_WINDOWS];
+  int u[GANTTS_MAX_WINDOWS];
+  float coef[GANTTS_MAX_WINDOWS][GANTTS_MAX_WINDOW_TAPS];
+} gantts_windows_t;
+
+/* ---------------------------------------------------------------------------------------------
+ * MLPG (replaces nnmnkwii.paramgen.unit_variance_mlpg_matrix + nnmnkwii.autograd.unit_variance_mlpg
+ * as called at reference train.py:510-513, gantts/multistream.py:82-123, gantts/models.py:66,115).
+ *
+ * The reference multiplies by the dense (T x nw*T) matrix R = (W^T W)^-1 W^T.  Here
+ *   y = P^-1 (sum_w W_w^T mu_w),  P = sum_w W_w^T W_w (banded SPD),
+ * is evaluated as a 3-tap stencil followed by a (2K+1)-tap row-variant FIR with the rows of P^-1
+ * (K = GANTTS_MLPG_HALF_TAPS), over the PADDED length T for every batch row, exactly like the
+ * reference (SURVEY.md 8a note iv).
+ *
+ * gantts_mlpg_table: HOST function.  Fills table_host[T * (2K+1)] with
+ *   table[t][j] = (P^-1)[t, t + j - K]   (0 outside [0,T)), computed in float64 by banded Cholesky,
+ * stored as float32.  The caller uploads it once per (windows, T) and passes the device copy below.
+ * Returns GANTTS_E_UNSUPPORTED when P^-1 has not decayed below 1e-8 of its diagonal at lag K.
+ */
+int gantts_mlpg_table(const gantts_windows_t* windows, int T, float* table_host);
+
+/* out[b,t,out_col] = MLPG(in[b,:,stream cols]) for dynamic streams, copy for static ones.
+ * in:  float32 [B][T][*] with element strides (in_bstride, in_tstride), unit column stride.
+ * out: float32 [B][T][*] with element strides (out_bstride, out_tstride). */
+int gantts_mlpg_fwd(const float* in, int64_t in_bstride, int64_t in_tstride,
+                    float* out, int64_t out_bstride, int64_t out_tstride,
+                    const float* table_dev, const gantts_streams_t* streams,
+                    const gantts_windows_t* windows, int B, int T, void* stream);
+
+/* grad_in[b,t,stream cols] (+)= W_w P^-1 grad_out (backward of the above; reference backward is
+ * R^T g).  Columns of grad_in belonging to no listed stream are NOT written.  accumulate != 0
+ * adds into grad_in instead of overwriting. */
+int gantts_mlpg_bwd(const float* grad_out, int64_t go_bstride, int64_t go_tstride,
+                    float* grad_in, int64_t gi_bstride, int64_t gi_tstride,
+                    const float* table_dev, const gantts_streams_t* streams,
+                    const gantts_windows_t* windows, int B, int T, int accumulate, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stream column gathers (reference gantts/multistream.py:33-43 select_streams, :56-79
+ * get_static_features, train.py:232-242 get_selected_static_stream).  Pure copies => bit-exact.
+ * out[r, j] = in[r, cols[j]] for r < rows.  cols_dev: int32[ncols] on the device.
+ */
+int gantts_gather_cols(const float* in, int64_t in_rstride, float* out, int64_t out_rstride,
+                       const int32_t* cols_dev, int ncols, int64_t rows, void* stream);
+/* Scatter-add of the backward: gin[r, cols[j]] += gout[r, j]. */
+int gantts_scatter_cols_add(const float* gout, int64_t go_rstride, float* gin, int64_t gi_rstride,
+                            const int32_t* cols_dev, int ncols, int64_t rows, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Sequence mask + masked MSE (reference gantts/seqloss.py:9-20 sequence_mask, :27-43
+ * MaskedMSELoss.forward).
+ */
+/* mask[b,t] = (t < lengths[b]) ? 1.f : 0.f ; lengths_dev int64[B]. */
+int gantts_sequence_mask(const int64_t* lengths_dev, float* mask, int B, int T, void* stream);
+
+/* sums_dev[0] = sum_{b,t,d} ((a - b) * m[b,t])^2 ; sums_dev[1] = sum_{b,t} m[b,t].
+ * a, b: float32 [rows][D] with row strides; mask: float32[rows].  Deterministic two-pass reduction;
+ * workspace must hold gantts_masked_sse_workspace_bytes() bytes. The loss is sums[0] / sums[1]. */
+size_t gantts_masked_sse_workspace_bytes(void);
+int gantts_masked_sse_fwd(const float* a, int64_t a_rstride, const float* b, int64_t b_rstride,
+                          const float* mask, int64_t rows, int D, float* sums_dev,
+                          void* workspace, size_t workspace_bytes, void* stream);
+/* grad_a[r,d] (+)= scale_dev[0] * 2 * (a - b) * m^2 ; scale is read on the device
+ * (= upstream_grad / sum(mask)), so no host sync is needed. */
+int gantts_masked_sse_bwd(const float* a, int64_t a_rstride, const float* b, int64_t b_rstride,
+                          const float* mask, int64_t rows, int D, const float* scale_dev,
+                          float* grad_a, int64_t ga_rstride, int accumulate, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Masked adversarial BCE terms (written inline in reference train.py:258-271,286,307-310):
+ *   kind 0 ("real"/"adv"):  -(log(D + 1e-20) * m).sum()      count: sum((D > 0.5) * m)
+ *   kind 1 ("fake"):        -(log(1 - D + 1e-20) * m).sum()   count: sum((D < 0.5) * m)
+ * D: float32[rows] discriminator outputs (after sigmoid).  out_dev[0] = un-normalised loss sum,
+ * out_dev[1] = count, out_dev[2] = sum(mask).  Same workspace contract as masked_sse.
+ */
+int gantts_masked_bce_fwd(const float* D, const float* mask, int64_t rows, int kind,
+                          float* out_dev, void* workspace, size_t workspace_bytes, void* stream);
+/* grad_D[r] = scale_dev[0] * d/dD of the un-normalised sum above. */
+int gantts_masked_bce_bwd(const float* D, const float* mask, int64_t rows, int kind,
+                          const float* scale_dev, float* grad_D, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused Linear -> LeakyReLU(0.01) -> Dropout layer (reference gantts/models.py:137-141 MLP.forward,
+ * :63-65 In2OutHighwayNet.forward; NOTE the reference order is Linear -> LeakyReLU -> Dropout).
+ *
+ * act: 0 = none (last_linear), 1 = LeakyReLU(slope) then dropout(p), 2 = sigmoid.
+ * Dropout keeps an element with probability 1-p and scales it by 1/(1-p); the keep decision is a
+ * counter-based hash of (seed, row * N + col), so no mask is stored: the backward recovers
+ * "dropped" / "negative" from the saved OUTPUT y (y == 0 <=> dropped, sign(y) = sign(pre-act)).
+ *
+ * engine: GANTTS_ENGINE_SIMT  = exact fp32 FFMA tiles (validation / odd shapes),
+ *         GANTTS_ENGINE_TC    = tcgen05 tensor cores, bf16x3 split operands with fp32 accumulation
+ *                               in TMEM (a_hi*b_hi + a_hi*b_lo + a_lo*b_hi, ~2^-16 per product).
+ */
+#define GANTTS_ENGINE_SIMT 0
+#define GANTTS_ENGINE_TC 1
+#define GANTTS_ACT_NONE 0
+#define GANTTS_ACT_LEAKY_DROPOUT 1
+#define GANTTS_ACT_SIGMOID 2
+
+/* y[M][N] = act(x[M][K] W[N][K]^T + bias[N]); x, y row-major with row strides; W row-major [N][K]
+ * (the nn.Linear state_dict layout). */
+int gantts_linear_fwd(const float* x, int64_t x_rstride, const float* W, const float* bias,
+                      float* y, int64_t y_rstride, int64_t M, int N, int K, int act, float slope,
+                      float p, uint64_t seed, int engine, void* workspace, size_t workspace_bytes,
+                      void* stream);
+size_t gantts_linear_workspace_bytes(int64_t M, int N, int K, int engine);
+
+/* Backward of the fused layer.  gy: upstream gradient w.r.t. the layer OUTPUT y [M][N].
+ * Computes gz = gy * act'(y) (in place into gz_scratch [M][N], may alias gy when gy is dead),
+ *   gx[M][K]  (=) gz W          (skipped when gx == NULL),
+ *   gW[N][K] (+)= gz^T x,  gb[N] (+)= column sums of gz   (accumulate != 0 adds; skipped if NULL).
+ */
+int gantts_linear_bwd(const float* gy, int64_t gy_rstride, const float* y, int64_t y_rstride,
+                      const float* x, int64_t x_rstride, const float* W,
+                      float* gz_scratch, float* gx, int64_t gx_rstride, float* gW, float* gb,
+                      int64_t M, int N, int K, int act, float slope, float p, int accumulate,
+                      int engine, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Gradient clipping + Adagrad (torch.nn.utils.clip_grad_norm_ + torch.optim.Adagrad as used at
+ * reference train.py:275-276,317-318 with hparams.py:223-227,240-244).  Operates on a list of
+ * parameter tensors given as device pointer arrays.
+ */
+/* Tensor lists are HOST arrays of device pointers (at most 32 tensors); sizes are element counts.
+ * sumsq_dev[0] = sum over all tensors of g^2 (deterministic two-stage reduction). */
+size_t gantts_optim_workspace_bytes(void);
+int gantts_grad_sumsq(float* const* grads, const int64_t* sizes_host, int ntensors, float* sumsq_dev,
+                      void* workspace, size_t workspace_bytes, void* stream);
+/* coef = min(1, max_norm / (sqrt(sumsq) + 1e-6)); g *= coef (in place, like clip_grad_norm_);
+ * g' = g + wd * p; s += g'*g'; p -= lr * g' / (sqrt(s) + eps).  sumsq_dev is read on the device. */
+int gantts_clip_adagrad_step(float* const* params, float* const* grads, float* const* state_sums,
+                             const int64_t* sizes_host, int ntensors, const float* sumsq_dev,
+                             float max_norm, float lr, float weight_decay, float eps, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GANTTS_B200_H_ */
