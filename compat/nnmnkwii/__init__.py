@@ -1,0 +1,2 @@
+"""Shim of the nnmnkwii symbols the reference imports (see compat/README.md)."""
+from . import paramgen, autograd, preprocessing  # noqa: F401

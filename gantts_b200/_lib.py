@@ -47,6 +47,9 @@ SIGNATURES = {
     "gantts_version": (_i, []),
     "gantts_last_error_string": (ctypes.c_char_p, []),
     "gantts_device_supported": (_i, []),
+    "gantts_launch_count": (ctypes.c_longlong, []),
+    "gantts_profile_enable": (_i, [_i]),
+    "gantts_profile_collect": (_i, [_vp, _vp, _vp]),
     "gantts_mlpg_table": (_i, [ctypes.POINTER(WindowsT), _i, _vp]),
     "gantts_mlpg_fwd": (_i, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, ctypes.POINTER(StreamsT),
                              ctypes.POINTER(WindowsT), _i, _i, _vp]),

@@ -393,7 +393,9 @@ static int launch_gemm_kk(const Planes& A, const Planes& B, float* C, int64_t ld
   }
   int total = p.num_a * p.num_b;
   int grid = total < num_sms() ? total : num_sms();
+  prof_begin(PROF_GEMM_KK, 2.0 * (double)p.rows_a * p.cols_b * (double)p.red, st);
   gemm_bf16x3_kernel<false><<<grid, TC_THREADS, smem, st>>>(mAh, mAl, mBh, mBl, p);
+  prof_end(st);
   GANTTS_LAUNCH_CHECK("gemm_bf16x3_kernel<K-major>");
   return GANTTS_OK;
 }
@@ -457,7 +459,9 @@ static int launch_gemm_mn(const Planes& A, const Planes& B, float* C, int accumu
   }
   int total = p.num_a * p.num_b * p.num_z;
   int grid = total < num_sms() ? total : num_sms();
+  prof_begin(PROF_GEMM_MN, 2.0 * (double)p.rows_a * p.cols_b * (double)p.red, st);
   gemm_bf16x3_kernel<true><<<grid, TC_THREADS, smem, st>>>(mAh, mAl, mBh, mBl, p);
+  prof_end(st);
   GANTTS_LAUNCH_CHECK("gemm_bf16x3_kernel<MN-major>");
   if (!direct) {
     int64_t n = (int64_t)p.rows_a * p.cols_b;

@@ -311,8 +311,14 @@ extern "C" int gantts_mlpg_fwd(const float* in, int64_t in_bs, int64_t in_ts, fl
     attr_done = true;
   }
   dim3 grid((ncols + TC - 1) / TC, (T + TT - 1) / TT, B);
+  {
+    int in_cols = 0;
+    for (int s = 0; s < st->n; ++s) in_cols += st->sd[s] * (st->dyn[s] ? win->n : 1);
+    prof_begin(PROF_MLPG_FWD, 4.0 * (double)B * T * (in_cols + ncols), as_stream(stream));
+  }
   mlpg_fwd_kernel<<<grid, MLPG_THREADS, smem, as_stream(stream)>>>(in, in_bs, in_ts, out, out_bs, out_ts,
                                                                   table_dev, *st, *win, T, ncols);
+  prof_end(as_stream(stream));
   GANTTS_LAUNCH_CHECK("mlpg_fwd_kernel");
   return GANTTS_OK;
 }
@@ -332,8 +338,14 @@ extern "C" int gantts_mlpg_bwd(const float* go, int64_t go_bs, int64_t go_ts, fl
     attr_done = true;
   }
   dim3 grid((ncols + TC - 1) / TC, (T + TT - 1) / TT, B);
+  {
+    int in_cols = 0;
+    for (int s = 0; s < st->n; ++s) in_cols += st->sd[s] * (st->dyn[s] ? win->n : 1);
+    prof_begin(PROF_MLPG_BWD, 4.0 * (double)B * T * (in_cols + ncols), as_stream(stream));
+  }
   mlpg_bwd_kernel<<<grid, MLPG_THREADS, smem, as_stream(stream)>>>(go, go_bs, go_ts, gi, gi_bs, gi_ts,
                                                                   table_dev, *st, *win, T, ncols, accumulate);
+  prof_end(as_stream(stream));
   GANTTS_LAUNCH_CHECK("mlpg_bwd_kernel");
   return GANTTS_OK;
 }

@@ -36,6 +36,14 @@ int gantts_version(void);                       /* 100 * major + minor */
 const char* gantts_last_error_string(void);     /* thread-local, never NULL */
 /* 1 when the current device is compute capability 10.x (the kernels are sm_100a only). */
 int gantts_device_supported(void);
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
+long long gantts_launch_count(void);
+/* Measurement hooks: when enabled, the tensor-core GEMM and MLPG launches are bracketed by CUDA
+ * events on the launching stream.  gantts_profile_collect synchronises those events and ADDS, per
+ * kind (0 = GEMM K-major, 1 = GEMM MN-major, 2 = MLPG fwd, 3 = MLPG bwd), the elapsed milliseconds,
+ * the algorithmic work (flops for GEMMs, bytes for MLPG) and the launch count into arrays of 8. */
+int gantts_profile_enable(int on);
+int gantts_profile_collect(double* ms, double* work, long long* launches);
 
 /* ---------------------------------------------------------------------------------------------
  * Feature-stream layout (reference hparams.py:196-206: stream_sizes / has_dynamic_features).

@@ -1,0 +1,147 @@
+"""CPU-only tests: C-ABI library loads and exports every declared symbol, host-side logic
+(stream column tables, MLPG table, argument validation), and the no-CPU-fallback rule."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, WINDOWS
+from oracle import nnmnkwii_port as nnp
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__
+    __graft_entry__.build()
+    from gantts_b200 import _lib
+    return _lib.load()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from gantts_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "gantts_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(gantts_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    for name in sorted(declared):
+        assert hasattr(lib, name), "libgantts_b200.so does not export %s" % name
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert lib.gantts_version() >= 100
+    assert lib.gantts_last_error_string() is not None
+
+
+def test_library_is_sm100a_only(lib):
+    import subprocess
+    from gantts_b200 import _lib
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out and "sm_90" not in out
+
+
+def test_mlpg_table_matches_dense_inverse(lib):
+    from gantts_b200 import ops
+    for wins, T in ((WINDOWS, 64), (WINDOWS, 257), (WINDOWS[:2], 50), (WINDOWS[:1], 9), (WINDOWS, 3)):
+        tab = ops.mlpg_table_host(wins, T)
+        Pi = np.linalg.inv(nnp.normal_matrix(wins, T))
+        K = 24
+        for t in range(T):
+            for j in range(49):
+                c = t + j - K
+                exp = Pi[t, c] if 0 <= c < T else 0.0
+                assert abs(tab[t, j] - exp) < 2e-7
+
+
+def test_mlpg_table_fir_equals_dense_R():
+    """Stencil + truncated FIR (the CUDA algorithm, evaluated here in numpy from the library's own
+    table) reproduces the reference's dense R matmul."""
+    from gantts_b200 import ops
+    T, sd = 120, 5
+    rng = np.random.default_rng(0)
+    mu = rng.standard_normal((T, 3 * sd))
+    R = nnp.unit_variance_mlpg_matrix(WINDOWS, T).astype(np.float64)
+    ref = R @ np.vstack([mu[:, w * sd:(w + 1) * sd] for w in range(3)])
+    tab = ops.mlpg_table_host(WINDOWS, T).astype(np.float64)
+    b = np.zeros((T, sd))
+    for w, (l, u, coef) in enumerate(WINDOWS):
+        for k in range(-l, u + 1):
+            for t in range(T):
+                if 0 <= t - k < T:
+                    b[t] += coef[k + l] * mu[t - k, w * sd:(w + 1) * sd]
+    y = np.zeros((T, sd))
+    for t in range(T):
+        for j in range(49):
+            c = t + j - 24
+            if 0 <= c < T:
+                y[t] += tab[t, j] * b[c]
+    assert np.max(np.abs(y - ref)) / np.max(np.abs(ref)) < 1e-6
+
+
+def test_bad_windows_rejected(lib):
+    from gantts_b200 import _lib
+    w = _lib.make_windows([(0, 0, [1.0])])
+    w.n = 9
+    tab = np.zeros((4, 49), np.float32)
+    assert lib.gantts_mlpg_table(ctypes.byref(w), 4, tab.ctypes.data) == 1
+    assert b"window" in lib.gantts_last_error_string()
+    with pytest.raises(RuntimeError):
+        _lib.make_windows([(3, 3, [1.0] * 7)])
+
+
+def test_stream_column_tables(golden_ops):
+    from gantts_b200 import multistream as ms
+    assert np.array_equal(ms.get_static_stream_sizes([180, 3, 1, 3], [True, True, False, True], 3),
+                          golden_ops["static_sizes"])
+    x = np.arange(63)
+    for name in ("1111", "1000", "1001", "0010", "0101"):
+        cols = ms.select_stream_columns([60, 1, 1, 1], [c == "1" for c in name])
+        assert np.array_equal(x[cols], golden_ops["select_" + name][0, 0])
+    y = golden_ops["ms_in"]
+    cols = ms.static_feature_columns(3, [180, 3, 1, 3], [True, True, False, True], [True] * 4)
+    assert np.array_equal(y[:, :, cols], golden_ops["static_all"])
+    cols = ms.static_feature_columns(3, [180, 3, 1, 3], [True, True, False, True], [True, False, False, True])
+    assert np.array_equal(y[:, :, cols], golden_ops["static_1001"])
+    entries, n = ms.mlpg_stream_entries([180, 3, 1, 3], [True, True, False, True], [True] * 4, 3)
+    assert entries == [(0, 60, True, 0), (180, 1, True, 60), (183, 1, False, 61), (184, 1, True, 62)] and n == 63
+    entries, n = ms.mlpg_stream_entries([180, 3, 1, 3], [True, True, False, True], [True, False, True, False], 3)
+    assert entries == [(0, 60, True, 0), (183, 1, False, 60)] and n == 61
+
+
+def test_no_cpu_fallback(lib):
+    """CPU tensors are rejected loudly instead of being routed to a host implementation."""
+    import gantts_b200
+    from gantts_b200 import ops
+    x = torch.zeros(2, 5, 63)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        gantts_b200.multistream.select_streams(x)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        gantts_b200.seqloss.sequence_mask(torch.LongTensor([3, 2]))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        gantts_b200.models.MLP(4, 2)(torch.zeros(3, 4))
+    with pytest.raises(RuntimeError):
+        gantts_b200.seqloss.MaskedMSELoss()(x, x)
+    with pytest.raises(RuntimeError, match="dimention"):
+        gantts_b200.multistream.multi_stream_mlpg(torch.zeros(1, 4, 100), None)
+    assert ops.windows_for(3)[2] == (1, 1, (1.0, -2.0, 1.0))
+
+
+def test_product_does_not_import_oracle():
+    """The oracle is test infrastructure: nothing under gantts_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "gantts_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src, os.path.join(dirpath, f)
+
+
+def test_state_dict_keys_match_reference_layout():
+    import gantts_b200
+    m = gantts_b200.models.MLP(in_dim=7, out_dim=3, num_hidden=2, hidden_dim=5)
+    assert list(m.state_dict()) == ["layers.0.weight", "layers.0.bias", "layers.1.weight", "layers.1.bias",
+                                    "last_linear.weight", "last_linear.bias"]
+    h = gantts_b200.models.In2OutHighwayNet(in_dim=6, out_dim=6, static_dim=2, num_hidden=2, hidden_dim=4)
+    assert list(h.state_dict()) == ["T.weight", "T.bias", "H.0.weight", "H.0.bias", "H.1.weight", "H.1.bias",
+                                    "last_linear.weight", "last_linear.bias"]
+    assert h.include_parameter_generation() and not m.include_parameter_generation()
