@@ -37,6 +37,20 @@ class WindowsT(ctypes.Structure):
                 ("coef", (ctypes.c_float * MAX_TAPS) * MAX_WINDOWS)]
 
 
+MAX_LAYERS = 8
+
+
+class MlpT(ctypes.Structure):
+    _fields_ = [("num_layers", ctypes.c_int),
+                ("dims", ctypes.c_int * (MAX_LAYERS + 1)),
+                ("W", ctypes.c_void_p * MAX_LAYERS),
+                ("b", ctypes.c_void_p * MAX_LAYERS),
+                ("slope", ctypes.c_float),
+                ("dropout_p", ctypes.c_float),
+                ("last_act", ctypes.c_int),
+                ("seed", ctypes.c_uint64)]
+
+
 _lib = None
 
 _vp, _i, _i64, _f, _u64, _sz = (ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float,
@@ -68,6 +82,11 @@ SIGNATURES = {
                                _vp, _sz, _vp]),
     "gantts_linear_bwd": (_i, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _i64,
                                _i, _i, _i, _f, _f, _i, _i, _vp, _sz, _vp]),
+    "gantts_mlp_tape_bytes": (_sz, [ctypes.POINTER(MlpT), _i64]),
+    "gantts_mlp_workspace_bytes": (_sz, [ctypes.POINTER(MlpT), _i64]),
+    "gantts_mlp_fwd": (_i, [ctypes.POINTER(MlpT), _vp, _i64, _i64, _vp, _i64, _vp, _sz, _vp]),
+    "gantts_mlp_bwd": (_i, [ctypes.POINTER(MlpT), _vp, _i64, _vp, _i64, _i64, _vp, _sz, _vp, _i64, _vp, _vp,
+                            _i, _vp, _sz, _vp]),
     "gantts_optim_workspace_bytes": (_sz, []),
     "gantts_grad_sumsq": (_i, [_vp, _vp, _i, _vp, _vp, _sz, _vp]),
     "gantts_clip_adagrad_step": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _f, _f, _f, _f, _vp]),

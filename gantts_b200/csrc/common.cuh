@@ -69,21 +69,20 @@ __device__ __forceinline__ void block_sum(float (&v)[NV], float* smem) {
   }
 }
 
-// Counter-based keep decision for dropout: 32-bit mix of (seed, element index), two elements per
-// hash (16-bit thresholds).  Not torch's Philox stream (hard part 4).
-__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+// Counter-based keep decision for dropout: one 32-bit hash per PAIR of adjacent columns
+// (key = row * ceil(N/2) + col/2, 32-bit wrap-around arithmetic), 16-bit threshold per element:
+// keep iff field >= thresh, thresh = round(p * 65536).  Both GEMM engines use exactly this
+// function, so they produce identical masks.  Not torch's Philox stream (hard part 4).
+__device__ __forceinline__ uint32_t dropout_pair_bits(uint64_t seed, uint32_t row, uint32_t half_n,
+                                                      uint32_t pair_col) {
+  uint32_t x = (row * half_n + pair_col) * 0x9E3779B1u + static_cast<uint32_t>(seed);
   x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
-  return x;
+  return x ^ static_cast<uint32_t>(seed >> 32);
 }
-__device__ __forceinline__ uint32_t dropout_bits(uint64_t seed, uint64_t pair_index) {
-  uint32_t lo = static_cast<uint32_t>(pair_index), hi = static_cast<uint32_t>(pair_index >> 32);
-  uint32_t s0 = static_cast<uint32_t>(seed), s1 = static_cast<uint32_t>(seed >> 32);
-  return mix32(mix32(lo ^ s0) + (hi ^ s1) * 0x9e3779b9U + 0x85ebca6bU);
-}
-// keep iff 16-bit field >= thresh, thresh = round(p * 65536).
-__device__ __forceinline__ bool dropout_keep(uint64_t seed, uint64_t elem_index, uint32_t thresh) {
-  uint32_t bits = dropout_bits(seed, elem_index >> 1);
-  uint32_t f = (elem_index & 1) ? (bits >> 16) : (bits & 0xffffu);
+__device__ __forceinline__ bool dropout_keep(uint64_t seed, uint32_t row, uint32_t n_cols, uint32_t col,
+                                             uint32_t thresh) {
+  uint32_t bits = dropout_pair_bits(seed, row, (n_cols + 1) >> 1, col >> 1);
+  uint32_t f = (col & 1) ? (bits >> 16) : (bits & 0xffffu);
   return f >= thresh;
 }
 

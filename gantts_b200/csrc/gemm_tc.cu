@@ -21,11 +21,17 @@
 
 namespace gantts {
 
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int TC_BM = 128;          // MMA M (TMEM lanes)
 constexpr int TC_BK = 64;           // reduction elements per stage (one 128B swizzle atom of bf16)
 constexpr int TC_MAX_STAGES = 4;
 constexpr uint32_t TC_A_PLANE = TC_BM * TC_BK * 2;   // 16 KB
+
+// Epilogue flavours (template parameter of the kernel).
+constexpr int EPI_F32 = 0;          // bias + {none | leaky+dropout | sigmoid} -> fp32 C (optionally +=)
+constexpr int EPI_PLANES_FWD = 1;   // bias + leaky + dropout -> bf16 hi/lo planes (next layer's operand)
+constexpr int EPI_PLANES_BWD = 2;   // acc * act'(saved output hi plane) -> bf16 hi/lo planes (gz)
 
 struct GemmParams {
   int64_t rows_a;       // output rows   (extent of A's MN dimension)
@@ -33,14 +39,21 @@ struct GemmParams {
   int64_t red;          // reduction extent
   int64_t red_chunk;    // reduction elements per z-slice (multiple of TC_BK)
   int num_a, num_b, num_z;
-  int bn;               // MMA N, multiple of 16, <= 256
+  int bn;               // MMA N, multiple of 32, <= 256
   int num_stages;
   uint32_t stage_bytes, b_plane_bytes, tx_bytes;
   uint32_t tmem_cols;
+  // EPI_F32 output
   float* C;
   int64_t ldc, c_zstride;
-  int vec_ok;
-  // epilogue
+  int vec_ok, accumulate;
+  // planes output (EPI_PLANES_*)
+  __nv_bfloat16 *out_hi, *out_lo;
+  int64_t out_pitch;
+  // saved activation (EPI_PLANES_BWD)
+  const __nv_bfloat16* h_hi;
+  int64_t h_pitch;
+  // epilogue math
   const float* bias;
   int act;
   float slope, keep_scale;
@@ -48,7 +61,123 @@ struct GemmParams {
   uint64_t seed;
 };
 
-template <bool MN>
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// Split 8 fp32 values into bf16 hi/lo and store them as two 16-byte vectors.
+__device__ __forceinline__ void store_planes8(const float* v, __nv_bfloat16* hi, __nv_bfloat16* lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float a = v[2 * i], b = v[2 * i + 1];
+    const uint32_t hp = pack_bf16x2(a, b);
+    const float ah = __uint_as_float(hp << 16), bh = __uint_as_float(hp & 0xffff0000u);
+    h[i] = hp;
+    l[i] = pack_bf16x2(a - ah, b - bh);
+  }
+  *reinterpret_cast<uint4*>(hi) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4*>(lo) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// One 16-column chunk of one output row: registers (fp32 accumulators) -> global.
+template <int EPI>
+__device__ __forceinline__ void epilogue_chunk16(const GemmParams& p, const uint32_t (&r)[16], int64_t row,
+                                                 int col, int z) {
+  float v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+  if (EPI == EPI_F32) {
+    float* crow = p.C + (int64_t)z * p.c_zstride + row * p.ldc;
+    if (p.bias) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (col + j < p.cols_b) v[j] += __ldg(p.bias + col + j);
+    }
+    if (p.act == GANTTS_ACT_LEAKY_DROPOUT) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], v[j] * p.slope);
+      if (p.thresh) {
+        const uint32_t half_n = (uint32_t)(p.cols_b + 1) >> 1;
+#pragma unroll
+        for (int j = 0; j < 16; j += 2) {
+          const uint32_t bits = dropout_pair_bits(p.seed, (uint32_t)row, half_n, (uint32_t)(col + j) >> 1);
+          v[j] = (bits & 0xffffu) >= p.thresh ? v[j] * p.keep_scale : 0.f;
+          v[j + 1] = (bits >> 16) >= p.thresh ? v[j + 1] * p.keep_scale : 0.f;
+        }
+      }
+    } else if (p.act == GANTTS_ACT_SIGMOID) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = 1.f / (1.f + expf(-v[j]));
+    }
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      const int c = col + j;
+      if (p.vec_ok && c + 3 < p.cols_b) {
+        *reinterpret_cast<float4*>(crow + c) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (c + e < p.cols_b) crow[c + e] = p.accumulate ? crow[c + e] + v[j + e] : v[j + e];
+      }
+    }
+  } else if (EPI == EPI_PLANES_FWD) {
+    // reference gantts/models.py:137-139: Dropout(LeakyReLU(Linear(x)))
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      const int c = col + j;
+      if (c + 3 < p.cols_b) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + c));
+        v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (c + e < p.cols_b) v[j + e] += __ldg(p.bias + c + e);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], v[j] * p.slope);
+    if (p.thresh) {
+      const uint32_t half_n = (uint32_t)(p.cols_b + 1) >> 1;
+#pragma unroll
+      for (int j = 0; j < 16; j += 2) {
+        const uint32_t bits = dropout_pair_bits(p.seed, (uint32_t)row, half_n, (uint32_t)(col + j) >> 1);
+        v[j] = (bits & 0xffffu) >= p.thresh ? v[j] * p.keep_scale : 0.f;
+        v[j + 1] = (bits >> 16) >= p.thresh ? v[j + 1] * p.keep_scale : 0.f;
+      }
+    }
+    __nv_bfloat16* oh = p.out_hi + row * p.out_pitch + col;
+    __nv_bfloat16* ol = p.out_lo + row * p.out_pitch + col;
+    if (col + 8 <= p.out_pitch) store_planes8(v, oh, ol);
+    if (col + 16 <= p.out_pitch) store_planes8(v + 8, oh + 8, ol + 8);
+  } else {  // EPI_PLANES_BWD: gz = g * act'(h), derivative recovered from the saved output's hi plane
+    const float dpos = p.keep_scale, dneg = p.slope * p.keep_scale;
+    const float dzero = p.thresh ? 0.f : p.slope;
+    const __nv_bfloat16* hrow = p.h_hi + row * p.h_pitch + col;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      if (col + 8 * half + 8 <= p.h_pitch) {
+        const uint4 hv = __ldg(reinterpret_cast<const uint4*>(hrow + 8 * half));
+        const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t lo16 = hw[i] & 0xffffu, hi16 = hw[i] >> 16;
+          const float d0 = (lo16 & 0x7fffu) == 0 ? dzero : ((lo16 & 0x8000u) ? dneg : dpos);
+          const float d1 = (hi16 & 0x7fffu) == 0 ? dzero : ((hi16 & 0x8000u) ? dneg : dpos);
+          v[8 * half + 2 * i] *= d0;
+          v[8 * half + 2 * i + 1] *= d1;
+        }
+      }
+    }
+    __nv_bfloat16* oh = p.out_hi + row * p.out_pitch + col;
+    __nv_bfloat16* ol = p.out_lo + row * p.out_pitch + col;
+    if (col + 8 <= p.out_pitch) store_planes8(v, oh, ol);
+    if (col + 16 <= p.out_pitch) store_planes8(v + 8, oh + 8, ol + 8);
+  }
+}
+
+template <bool MN, int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                    const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
@@ -69,7 +198,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(tfull0 + 8 * a, 1);
-      ptx::mbar_init(tempty0 + 8 * a, 4);
+      ptx::mbar_init(tempty0 + 8 * a, TC_EPI_WARPS);
     }
     ptx::fence_barrier_init();
     ptx::prefetch_tensormap(&tmAh);
@@ -107,8 +236,8 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
           const uint32_t sb_hi = sa_lo + TC_A_PLANE, sb_lo = sb_hi + p.b_plane_bytes;
           if (!MN) {
             ptx::tma_load_2d(sa_hi, &tmAh, fb, (int32_t)r0, a0);
-            ptx::tma_load_2d(sa_lo, &tmAl, fb, (int32_t)r0, a0);
             ptx::tma_load_2d(sb_hi, &tmBh, fb, (int32_t)r0, b0);
+            ptx::tma_load_2d(sa_lo, &tmAl, fb, (int32_t)r0, a0);
             ptx::tma_load_2d(sb_lo, &tmBl, fb, (int32_t)r0, b0);
           } else {
             // 64-wide MN atoms, each [TC_BK reduction rows][128 B]
@@ -167,8 +296,12 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
       }
     }
   } else {
-    // -------------------------------------------------------------- epilogue warps (2..5)
-    const int q = warp & 3;                        // TMEM lane quarter this warp may access
+    // -------------------------------------------------------------- epilogue warps (2..9)
+    // warp w may access TMEM lanes 32*(w%4)..+31; warps 2-5 take the first half of the tile's
+    // columns, warps 6-9 the second half, so all four SM sub-partitions work on the epilogue.
+    const int q = warp & 3;
+    const int chalf = (warp - 2) >> 2;
+    const int cbeg = chalf * (p.bn >> 1), cend = cbeg + (p.bn >> 1);
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int z = tile / tiles_ab, rem = tile - z * tiles_ab;
@@ -179,41 +312,17 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
       ptx::tc_fence_after();
       const int64_t row = (int64_t)ta * TC_BM + q * 32 + lane;
       const int col0 = tb * p.bn;
-      float* crow = p.C + (int64_t)z * p.c_zstride + row * p.ldc;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256;
-      for (int c = 0; c < p.bn; c += 16) {
-        uint32_t r[16];
-        ptx::tmem_ld16(taddr + c, r);
+      const bool row_ok = row < p.rows_a;
+      for (int c = cbeg; c < cend; c += 32) {
+        uint32_t r0[16], r1[16];
+        const bool two = c + 32 <= cend;
+        ptx::tmem_ld16(taddr + c, r0);
+        if (two) ptx::tmem_ld16(taddr + c + 16, r1);
         ptx::tmem_ld_wait();
-        if (row < p.rows_a) {
-          float v[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int col = col0 + c + j;
-            float x = __uint_as_float(r[j]);
-            if (p.bias && col < p.cols_b) x += p.bias[col];
-            if (p.act == GANTTS_ACT_LEAKY_DROPOUT) {
-              x = x > 0.f ? x : x * p.slope;
-              if (p.thresh) {
-                bool keep = dropout_keep(p.seed, (uint64_t)row * (uint64_t)p.cols_b + (uint64_t)col, p.thresh);
-                x = keep ? x * p.keep_scale : 0.f;
-              }
-            } else if (p.act == GANTTS_ACT_SIGMOID) {
-              x = 1.f / (1.f + expf(-x));
-            }
-            v[j] = x;
-          }
-#pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            const int col = col0 + c + j;
-            if (p.vec_ok && col + 3 < p.cols_b) {
-              *reinterpret_cast<float4*>(crow + col) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            } else {
-#pragma unroll
-              for (int e = 0; e < 4; ++e)
-                if (col + e < p.cols_b) crow[col + e] = v[j + e];
-            }
-          }
+        if (row_ok) {
+          if (col0 + c < p.cols_b) epilogue_chunk16<EPI>(p, r0, row, col0 + c, z);
+          if (two && col0 + c + 16 < p.cols_b) epilogue_chunk16<EPI>(p, r1, row, col0 + c + 16, z);
         }
       }
       ptx::tc_fence_before();
@@ -336,27 +445,79 @@ static int launch_split(const float* src, int64_t rs, int64_t rows, int cols, co
 }
 
 static int pick_bn(int n) {
-  int bn = (n + 15) / 16 * 16;
+  int bn = (n + 31) / 32 * 32;
   if (bn <= 256) return bn;
   int tiles = (n + 255) / 256;
-  bn = ((n + tiles - 1) / tiles + 15) / 16 * 16;
+  bn = ((n + tiles - 1) / tiles + 31) / 32 * 32;
   return bn;
 }
 
+// Epilogue description filled by the callers of launch_gemm_kk.
 struct EpiArgs {
+  int epi = EPI_F32;
+  // EPI_F32
+  float* C = nullptr;
+  int64_t ldc = 0;
+  int accumulate = 0;
+  // EPI_PLANES_*
+  __nv_bfloat16 *out_hi = nullptr, *out_lo = nullptr;
+  int64_t out_pitch = 0;
+  const __nv_bfloat16* h_hi = nullptr;
+  int64_t h_pitch = 0;
+  // math
   const float* bias = nullptr;
   int act = GANTTS_ACT_NONE;
   float slope = 0.f, p = 0.f;
   uint64_t seed = 0;
 };
 
-// C[rows_a][cols_b] = A * B^T (K-major planes A [rows_a][red], B [cols_b][red]).
-static int launch_gemm_kk(const Planes& A, const Planes& B, float* C, int64_t ldc, const EpiArgs& e,
-                          cudaStream_t st) {
+static void fill_epilogue(GemmParams& p, const EpiArgs& e) {
+  p.C = e.C;
+  p.ldc = e.ldc;
+  p.accumulate = e.accumulate;
+  p.vec_ok = (!e.accumulate && e.C && (e.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(e.C) & 15) == 0) ? 1 : 0;
+  p.out_hi = e.out_hi;
+  p.out_lo = e.out_lo;
+  p.out_pitch = e.out_pitch;
+  p.h_hi = e.h_hi;
+  p.h_pitch = e.h_pitch;
+  p.bias = e.bias;
+  p.act = e.act;
+  p.slope = e.slope;
+  p.keep_scale = e.p > 0.f ? 1.f / (1.f - e.p) : 1.f;
+  p.thresh = e.p > 0.f ? (uint32_t)(e.p * 65536.f + 0.5f) : 0u;
+  p.seed = e.seed;
+}
+
+template <bool MN, int EPI>
+static int launch_kernel(const CUtensorMap& mAh, const CUtensorMap& mAl, const CUtensorMap& mBh,
+                         const CUtensorMap& mBl, const GemmParams& p, cudaStream_t st) {
+  const size_t smem = (size_t)p.num_stages * p.stage_bytes + 1024 + 256;
+  static bool attr = false;
+  if (!attr) {
+    GANTTS_CUDA(cudaFuncSetAttribute(gemm_bf16x3_kernel<MN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     227 * 1024));
+    attr = true;
+  }
+  const int total = p.num_a * p.num_b * p.num_z;
+  const int grid = total < num_sms() ? total : num_sms();
+  prof_begin(MN ? PROF_GEMM_MN : PROF_GEMM_KK, 2.0 * (double)p.rows_a * p.cols_b * (double)p.red, st);
+  gemm_bf16x3_kernel<MN, EPI><<<grid, TC_THREADS, smem, st>>>(mAh, mAl, mBh, mBl, p);
+  prof_end(st);
+  GANTTS_LAUNCH_CHECK("gemm_bf16x3_kernel");
+  return GANTTS_OK;
+}
+
+// out[rows_a][cols_b] = epi(A * B^T)   (K-major planes A [rows_a][red], B [cols_b][red]).
+static int launch_gemm_kk(const Planes& A, const Planes& B, const EpiArgs& e, cudaStream_t st) {
   GemmParams p{};
   p.rows_a = A.rows;
   p.cols_b = (int)B.rows;
   p.red = A.cols;
+  if (B.cols != A.cols) {
+    set_error("gemm_kk: reduction extents differ (%lld vs %lld)", (long long)A.cols, (long long)B.cols);
+    return GANTTS_E_BADARG;
+  }
   p.red_chunk = (p.red + TC_BK - 1) / TC_BK * TC_BK;
   p.bn = pick_bn(p.cols_b);
   p.num_a = (int)((p.rows_a + TC_BM - 1) / TC_BM);
@@ -368,36 +529,21 @@ static int launch_gemm_kk(const Planes& A, const Planes& B, float* C, int64_t ld
   p.num_stages = (int)((220 * 1024) / p.stage_bytes);
   if (p.num_stages > TC_MAX_STAGES) p.num_stages = TC_MAX_STAGES;
   p.tmem_cols = 512;
-  p.C = C;
-  p.ldc = ldc;
   p.c_zstride = 0;
-  p.vec_ok = ((ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0 && (p.bn % 4) == 0) ? 1 : 0;
-  p.bias = e.bias;
-  p.act = e.act;
-  p.slope = e.slope;
-  p.keep_scale = e.p > 0.f ? 1.f / (1.f - e.p) : 1.f;
-  p.thresh = (e.act == GANTTS_ACT_LEAKY_DROPOUT && e.p > 0.f) ? (uint32_t)(e.p * 65536.f + 0.5f) : 0u;
-  p.seed = e.seed;
+  fill_epilogue(p, e);
   CUtensorMap mAh, mAl, mBh, mBl;
   int rc;
   if ((rc = make_map(&mAh, A.hi, A.rows, A.cols, A.pitch, TC_BM))) return rc;
   if ((rc = make_map(&mAl, A.lo, A.rows, A.cols, A.pitch, TC_BM))) return rc;
   if ((rc = make_map(&mBh, B.hi, B.rows, B.cols, B.pitch, p.bn))) return rc;
   if ((rc = make_map(&mBl, B.lo, B.rows, B.cols, B.pitch, p.bn))) return rc;
-  const size_t smem = (size_t)p.num_stages * p.stage_bytes + 1024 + 256;
-  static bool attr = false;
-  if (!attr) {
-    GANTTS_CUDA(cudaFuncSetAttribute(gemm_bf16x3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     227 * 1024));
-    attr = true;
+  switch (e.epi) {
+    case EPI_F32: return launch_kernel<false, EPI_F32>(mAh, mAl, mBh, mBl, p, st);
+    case EPI_PLANES_FWD: return launch_kernel<false, EPI_PLANES_FWD>(mAh, mAl, mBh, mBl, p, st);
+    case EPI_PLANES_BWD: return launch_kernel<false, EPI_PLANES_BWD>(mAh, mAl, mBh, mBl, p, st);
   }
-  int total = p.num_a * p.num_b;
-  int grid = total < num_sms() ? total : num_sms();
-  prof_begin(PROF_GEMM_KK, 2.0 * (double)p.rows_a * p.cols_b * (double)p.red, st);
-  gemm_bf16x3_kernel<false><<<grid, TC_THREADS, smem, st>>>(mAh, mAl, mBh, mBl, p);
-  prof_end(st);
-  GANTTS_LAUNCH_CHECK("gemm_bf16x3_kernel<K-major>");
-  return GANTTS_OK;
+  set_error("gemm_kk: bad epilogue %d", e.epi);
+  return GANTTS_E_BADARG;
 }
 
 // C[n][k] (+)= sum_m A[m][n] * B[m][k]  (MN-major planes A [red][rows_a], B [red][cols_b]);
@@ -413,7 +559,7 @@ static size_t mn_partial_bytes(int64_t red, int rows_a, int cols_b, int* splits_
   splits = (red + chunk - 1) / chunk;
   if (splits_out) *splits_out = (int)splits;
   if (chunk_out) *chunk_out = chunk;
-  return (size_t)splits * rows_a * cols_b * sizeof(float);
+  return ((size_t)splits * rows_a * cols_b * sizeof(float) + 255) / 256 * 256;
 }
 
 static int launch_gemm_mn(const Planes& A, const Planes& B, float* C, int accumulate, float* partial,
@@ -422,6 +568,10 @@ static int launch_gemm_mn(const Planes& A, const Planes& B, float* C, int accumu
   p.rows_a = A.cols;
   p.cols_b = (int)B.cols;
   p.red = A.rows;
+  if (B.rows != A.rows) {
+    set_error("gemm_mn: reduction extents differ (%lld vs %lld)", (long long)A.rows, (long long)B.rows);
+    return GANTTS_E_BADARG;
+  }
   int splits;
   int64_t chunk;
   mn_partial_bytes(p.red, (int)p.rows_a, p.cols_b, &splits, &chunk);
@@ -438,31 +588,19 @@ static int launch_gemm_mn(const Planes& A, const Planes& B, float* C, int accumu
   if (p.num_stages > TC_MAX_STAGES) p.num_stages = TC_MAX_STAGES;
   p.tmem_cols = 512;
   const bool direct = (splits == 1 && !accumulate);
-  p.C = direct ? C : partial;
-  p.ldc = p.cols_b;
+  EpiArgs e;
+  e.epi = EPI_F32;
+  e.C = direct ? C : partial;
+  e.ldc = p.cols_b;
+  fill_epilogue(p, e);
   p.c_zstride = (int64_t)p.rows_a * p.cols_b;
-  p.vec_ok = ((p.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0 && (p.bn % 4) == 0) ? 1 : 0;
-  p.act = GANTTS_ACT_NONE;
-  p.keep_scale = 1.f;
   CUtensorMap mAh, mAl, mBh, mBl;
   int rc;
   if ((rc = make_map(&mAh, A.hi, A.rows, A.cols, A.pitch, TC_BK))) return rc;
   if ((rc = make_map(&mAl, A.lo, A.rows, A.cols, A.pitch, TC_BK))) return rc;
   if ((rc = make_map(&mBh, B.hi, B.rows, B.cols, B.pitch, TC_BK))) return rc;
   if ((rc = make_map(&mBl, B.lo, B.rows, B.cols, B.pitch, TC_BK))) return rc;
-  const size_t smem = (size_t)p.num_stages * p.stage_bytes + 1024 + 256;
-  static bool attr = false;
-  if (!attr) {
-    GANTTS_CUDA(cudaFuncSetAttribute(gemm_bf16x3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     227 * 1024));
-    attr = true;
-  }
-  int total = p.num_a * p.num_b * p.num_z;
-  int grid = total < num_sms() ? total : num_sms();
-  prof_begin(PROF_GEMM_MN, 2.0 * (double)p.rows_a * p.cols_b * (double)p.red, st);
-  gemm_bf16x3_kernel<true><<<grid, TC_THREADS, smem, st>>>(mAh, mAl, mBh, mBl, p);
-  prof_end(st);
-  GANTTS_LAUNCH_CHECK("gemm_bf16x3_kernel<MN-major>");
+  if ((rc = launch_kernel<true, EPI_F32>(mAh, mAl, mBh, mBl, p, st))) return rc;
   if (!direct) {
     int64_t n = (int64_t)p.rows_a * p.cols_b;
     splitk_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(partial, splits, n, C, accumulate);
@@ -493,12 +631,15 @@ int tc_linear_fwd(const float* x, int64_t x_rs, const float* W, const float* bia
   if ((rc = launch_split(x, x_rs, M, K, X, 0, st))) return rc;
   if ((rc = launch_split(W, K, N, K, Wp, 0, st))) return rc;
   EpiArgs e;
+  e.epi = EPI_F32;
+  e.C = y;
+  e.ldc = y_rs;
   e.bias = bias;
   e.act = act;
   e.slope = slope;
-  e.p = p;
+  e.p = act == GANTTS_ACT_LEAKY_DROPOUT ? p : 0.f;
   e.seed = seed;
-  return launch_gemm_kk(X, Wp, y, y_rs, e, st);
+  return launch_gemm_kk(X, Wp, e, st);
 }
 
 int tc_linear_bwd_gemms(const float* gz, const float* x, int64_t x_rs, const float* W, float* gx,
@@ -519,7 +660,10 @@ int tc_linear_bwd_gemms(const float* gz, const float* x, int64_t x_rs, const flo
   if (gx) {
     if ((rc = launch_split(W, K, N, K, Wt, 1, st))) return rc;      // Wt[k][n] = W[n][k]
     EpiArgs e;
-    if ((rc = launch_gemm_kk(G, Wt, gx, gx_rs, e, st))) return rc;  // gx[m][k] = sum_n gz[m][n] W[n][k]
+    e.epi = EPI_F32;
+    e.C = gx;
+    e.ldc = gx_rs;
+    if ((rc = launch_gemm_kk(G, Wt, e, st))) return rc;             // gx[m][k] = sum_n gz[m][n] W[n][k]
   }
   if (gW) {
     if ((rc = launch_split(x, x_rs, M, K, X, 0, st))) return rc;

@@ -5,5 +5,6 @@
 #include "losses.cu"
 #include "linear_simt.cu"
 #include "gemm_tc.cu"
+#include "mlp_tc.cu"
 #include "linear.cu"
 #include "optim.cu"

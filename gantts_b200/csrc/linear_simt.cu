@@ -85,7 +85,7 @@ sgemm_kernel(const float* __restrict__ A, int64_t a_si, int64_t a_sk, const floa
       if (ep.act == GANTTS_ACT_LEAKY_DROPOUT) {
         v = v > 0.f ? v : v * ep.slope;
         if (ep.thresh) {
-          bool keep = dropout_keep(ep.seed, (uint64_t)gi * (uint64_t)Nj + (uint64_t)gj, ep.thresh);
+          bool keep = dropout_keep(ep.seed, (uint32_t)gi, (uint32_t)Nj, (uint32_t)gj, ep.thresh);
           v = keep ? v * ep.keep_scale : 0.f;
         }
       } else if (ep.act == GANTTS_ACT_SIGMOID) {

@@ -1,0 +1,249 @@
+// Whole-MLP forward / backward on the tcgen05 engine with activations resident as bf16 hi/lo planes
+// (include/gantts_b200.h: gantts_mlp_*).  Replaces reference gantts/models.py:137-141 (MLP.forward)
+// and its autograd backward with one GEMM launch per layer and direction:
+//   forward  l: H_{l+1} = Dropout(LeakyReLU(H_l W_l^T + b_l))  epilogue writes the next layer's planes
+//   backward l: gW_l = gZ_l^T H_l (MN-major GEMM, split over rows), gb_l = colsum(gZ_l),
+//               gZ_{l-1} = (gZ_l W_l) * act'(H_l)              epilogue writes the next gradient's planes
+// No fp32 activation ever round-trips through HBM between layers; the tape the caller keeps for the
+// backward holds the same planes the forward consumed (4 B per activation element, like fp32).
+#include "common.cuh"
+
+namespace gantts {
+
+// gz = gy (* y (1-y) for a sigmoid output) -> planes
+__global__ void grad_out_to_planes_kernel(const float* __restrict__ gy, int64_t gy_rs,
+                                          const float* __restrict__ y, int64_t y_rs, int64_t rows, int cols,
+                                          __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                          int64_t pitch, int sigmoid) {
+  const int64_t total = rows * cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / cols;
+    int c = (int)(i - r * cols);
+    float v = gy[r * gy_rs + c];
+    if (sigmoid) {
+      float yy = y[r * y_rs + c];
+      v *= yy * (1.f - yy);
+    }
+    __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi[r * pitch + c] = h;
+    lo[r * pitch + c] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
+// Column sums of a planes matrix (hi + lo): partial[chunk][col].
+__global__ void __launch_bounds__(256)
+colsum_planes_partial_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
+                             int64_t pitch, int64_t M, int N, int64_t rows_per_chunk,
+                             float* __restrict__ partial) {
+  __shared__ float sm[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + cx;
+  const int64_t rbeg = (int64_t)blockIdx.y * rows_per_chunk;
+  const int64_t rend = rbeg + rows_per_chunk < M ? rbeg + rows_per_chunk : M;
+  float s = 0.f;
+  if (col < N)
+    for (int64_t r = rbeg + ry; r < rend; r += 8)
+      s += __bfloat162float(hi[r * pitch + col]) + __bfloat162float(lo[r * pitch + col]);
+  sm[ry][cx] = s;
+  __syncthreads();
+  if (ry == 0 && col < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += sm[k][cx];
+    partial[(int64_t)blockIdx.y * N + col] = t;
+  }
+}
+
+constexpr int MLP_COLSUM_CHUNKS = 128;
+
+static int colsum_planes(const Planes& G, float* gb, int accumulate, float* partial, cudaStream_t st) {
+  int chunks = MLP_COLSUM_CHUNKS;
+  int64_t rpc = (G.rows + chunks - 1) / chunks;
+  if (rpc < 8) rpc = 8;
+  chunks = (int)((G.rows + rpc - 1) / rpc);
+  dim3 grid((unsigned)((G.cols + 31) / 32), chunks);
+  colsum_planes_partial_kernel<<<grid, 256, 0, st>>>(G.hi, G.lo, G.pitch, G.rows, (int)G.cols, rpc, partial);
+  GANTTS_LAUNCH_CHECK("colsum_planes_partial_kernel");
+  splitk_reduce_kernel<<<(unsigned)((G.cols + 255) / 256), 256, 0, st>>>(partial, chunks, G.cols, gb, accumulate);
+  GANTTS_LAUNCH_CHECK("splitk_reduce_kernel(colsum planes)");
+  return GANTTS_OK;
+}
+
+struct MlpTape {
+  Planes H[GANTTS_MAX_LAYERS];      // H[0] = input planes, H[l] = output of hidden layer l-1
+  Planes W[GANTTS_MAX_LAYERS];      // [d_{l+1}][d_l]
+  Planes Wt[GANTTS_MAX_LAYERS];     // [d_l][d_{l+1}]
+};
+
+static int check_mlp(const gantts_mlp_t* m, int64_t M) {
+  GANTTS_CHECK_ARG(m, "mlp: null descriptor");
+  GANTTS_CHECK_ARG(m->num_layers >= 1 && m->num_layers <= GANTTS_MAX_LAYERS, "mlp: bad layer count %d", m->num_layers);
+  GANTTS_CHECK_ARG(M >= 1, "mlp: M must be >= 1");
+  for (int l = 0; l <= m->num_layers; ++l) GANTTS_CHECK_ARG(m->dims[l] >= 1, "mlp: bad dim[%d]", l);
+  for (int l = 0; l < m->num_layers; ++l) {
+    GANTTS_CHECK_ARG(m->W[l] && m->b[l], "mlp: null weight/bias of layer %d", l);
+    GANTTS_CHECK_ARG((reinterpret_cast<uintptr_t>(m->b[l]) & 15) == 0, "mlp: bias %d must be 16-byte aligned", l);
+  }
+  GANTTS_CHECK_ARG(m->dropout_p >= 0.f && m->dropout_p < 1.f, "mlp: dropout p out of [0,1)");
+  GANTTS_CHECK_ARG(m->last_act == GANTTS_ACT_NONE || m->last_act == GANTTS_ACT_SIGMOID, "mlp: bad last_act");
+  return GANTTS_OK;
+}
+
+static size_t carve_tape(const gantts_mlp_t* m, int64_t M, char* base, MlpTape* t) {
+  char* cur = base;
+  for (int l = 0; l < m->num_layers; ++l) {
+    Planes p = carve_planes(cur, M, m->dims[l]);
+    if (t) t->H[l] = p;
+  }
+  for (int l = 0; l < m->num_layers; ++l) {
+    Planes a = carve_planes(cur, m->dims[l + 1], m->dims[l]);
+    Planes b = carve_planes(cur, m->dims[l], m->dims[l + 1]);
+    if (t) { t->W[l] = a; t->Wt[l] = b; }
+  }
+  return (size_t)(cur - base);
+}
+
+static inline uint64_t layer_seed(uint64_t seed, int l) { return seed + 0x9E3779B97F4A7C15ull * (uint64_t)(l + 1); }
+
+}  // namespace gantts
+
+using namespace gantts;
+
+extern "C" size_t gantts_mlp_tape_bytes(const gantts_mlp_t* m, int64_t M) {
+  if (!m || m->num_layers < 1 || m->num_layers > GANTTS_MAX_LAYERS || M < 1) return 0;
+  return carve_tape(m, M, nullptr, nullptr) + 512;
+}
+
+extern "C" size_t gantts_mlp_workspace_bytes(const gantts_mlp_t* m, int64_t M) {
+  if (!m || m->num_layers < 1 || m->num_layers > GANTTS_MAX_LAYERS || M < 1) return 0;
+  int maxd = 0;
+  size_t part = 0;
+  for (int l = 0; l <= m->num_layers; ++l) maxd = m->dims[l] > maxd ? m->dims[l] : maxd;
+  for (int l = 0; l < m->num_layers; ++l) {
+    size_t p = mn_partial_bytes(M, m->dims[l + 1], m->dims[l], nullptr, nullptr);
+    part = p > part ? p : part;
+  }
+  return 4 * plane_bytes(M, maxd) + part + (size_t)MLP_COLSUM_CHUNKS * maxd * sizeof(float) + 2048;
+}
+
+extern "C" int gantts_mlp_fwd(const gantts_mlp_t* m, const float* x, int64_t x_rs, int64_t M, float* y,
+                              int64_t y_rs, void* tape, size_t tape_bytes, void* stream) {
+  int rc = check_mlp(m, M);
+  if (rc) return rc;
+  GANTTS_CHECK_ARG(x && y && x_rs >= m->dims[0] && y_rs >= m->dims[m->num_layers], "mlp_fwd: bad pointers/strides");
+  size_t need = gantts_mlp_tape_bytes(m, M);
+  if (!tape || tape_bytes < need) {
+    set_error("mlp_fwd: tape too small (%zu < %zu)", tape_bytes, need);
+    return GANTTS_E_WORKSPACE;
+  }
+  cudaStream_t st = as_stream(stream);
+  MlpTape t;
+  carve_tape(m, M, reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(tape) + 255) / 256 * 256), &t);
+  const int L = m->num_layers;
+  if ((rc = launch_split(x, x_rs, M, m->dims[0], t.H[0], 0, st))) return rc;
+  for (int l = 0; l < L; ++l) {
+    if ((rc = launch_split(m->W[l], m->dims[l], m->dims[l + 1], m->dims[l], t.W[l], 0, st))) return rc;
+    if ((rc = launch_split(m->W[l], m->dims[l], m->dims[l + 1], m->dims[l], t.Wt[l], 1, st))) return rc;
+  }
+  for (int l = 0; l < L; ++l) {
+    EpiArgs e;
+    e.bias = m->b[l];
+    if (l < L - 1) {
+      e.epi = EPI_PLANES_FWD;
+      e.out_hi = t.H[l + 1].hi;
+      e.out_lo = t.H[l + 1].lo;
+      e.out_pitch = t.H[l + 1].pitch;
+      e.act = GANTTS_ACT_LEAKY_DROPOUT;
+      e.slope = m->slope;
+      e.p = m->dropout_p;
+      e.seed = layer_seed(m->seed, l);
+    } else {
+      e.epi = EPI_F32;
+      e.C = y;
+      e.ldc = y_rs;
+      e.act = m->last_act;
+    }
+    if ((rc = launch_gemm_kk(t.H[l], t.W[l], e, st))) return rc;
+  }
+  return GANTTS_OK;
+}
+
+extern "C" int gantts_mlp_bwd(const gantts_mlp_t* m, const float* gy, int64_t gy_rs, const float* y,
+                              int64_t y_rs, int64_t M, const void* tape, size_t tape_bytes, float* gx,
+                              int64_t gx_rs, float* const* gW, float* const* gb, int accumulate,
+                              void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_mlp(m, M);
+  if (rc) return rc;
+  const int L = m->num_layers;
+  GANTTS_CHECK_ARG(gy && gy_rs >= m->dims[L], "mlp_bwd: bad gy");
+  GANTTS_CHECK_ARG(m->last_act != GANTTS_ACT_SIGMOID || y, "mlp_bwd: sigmoid output needs y");
+  if (!tape || tape_bytes < gantts_mlp_tape_bytes(m, M)) {
+    set_error("mlp_bwd: tape too small");
+    return GANTTS_E_WORKSPACE;
+  }
+  size_t need = gantts_mlp_workspace_bytes(m, M);
+  if (!workspace || workspace_bytes < need) {
+    set_error("mlp_bwd: workspace too small (%zu < %zu)", workspace_bytes, need);
+    return GANTTS_E_WORKSPACE;
+  }
+  cudaStream_t st = as_stream(stream);
+  MlpTape t;
+  carve_tape(m, M, reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(const_cast<void*>(tape)) + 255) / 256 * 256), &t);
+  int maxd = 0;
+  for (int l = 0; l <= L; ++l) maxd = m->dims[l] > maxd ? m->dims[l] : maxd;
+  char* cur = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 255) / 256 * 256);
+  char* gbuf[2];
+  gbuf[0] = cur;
+  cur += 2 * plane_bytes(M, maxd);
+  gbuf[1] = cur;
+  cur += 2 * plane_bytes(M, maxd);
+  float* colpart = reinterpret_cast<float*>(cur);
+  cur += ((size_t)MLP_COLSUM_CHUNKS * maxd * sizeof(float) + 255) / 256 * 256;
+  float* partial = reinterpret_cast<float*>(cur);
+
+  int pp = 0;
+  char* c0 = gbuf[pp];
+  Planes G = carve_planes(c0, M, m->dims[L]);
+  {
+    int64_t total = M * m->dims[L];
+    int nb = (int)((total + 1023) / 1024);
+    if (nb > num_sms() * 8) nb = num_sms() * 8;
+    if (nb < 1) nb = 1;
+    grad_out_to_planes_kernel<<<nb, 256, 0, st>>>(gy, gy_rs, y, y_rs, M, m->dims[L], G.hi, G.lo, G.pitch,
+                                                  m->last_act == GANTTS_ACT_SIGMOID ? 1 : 0);
+    GANTTS_LAUNCH_CHECK("grad_out_to_planes_kernel");
+  }
+  for (int l = L - 1; l >= 0; --l) {
+    if (gW && gW[l]) {
+      if ((rc = launch_gemm_mn(G, t.H[l], gW[l], accumulate, partial, st))) return rc;
+    }
+    if (gb && gb[l]) {
+      if ((rc = colsum_planes(G, gb[l], accumulate, colpart, st))) return rc;
+    }
+    if (l > 0) {
+      char* c1 = gbuf[pp ^ 1];
+      Planes Gn = carve_planes(c1, M, m->dims[l]);
+      EpiArgs e;
+      e.epi = EPI_PLANES_BWD;
+      e.out_hi = Gn.hi;
+      e.out_lo = Gn.lo;
+      e.out_pitch = Gn.pitch;
+      e.h_hi = t.H[l].hi;
+      e.h_pitch = t.H[l].pitch;
+      e.slope = m->slope;
+      e.p = m->dropout_p;
+      if ((rc = launch_gemm_kk(G, t.Wt[l], e, st))) return rc;
+      G = Gn;
+      pp ^= 1;
+    } else if (gx) {
+      EpiArgs e;
+      e.epi = EPI_F32;
+      e.C = gx;
+      e.ldc = gx_rs;
+      e.accumulate = accumulate;
+      if ((rc = launch_gemm_kk(G, t.Wt[0], e, st))) return rc;
+    }
+  }
+  return GANTTS_OK;
+}

@@ -4,6 +4,7 @@ import torch
 from torch import nn
 
 from . import _lib
+from . import config
 from . import ops
 
 
@@ -15,11 +16,17 @@ class AbstractModel(object):
         return False
 
 
-def _hidden_stack(x, layers, p, training, engine=None):
-    for layer in layers:
+def _mlp(x, hidden, last, p, training, last_act, engine=None):
+    """Hidden stack + last_linear.  Tensor-core engine: ONE fused stack op (planes-resident
+    activations); SIMT engine: per-layer exact-fp32 ops (validation path)."""
+    if (engine or config.engine) == "tc":
+        layers = list(hidden) + [last]
+        return ops.mlp_stack(x, [l.weight for l in layers], [l.bias for l in layers], p=p, training=training,
+                             last_act=last_act)
+    for layer in hidden:
         x = ops.linear_act(x, layer.weight, layer.bias, _lib.ACT_LEAKY_DROPOUT, p=p, training=training,
                            engine=engine)
-    return x
+    return ops.linear_act(x, last.weight, last.bias, last_act, engine=engine)
 
 
 class MLP(AbstractModel, nn.Module):
@@ -41,9 +48,8 @@ class MLP(AbstractModel, nn.Module):
         self.engine = None          # None -> gantts_b200.config.engine
 
     def forward(self, x, lengths=None):
-        x = _hidden_stack(x, self.layers, self.dropout_p, self.training, self.engine)
         act = _lib.ACT_SIGMOID if self.last_sigmoid else _lib.ACT_NONE
-        return ops.linear_act(x, self.last_linear.weight, self.last_linear.bias, act, engine=self.engine)
+        return _mlp(x, self.layers, self.last_linear, self.dropout_p, self.training, act, self.engine)
 
 
 class In2OutHighwayNet(AbstractModel, nn.Module):
@@ -71,7 +77,6 @@ class In2OutHighwayNet(AbstractModel, nn.Module):
         x = x.unsqueeze(0) if x.dim() == 2 else x
         x_static = x[:, :, :self.static_dim]
         Tx = ops.linear_act(x_static, self.T.weight, self.T.bias, _lib.ACT_SIGMOID, engine=self.engine)
-        h = _hidden_stack(x, self.H, self.dropout_p, self.training, self.engine)
-        h = ops.linear_act(h, self.last_linear.weight, self.last_linear.bias, _lib.ACT_NONE, engine=self.engine)
+        h = _mlp(x, self.H, self.last_linear, self.dropout_p, self.training, _lib.ACT_NONE, self.engine)
         Gx = ops.unit_variance_mlpg(R, h)
         return h, ops.highway_combine(x_static, Tx, Gx)

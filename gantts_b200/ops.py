@@ -386,6 +386,86 @@ def linear_act(x, W, b, act=_lib.ACT_NONE, p=0.0, training=False, slope=LEAKY_SL
     return _LinearAct.apply(x, W, b, int(act), float(slope), p_eff, int(seed or 0), eng)
 
 
+# ------------------------------------------------------------------ whole MLP (tensor cores)
+class _MLPStack(torch.autograd.Function):
+    """y = MLP(x) through gantts_mlp_fwd / gantts_mlp_bwd: one tcgen05 GEMM per layer and direction,
+    activations resident as bf16 hi/lo planes (the tape)."""
+
+    @staticmethod
+    def forward(ctx, x, slope, p, last_act, seed, *params):
+        require_cuda(x, *params)
+        lib = _lib.load()
+        L = len(params) // 2
+        if L > _lib.MAX_LAYERS:
+            raise RuntimeError("gantts_b200: at most %d layers" % _lib.MAX_LAYERS)
+        x2, xrs = _rows2d(x)
+        M = x2.shape[0]
+        Ws = [params[2 * i].contiguous() for i in range(L)]
+        bs = [params[2 * i + 1].contiguous() for i in range(L)]
+        d = _lib.MlpT()
+        d.num_layers = L
+        d.dims[0] = x2.shape[1]
+        for i in range(L):
+            if Ws[i].shape[1] != d.dims[i]:
+                raise RuntimeError("gantts_b200: MLP layer %d expects %d inputs, got %d" % (i, Ws[i].shape[1], d.dims[i]))
+            d.dims[i + 1] = Ws[i].shape[0]
+            d.W[i] = Ws[i].data_ptr()
+            d.b[i] = bs[i].data_ptr()
+        d.slope, d.dropout_p, d.last_act, d.seed = float(slope), float(p), int(last_act), int(seed)
+        N = d.dims[L]
+        y = torch.empty(M, N, dtype=torch.float32, device=x.device)
+        tape = torch.empty(lib.gantts_mlp_tape_bytes(ctypes.byref(d), M), dtype=torch.uint8, device=x.device)
+        _lib.check(lib.gantts_mlp_fwd(ctypes.byref(d), x2.data_ptr(), xrs, M, y.data_ptr(), N, tape.data_ptr(),
+                                      tape.numel(), _stream()))
+        ctx.save_for_backward(tape, y, *Ws, *bs)
+        ctx.cfg = (d.dims[:L + 1], float(slope), float(p), int(last_act), int(seed), tuple(x.shape))
+        return y.view(x.shape[:-1] + (N,))
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = _lib.load()
+        saved = ctx.saved_tensors
+        tape, y = saved[0], saved[1]
+        dims, slope, p, last_act, seed, xshape = ctx.cfg
+        L = len(dims) - 1
+        Ws, bs = saved[2:2 + L], saved[2 + L:2 + 2 * L]
+        d = _lib.MlpT()
+        d.num_layers = L
+        for i, v in enumerate(dims):
+            d.dims[i] = v
+        for i in range(L):
+            d.W[i], d.b[i] = Ws[i].data_ptr(), bs[i].data_ptr()
+        d.slope, d.dropout_p, d.last_act, d.seed = slope, p, last_act, seed
+        gy2, gyrs = _rows2d(gy)
+        M = gy2.shape[0]
+        dev = gy.device
+        need_gx = ctx.needs_input_grad[0]
+        gx = torch.empty(M, dims[0], dtype=torch.float32, device=dev) if need_gx else None
+        gWs = [torch.empty_like(W) if ctx.needs_input_grad[5 + 2 * i] else None for i, W in enumerate(Ws)]
+        gbs = [torch.empty_like(b) if ctx.needs_input_grad[6 + 2 * i] else None for i, b in enumerate(bs)]
+        arr = lambda ts: (ctypes.c_void_p * L)(*[t.data_ptr() if t is not None else None for t in ts])
+        ws = workspace(lib.gantts_mlp_workspace_bytes(ctypes.byref(d), M), dev, "mlp")
+        _lib.check(lib.gantts_mlp_bwd(ctypes.byref(d), gy2.data_ptr(), gyrs, y.data_ptr(), dims[L], M,
+                                      tape.data_ptr(), tape.numel(), gx.data_ptr() if gx is not None else None,
+                                      dims[0], arr(gWs), arr(gbs), 0, ws.data_ptr(), ws.numel(), _stream()))
+        grads = []
+        for i in range(L):
+            grads += [gWs[i], gbs[i]]
+        return (gx.view(xshape) if gx is not None else None, None, None, None, None) + tuple(grads)
+
+
+def mlp_stack(x, weights, biases, p=0.0, training=False, last_act=_lib.ACT_NONE, slope=LEAKY_SLOPE, seed=None):
+    """Whole MLP (hidden: Linear -> LeakyReLU -> Dropout; last: Linear [-> sigmoid]) on the tcgen05
+    engine.  reference gantts/models.py:137-141."""
+    p_eff = float(p) if training else 0.0
+    if p_eff > 0.0 and seed is None:
+        seed = draw_seed()
+    params = []
+    for W, b in zip(weights, biases):
+        params += [W, b]
+    return _MLPStack.apply(x, float(slope), p_eff, int(last_act), int(seed or 0), *params)
+
+
 def highway_combine(x_static, Tx, Gx):
     """y = x_static + Tx * Gx (reference gantts/models.py:69)."""
     require_cuda(x_static, Tx, Gx)

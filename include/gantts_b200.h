@@ -184,6 +184,37 @@ int gantts_linear_bwd(const float* gy, int64_t gy_rstride, const float* y, int64
                       int engine, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Whole MLP on the tensor-core engine (reference gantts/models.py:121-141 MLP, used as generator and
+ * discriminator): hidden layers Linear -> LeakyReLU(slope) -> Dropout(p), then last_linear with
+ * last_act (NONE or SIGMOID).  Activations stay resident as bf16 hi/lo planes between layers; the
+ * caller-owned `tape` keeps them (plus the split weights) for the backward.  dropout_p = 0 in eval
+ * mode; hidden layer l draws its mask from seed + golden-ratio * (l+1).
+ */
+typedef struct {
+  int num_layers;                     /* linear layers including last_linear, 1..GANTTS_MAX_LAYERS */
+  int dims[GANTTS_MAX_LAYERS + 1];    /* dims[0] = in ... dims[num_layers] = out */
+  const float* W[GANTTS_MAX_LAYERS];  /* W[l]: [dims[l+1]][dims[l]] row-major (nn.Linear layout) */
+  const float* b[GANTTS_MAX_LAYERS];  /* b[l]: [dims[l+1]], 16-byte aligned */
+  float slope;
+  float dropout_p;
+  int last_act;
+  uint64_t seed;
+} gantts_mlp_t;
+
+size_t gantts_mlp_tape_bytes(const gantts_mlp_t* mlp, int64_t M);
+size_t gantts_mlp_workspace_bytes(const gantts_mlp_t* mlp, int64_t M);
+/* y[M][dims[L]] = MLP(x[M][dims[0]]); fills `tape`. */
+int gantts_mlp_fwd(const gantts_mlp_t* mlp, const float* x, int64_t x_rstride, int64_t M, float* y,
+                   int64_t y_rstride, void* tape, size_t tape_bytes, void* stream);
+/* Backward from gy = dL/dy.  y is the forward output (needed for SIGMOID, may be NULL otherwise).
+ * gW[l] / gb[l] (host arrays of device pointers, entries may be NULL) receive (+= when accumulate)
+ * the parameter gradients; gx (may be NULL) receives dL/dx. */
+int gantts_mlp_bwd(const gantts_mlp_t* mlp, const float* gy, int64_t gy_rstride, const float* y,
+                   int64_t y_rstride, int64_t M, const void* tape, size_t tape_bytes, float* gx,
+                   int64_t gx_rstride, float* const* gW, float* const* gb, int accumulate,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Gradient clipping + Adagrad (torch.nn.utils.clip_grad_norm_ + torch.optim.Adagrad as used at
  * reference train.py:275-276,317-318 with hparams.py:223-227,240-244).  Operates on a list of
  * parameter tensors given as device pointer arrays.
