@@ -196,9 +196,28 @@ def run_b200_arm(args):
     md = gantts_b200.models.MLP(w["d_in_adv"], 1, w["d_layers"], w["d_hidden"], dropout=w["dropout_d"],
                                 last_sigmoid=True).to(dev).train()
     hp = gstep.TTS_ACOUSTIC
-    trainer = gstep.GanTrainer(mg, md, hp, w_d=1.0, mse_w=0.0, mge_w=1.0)
-    R = torch.from_numpy(unit_variance_mlpg_matrix(hp.windows, w["T"])).to(dev)
     lengths = torch.full((w["B"],), w["T"], dtype=torch.int64, device=dev)
+    frames_global = w["B"] * w["T"] * world
+
+    class Runner(object):
+        """path 'fused': gantts_gan_step (one C call per mini-batch); 'modular': GanTrainer."""
+
+        def __init__(self):
+            if args.path == "fused":
+                from gantts_b200 import fused
+                self.fs = fused.FusedGanStep(mg, md, hp, w["B"], w["T"], w_d=1.0, mse_w=0.0, mge_w=1.0)
+            else:
+                self.tr = gstep.GanTrainer(mg, md, hp, w_d=1.0, mse_w=0.0, mge_w=1.0)
+                self.R = torch.from_numpy(unit_variance_mlpg_matrix(hp.windows, w["T"])).to(dev)
+
+        def step(self, x, y, lengths, R=None):
+            if args.path == "fused":
+                losses = self.fs.step(x, y, lengths, frames=frames_global)
+                return {"loss_d": losses[0], "loss_mge": losses[4], "loss_adv": losses[5], "loss_g": losses[6]}, None, None
+            return self.tr.step(x, y, lengths, self.R)
+
+    trainer = Runner()
+    R = None
     host = make_batches(w, 1234 + rank, NUM_BATCHES, pinned=True)
     resident = [(x.to(dev), y.to(dev)) for x, y in host]
     frames_per_step = w["B"] * w["T"] * world
@@ -313,12 +332,13 @@ def run_b200_arm(args):
             "data": "synthetic", "config": workload_config(w, args.engine), "clocks": clocks,
             "e2e": {"value": frames_per_step / (e2e_ms * 1e-3), "unit": "frames/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16,
-                    "how": "pinned host x,y -> double-buffered cudaMemcpyAsync on a copy stream -> GanTrainer.step "
-                           "-> 4 loss scalars D2H; copies inside the timed region"},
+                    "how": "pinned host x,y -> double-buffered cudaMemcpyAsync on a copy stream -> one step through the "
+                           "public API (%s) -> 4 loss scalars D2H; copies inside the timed region" % args.path},
             "gpu_launches": int(launches), "gpu_launches_per_step": launches / args.steps,
             "algorithmic_gflop_per_step": algorithmic_flops_per_frame(w) * w["B"] * w["T"] / 1e9,
             "step_tflops_algorithmic": algorithmic_flops_per_frame(w) * frames_per_step / (ms_per_step * 1e-3) / 1e12 / world,
-            "roofline": roofline, "loss_g_last": loss_g, "path": "GanTrainer (python-orchestrated native ops)"}
+            "roofline": roofline, "loss_g_last": loss_g,
+            "path": "gantts_gan_step (one C call per mini-batch)" if args.path == "fused" else "GanTrainer (python-orchestrated native ops)"}
     if cb is not None:
         line["cpu_baseline"] = cb
     print(json.dumps(line), flush=True)
@@ -332,6 +352,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--engine", default=os.environ.get("GANTTS_B200_ENGINE", "tc"), choices=["tc", "simt"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--path", default="fused", choices=["fused", "modular"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

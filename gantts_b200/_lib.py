@@ -51,6 +51,26 @@ class MlpT(ctypes.Structure):
                 ("seed", ctypes.c_uint64)]
 
 
+MAX_COLS = 256
+
+
+class GanStepT(ctypes.Structure):
+    _fields_ = [("B", ctypes.c_int), ("T", ctypes.c_int),
+                ("g", MlpT), ("d", MlpT),
+                ("g_sumW", ctypes.c_void_p * MAX_LAYERS), ("g_sumb", ctypes.c_void_p * MAX_LAYERS),
+                ("d_sumW", ctypes.c_void_p * MAX_LAYERS), ("d_sumb", ctypes.c_void_p * MAX_LAYERS),
+                ("streams", StreamsT), ("windows", WindowsT),
+                ("mlpg_table", ctypes.c_void_p),
+                ("n_static", ctypes.c_int), ("n_static_cols", ctypes.c_int),
+                ("static_cols", ctypes.c_int * MAX_COLS),
+                ("n_adv", ctypes.c_int), ("adv_cols", ctypes.c_int * MAX_COLS),
+                ("d_conditioned", ctypes.c_int),
+                ("lr_g", ctypes.c_float), ("lr_d", ctypes.c_float), ("wd_g", ctypes.c_float),
+                ("wd_d", ctypes.c_float), ("eps", ctypes.c_float), ("max_norm", ctypes.c_float),
+                ("w_d", ctypes.c_float), ("mse_w", ctypes.c_float), ("mge_w", ctypes.c_float),
+                ("adv_w", ctypes.c_float)]
+
+
 _lib = None
 
 _vp, _i, _i64, _f, _u64, _sz = (ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float,
@@ -87,6 +107,10 @@ SIGNATURES = {
     "gantts_mlp_fwd": (_i, [ctypes.POINTER(MlpT), _vp, _i64, _i64, _vp, _i64, _vp, _sz, _vp]),
     "gantts_mlp_bwd": (_i, [ctypes.POINTER(MlpT), _vp, _i64, _vp, _i64, _i64, _vp, _sz, _vp, _i64, _vp, _vp,
                             _i, _vp, _sz, _vp]),
+    "gantts_gan_step_workspace_bytes": (_sz, [ctypes.POINTER(GanStepT)]),
+    "gantts_gan_step_grad_buffer": (_i, [ctypes.POINTER(GanStepT), _vp, _i, ctypes.POINTER(ctypes.c_void_p),
+                                         ctypes.POINTER(ctypes.c_int64)]),
+    "gantts_gan_step": (_i, [ctypes.POINTER(GanStepT), _i, _vp, _vp, _vp, _f, _u64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "gantts_optim_workspace_bytes": (_sz, []),
     "gantts_grad_sumsq": (_i, [_vp, _vp, _i, _vp, _vp, _sz, _vp]),
     "gantts_clip_adagrad_step": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _f, _f, _f, _f, _vp]),

@@ -53,6 +53,9 @@ struct GemmParams {
   // saved activation (EPI_PLANES_BWD)
   const __nv_bfloat16* h_hi;
   int64_t h_pitch;
+  // MN-major only: column sums of A (= bias gradient) via an extra N=16 MMA against a tile of ones
+  float* db;            // [num_z][rows_a] partial sums, or null
+  uint32_t ones_off;    // byte offset of the 8 KB all-ones bf16 tile from the aligned smem base
   // epilogue math
   const float* bias;
   int act;
@@ -84,7 +87,7 @@ __device__ __forceinline__ void store_planes8(const float* v, __nv_bfloat16* hi,
 // One 16-column chunk of one output row: registers (fp32 accumulators) -> global.
 template <int EPI>
 __device__ __forceinline__ void epilogue_chunk16(const GemmParams& p, const uint32_t (&r)[16], int64_t row,
-                                                 int col, int z) {
+                                                 int col, int z, const uint4& hv0, const uint4& hv1) {
   float v[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
@@ -154,11 +157,10 @@ __device__ __forceinline__ void epilogue_chunk16(const GemmParams& p, const uint
   } else {  // EPI_PLANES_BWD: gz = g * act'(h), derivative recovered from the saved output's hi plane
     const float dpos = p.keep_scale, dneg = p.slope * p.keep_scale;
     const float dzero = p.thresh ? 0.f : p.slope;
-    const __nv_bfloat16* hrow = p.h_hi + row * p.h_pitch + col;
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
-      if (col + 8 * half + 8 <= p.h_pitch) {
-        const uint4 hv = __ldg(reinterpret_cast<const uint4*>(hrow + 8 * half));
+      {
+        const uint4 hv = half ? hv1 : hv0;      // prefetched at tile start (zeros beyond the pitch)
         const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -185,7 +187,8 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
-  const uint32_t bar_base = base + p.num_stages * p.stage_bytes;
+  const uint32_t ones_base = base + p.ones_off;                       // MN only (8 KB), else unused
+  const uint32_t bar_base = base + p.num_stages * p.stage_bytes + (MN ? 8192u : 0u);
   const uint32_t full0 = bar_base, empty0 = bar_base + 8 * TC_MAX_STAGES;
   const uint32_t tfull0 = bar_base + 16 * TC_MAX_STAGES, tempty0 = tfull0 + 16;
   const uint32_t tmem_slot = tempty0 + 16;
@@ -209,6 +212,12 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
   if (warp == 1) {
     ptx::tmem_alloc(tmem_slot, p.tmem_cols);
     ptx::tmem_relinquish();
+  }
+  if (MN && p.db) {
+    // all-ones bf16 tile (any swizzle of a constant tile is the same tile)
+    uint32_t* ones = reinterpret_cast<uint32_t*>(smem_raw + (ones_base - raw));
+    for (int i = threadIdx.x; i < 8192 / 4; i += TC_THREADS) ones[i] = 0x3F803F80u;
+    ptx::fence_proxy_async();
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -267,11 +276,17 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
         const int z = tile / tiles_ab;
         const int64_t r_beg = (int64_t)z * p.red_chunk;
         const int64_t r_end = r_beg + p.red_chunk < p.red ? r_beg + p.red_chunk : p.red;
-        const int acc = it & 1;
-        const uint32_t aph = (it >> 1) & 1;
+        // K-major: two accumulators (epilogue of tile i overlaps MMAs of tile i+1); MN-major: one
+        // accumulator at columns [0,256) plus the bias-gradient accumulator at columns [256,272).
+        const int acc = MN ? 0 : (it & 1);
+        const uint32_t aph = MN ? (it & 1) : ((it >> 1) & 1);
         ptx::mbar_wait(tempty0 + 8 * acc, aph ^ 1);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256;
+        const int rem_i = tile - z * tiles_ab;
+        const bool do_db = MN && p.db != nullptr && (rem_i % p.num_b) == 0;
+        const uint32_t idesc_db = ptx::make_idesc_bf16(TC_BM, 16, 1, 1);
+        const uint64_t d_ones = ptx::make_smem_desc(ones_base, lbo, 1024);
         uint32_t first = 0;
         for (int64_t r0 = r_beg; r0 < r_end; r0 += TC_BK) {
           ptx::mbar_wait(full0 + 8 * s, ph);
@@ -285,6 +300,10 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
             const uint64_t db_hi = ptx::make_smem_desc(sb_hi + k * kstep, lbo, 1024);
             const uint64_t db_lo = ptx::make_smem_desc(sb_lo + k * kstep, lbo, 1024);
             ptx::mma_bf16_ss(d_tmem, da_hi, db_hi, idesc, first);
+            if (do_db) {
+              ptx::mma_bf16_ss(tmem_base + 256, da_hi, d_ones, idesc_db, first);
+              ptx::mma_bf16_ss(tmem_base + 256, da_lo, d_ones, idesc_db, 1);
+            }
             first = 1;
             ptx::mma_bf16_ss(d_tmem, da_hi, db_lo, idesc, 1);
             ptx::mma_bf16_ss(d_tmem, da_lo, db_hi, idesc, 1);
@@ -306,24 +325,52 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int z = tile / tiles_ab, rem = tile - z * tiles_ab;
       const int ta = rem / p.num_b, tb = rem - ta * p.num_b;
-      const int acc = it & 1;
-      const uint32_t aph = (it >> 1) & 1;
-      ptx::mbar_wait(tfull0 + 8 * acc, aph);
-      ptx::tc_fence_after();
+      const int acc = MN ? 0 : (it & 1);
+      const uint32_t aph = MN ? (it & 1) : ((it >> 1) & 1);
       const int64_t row = (int64_t)ta * TC_BM + q * 32 + lane;
       const int col0 = tb * p.bn;
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256;
       const bool row_ok = row < p.rows_a;
-      for (int c = cbeg; c < cend; c += 32) {
-        uint32_t r0[16], r1[16];
-        const bool two = c + 32 <= cend;
-        ptx::tmem_ld16(taddr + c, r0);
-        if (two) ptx::tmem_ld16(taddr + c + 16, r1);
-        ptx::tmem_ld_wait();
-        if (row_ok) {
-          if (col0 + c < p.cols_b) epilogue_chunk16<EPI>(p, r0, row, col0 + c, z);
-          if (two && col0 + c + 16 < p.cols_b) epilogue_chunk16<EPI>(p, r1, row, col0 + c + 16, z);
+      // EPI_PLANES_BWD: fetch this thread's slice of the saved activation BEFORE waiting for the
+      // accumulator, so the (row-strided, uncoalesced) loads overlap the MMAs of this tile.
+      uint4 hpre[16];
+      if (EPI == EPI_PLANES_BWD) {
+        const __nv_bfloat16* hrow = p.h_hi + row * p.h_pitch + col0 + cbeg;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int c = col0 + cbeg + 8 * i;
+          hpre[i] = (row_ok && cbeg + 8 * i < cend && c + 8 <= p.h_pitch)
+                        ? __ldg(reinterpret_cast<const uint4*>(hrow + 8 * i))
+                        : make_uint4(0u, 0u, 0u, 0u);
         }
+      }
+      ptx::mbar_wait(tfull0 + 8 * acc, aph);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256;
+#pragma unroll
+      for (int ci = 0; ci < 4; ++ci) {
+        const int c = cbeg + 32 * ci;
+        if (c < cend) {
+          uint32_t r0[16], r1[16];
+          const bool two = c + 32 <= cend;
+          ptx::tmem_ld16(taddr + c, r0);
+          if (two) ptx::tmem_ld16(taddr + c + 16, r1);
+          ptx::tmem_ld_wait();
+          if (row_ok) {
+            const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+            if (col0 + c < p.cols_b)
+              epilogue_chunk16<EPI>(p, r0, row, col0 + c, z, EPI == EPI_PLANES_BWD ? hpre[4 * ci] : z4,
+                                    EPI == EPI_PLANES_BWD ? hpre[4 * ci + 1] : z4);
+            if (two && col0 + c + 16 < p.cols_b)
+              epilogue_chunk16<EPI>(p, r1, row, col0 + c + 16, z, EPI == EPI_PLANES_BWD ? hpre[4 * ci + 2] : z4,
+                                    EPI == EPI_PLANES_BWD ? hpre[4 * ci + 3] : z4);
+          }
+        }
+      }
+      if (MN && p.db != nullptr && tb == 0 && chalf == 0) {
+        uint32_t r0[16];
+        ptx::tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + 256, r0);
+        ptx::tmem_ld_wait();
+        if (row_ok) p.db[(int64_t)z * p.rows_a + row] = __uint_as_float(r0[0]);
       }
       ptx::tc_fence_before();
       __syncwarp();
@@ -492,7 +539,7 @@ static void fill_epilogue(GemmParams& p, const EpiArgs& e) {
 template <bool MN, int EPI>
 static int launch_kernel(const CUtensorMap& mAh, const CUtensorMap& mAl, const CUtensorMap& mBh,
                          const CUtensorMap& mBl, const GemmParams& p, cudaStream_t st) {
-  const size_t smem = (size_t)p.num_stages * p.stage_bytes + 1024 + 256;
+  const size_t smem = (size_t)p.num_stages * p.stage_bytes + (MN ? 8192 : 0) + 1024 + 256;
   static bool attr = false;
   if (!attr) {
     GANTTS_CUDA(cudaFuncSetAttribute(gemm_bf16x3_kernel<MN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -559,10 +606,11 @@ static size_t mn_partial_bytes(int64_t red, int rows_a, int cols_b, int* splits_
   splits = (red + chunk - 1) / chunk;
   if (splits_out) *splits_out = (int)splits;
   if (chunk_out) *chunk_out = chunk;
-  return ((size_t)splits * rows_a * cols_b * sizeof(float) + 255) / 256 * 256;
+  return ((size_t)splits * ((size_t)rows_a * cols_b + rows_a) * sizeof(float) + 255) / 256 * 256;
 }
 
-static int launch_gemm_mn(const Planes& A, const Planes& B, float* C, int accumulate, float* partial,
+// gb (optional) receives the column sums of A (the bias gradient) from the same launch.
+static int launch_gemm_mn(const Planes& A, const Planes& B, float* C, float* gb, int accumulate, float* partial,
                           cudaStream_t st) {
   GemmParams p{};
   p.rows_a = A.cols;
@@ -584,16 +632,20 @@ static int launch_gemm_mn(const Planes& A, const Planes& B, float* C, int accumu
   p.b_plane_bytes = (uint32_t)nb_atoms * 8192;
   p.stage_bytes = 2 * TC_A_PLANE + 2 * p.b_plane_bytes;
   p.tx_bytes = p.stage_bytes;
-  p.num_stages = (int)((220 * 1024) / p.stage_bytes);
+  p.num_stages = (int)((212 * 1024) / p.stage_bytes);
   if (p.num_stages > TC_MAX_STAGES) p.num_stages = TC_MAX_STAGES;
+  p.ones_off = (uint32_t)p.num_stages * p.stage_bytes;
   p.tmem_cols = 512;
   const bool direct = (splits == 1 && !accumulate);
+  const int64_t n = (int64_t)p.rows_a * p.cols_b;
+  float* db_partial = partial + (int64_t)splits * n;
   EpiArgs e;
   e.epi = EPI_F32;
   e.C = direct ? C : partial;
   e.ldc = p.cols_b;
   fill_epilogue(p, e);
-  p.c_zstride = (int64_t)p.rows_a * p.cols_b;
+  p.c_zstride = n;
+  p.db = gb ? (direct ? gb : db_partial) : nullptr;
   CUtensorMap mAh, mAl, mBh, mBl;
   int rc;
   if ((rc = make_map(&mAh, A.hi, A.rows, A.cols, A.pitch, TC_BK))) return rc;
@@ -602,9 +654,13 @@ static int launch_gemm_mn(const Planes& A, const Planes& B, float* C, int accumu
   if ((rc = make_map(&mBl, B.lo, B.rows, B.cols, B.pitch, TC_BK))) return rc;
   if ((rc = launch_kernel<true, EPI_F32>(mAh, mAl, mBh, mBl, p, st))) return rc;
   if (!direct) {
-    int64_t n = (int64_t)p.rows_a * p.cols_b;
-    splitk_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(partial, splits, n, C, accumulate);
+    splitk_reduce_kernel<<<(unsigned)((n + 1023) / 1024), 256, 0, st>>>(partial, splits, n, C, accumulate);
     GANTTS_LAUNCH_CHECK("splitk_reduce_kernel(tc gW)");
+    if (gb) {
+      splitk_reduce_kernel<<<(unsigned)((p.rows_a + 1023) / 1024), 256, 0, st>>>(db_partial, splits, p.rows_a, gb,
+                                                                               accumulate);
+      GANTTS_LAUNCH_CHECK("splitk_reduce_kernel(tc gb)");
+    }
   }
   return GANTTS_OK;
 }
@@ -667,7 +723,7 @@ int tc_linear_bwd_gemms(const float* gz, const float* x, int64_t x_rs, const flo
   }
   if (gW) {
     if ((rc = launch_split(x, x_rs, M, K, X, 0, st))) return rc;
-    if ((rc = launch_gemm_mn(G, X, gW, accumulate, partial, st))) return rc;
+    if ((rc = launch_gemm_mn(G, X, gW, nullptr, accumulate, partial, st))) return rc;
   }
   return GANTTS_OK;
 }

@@ -8,3 +8,4 @@
 #include "mlp_tc.cu"
 #include "linear.cu"
 #include "optim.cu"
+#include "gan_step.cu"

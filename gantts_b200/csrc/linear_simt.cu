@@ -96,14 +96,32 @@ sgemm_kernel(const float* __restrict__ A, int64_t a_si, int64_t a_sk, const floa
   }
 }
 
-// out[i] (+)= sum_z partial[z][i]
+// out[i] (+)= sum_z partial[z][i]   (deterministic: fixed summation order over z)
 __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int nsplit, int64_t n,
                                      float* __restrict__ out, int accumulate) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  float s = 0.f;
-  for (int z = 0; z < nsplit; ++z) s += partial[(int64_t)z * n + i];
-  out[i] = accumulate ? out[i] + s : s;
+  const int64_t i4 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i4 >= n) return;
+  const bool vec = (n & 3) == 0 && ((reinterpret_cast<uintptr_t>(partial) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+  if (vec) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int z = 0; z < nsplit; ++z) {
+      const float4 v = *reinterpret_cast<const float4*>(partial + (int64_t)z * n + i4);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    float4* o = reinterpret_cast<float4*>(out + i4);
+    if (accumulate) {
+      const float4 c = *o;
+      s.x += c.x; s.y += c.y; s.z += c.z; s.w += c.w;
+    }
+    *o = s;
+  } else {
+    for (int64_t i = i4; i < i4 + 4 && i < n; ++i) {
+      float s = 0.f;
+      for (int z = 0; z < nsplit; ++z) s += partial[(int64_t)z * n + i];
+      out[i] = accumulate ? out[i] + s : s;
+    }
+  }
 }
 
 // gz = gy * act'(y), derivative recovered from the saved layer OUTPUT y.
@@ -211,7 +229,7 @@ int colsum(const float* gz, int64_t M, int N, float* gb, int accumulate, float* 
   dim3 grid((N + 31) / 32, chunks);
   colsum_partial_kernel<<<grid, 256, 0, st>>>(gz, M, N, rpc, partial);
   GANTTS_LAUNCH_CHECK("colsum_partial_kernel");
-  splitk_reduce_kernel<<<(N + 255) / 256, 256, 0, st>>>(partial, chunks, N, gb, accumulate);
+  splitk_reduce_kernel<<<(N + 1023) / 1024, 256, 0, st>>>(partial, chunks, N, gb, accumulate);
   GANTTS_LAUNCH_CHECK("splitk_reduce_kernel(colsum)");
   return GANTTS_OK;
 }
@@ -242,7 +260,7 @@ int simt_linear_bwd_gemms(const float* gz, const float* x, int64_t x_rs, const f
                                                   kchunk, ep);
       GANTTS_LAUNCH_CHECK("sgemm_kernel(gW split)");
       int64_t n = (int64_t)N * K;
-      splitk_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ws, (int)s, n, gW, accumulate);
+      splitk_reduce_kernel<<<(unsigned)((n + 1023) / 1024), 256, 0, st>>>(ws, (int)s, n, gW, accumulate);
       GANTTS_LAUNCH_CHECK("splitk_reduce_kernel(gW)");
     }
   }

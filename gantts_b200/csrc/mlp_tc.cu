@@ -65,7 +65,7 @@ static int colsum_planes(const Planes& G, float* gb, int accumulate, float* part
   dim3 grid((unsigned)((G.cols + 31) / 32), chunks);
   colsum_planes_partial_kernel<<<grid, 256, 0, st>>>(G.hi, G.lo, G.pitch, G.rows, (int)G.cols, rpc, partial);
   GANTTS_LAUNCH_CHECK("colsum_planes_partial_kernel");
-  splitk_reduce_kernel<<<(unsigned)((G.cols + 255) / 256), 256, 0, st>>>(partial, chunks, G.cols, gb, accumulate);
+  splitk_reduce_kernel<<<(unsigned)((G.cols + 1023) / 1024), 256, 0, st>>>(partial, chunks, G.cols, gb, accumulate);
   GANTTS_LAUNCH_CHECK("splitk_reduce_kernel(colsum planes)");
   return GANTTS_OK;
 }
@@ -215,11 +215,12 @@ extern "C" int gantts_mlp_bwd(const gantts_mlp_t* m, const float* gy, int64_t gy
     GANTTS_LAUNCH_CHECK("grad_out_to_planes_kernel");
   }
   for (int l = L - 1; l >= 0; --l) {
+    float* gbl = (gb && gb[l]) ? gb[l] : nullptr;
     if (gW && gW[l]) {
-      if ((rc = launch_gemm_mn(G, t.H[l], gW[l], accumulate, partial, st))) return rc;
-    }
-    if (gb && gb[l]) {
-      if ((rc = colsum_planes(G, gb[l], accumulate, colpart, st))) return rc;
+      // gW_l and (via the ones-MMA) gb_l from one launch
+      if ((rc = launch_gemm_mn(G, t.H[l], gW[l], gbl, accumulate, partial, st))) return rc;
+    } else if (gbl) {
+      if ((rc = colsum_planes(G, gbl, accumulate, colpart, st))) return rc;
     }
     if (l > 0) {
       char* c1 = gbuf[pp ^ 1];

@@ -80,28 +80,38 @@ mlpg_fwd_kernel(const float* __restrict__ in, int64_t in_bs, int64_t in_ts,
     int r = i / GROW, j = i - r * GROW, t = t0 + r;
     gs[i] = (t < T && j < NTAPS) ? table[(int64_t)t * NTAPS + j] : 0.f;
   }
-  // Phase 1: b = W^T mu over [t0-K, t0+TT+K) (or the raw input for static streams).
-  for (int i = threadIdx.x; i < (TT + 2 * K_HALF) * TC; i += MLPG_THREADS) {
-    int r = i / TC, c = i - r * TC, t = t0 - K_HALF + r;
-    float v = 0.f;
-    ColInfo ci = find_col(st, c0 + c);
-    if (ci.in_col >= 0 && t >= 0 && t < T) {
-      if (!ci.dyn) {
-        v = inb[(int64_t)t * in_ts + ci.in_col];
-      } else {
-#pragma unroll 1
-        for (int w = 0; w < win.n; ++w) {
-          const int l = win.l[w], u = win.u[w];
-          const float* colp = inb + ci.in_col + w * ci.sd;
-          for (int k = -l; k <= u; ++k) {
-            int tt = t - k;
-            float cf = win.coef[w][k + l];
-            if (tt >= 0 && tt < T && cf != 0.f) v = fmaf(cf, colp[(int64_t)tt * in_ts], v);
+  // Phase 1: b = W^T mu over [t0-K, t0+TT+K) (or the raw input for static streams).  Each thread
+  // owns ONE column (stream lookup hoisted) and strides over rows; the tap loops are fully unrolled
+  // and predicated so the (coalesced, 128 B per warp) loads of a row are independent.
+  {
+    const int cx = threadIdx.x & (TC - 1), rg = threadIdx.x / TC;
+    const ColInfo ci = find_col(st, c0 + cx);
+    const float* colp = inb + (ci.in_col >= 0 ? ci.in_col : 0);
+#pragma unroll 2
+    for (int r = rg; r < TT + 2 * K_HALF; r += MLPG_THREADS / TC) {
+      const int t = t0 - K_HALF + r;
+      float v = 0.f;
+      if (ci.in_col >= 0 && t >= 0 && t < T) {
+        if (!ci.dyn) {
+          v = colp[(int64_t)t * in_ts];
+        } else {
+#pragma unroll
+          for (int w = 0; w < GANTTS_MAX_WINDOWS; ++w) {
+            if (w < win.n) {
+              const int l = win.l[w], ntap = win.l[w] + win.u[w] + 1;
+#pragma unroll
+              for (int kk = 0; kk < GANTTS_MAX_WINDOW_TAPS; ++kk) {
+                const int tt = t - (kk - l);
+                const float cf = win.coef[w][kk];
+                if (kk < ntap && cf != 0.f && tt >= 0 && tt < T)
+                  v = fmaf(cf, colp[(int64_t)tt * in_ts + w * ci.sd], v);
+              }
+            }
           }
         }
       }
+      bv[r * TC + cx] = v;
     }
-    bv[i] = v;
   }
   __syncthreads();
   // Phase 2: FIR with the rows of P^-1.
@@ -175,25 +185,37 @@ mlpg_bwd_kernel(const float* __restrict__ go, int64_t go_bs, int64_t go_ts,
   }
   __syncthreads();
   // Phase 3: grad wrt window w of stream column = sum_k coef_w[k+l] z_{t+k}; static: copy g.
-  float* gib = gi + (int64_t)b * gi_bs;
-  const int nw = win.n;
-  for (int i = threadIdx.x; i < nw * TT * TC; i += MLPG_THREADS) {
-    int c = i % TC, r = (i / TC) % TT, w = i / (TC * TT);
-    int t = t0 + r, oc = c0 + c;
-    if (t >= T || oc >= ncols) continue;
-    ColInfo ci = find_col(st, oc);
-    if (ci.in_col < 0) continue;
-    float v;
-    if (!ci.dyn) {
-      if (w != 0) continue;
-      v = gv[(HALO + K_HALF + r) * TC + c];
-    } else {
-      const int l = win.l[w], u = win.u[w];
-      v = 0.f;
-      for (int k = -l; k <= u; ++k) v = fmaf(win.coef[w][k + l], zs[(HALO + r + k) * TC + c], v);
+  // One column per thread (stream lookup hoisted), rows strided, coalesced 128 B stores per warp.
+  {
+    const int cx = threadIdx.x & (TC - 1), rg = threadIdx.x / TC;
+    const int oc = c0 + cx;
+    const ColInfo ci = find_col(st, oc);
+    if (ci.in_col >= 0 && oc < ncols) {
+      float* gib = gi + (int64_t)b * gi_bs + ci.in_col;
+#pragma unroll 2
+      for (int r = rg; r < TT; r += MLPG_THREADS / TC) {
+        const int t = t0 + r;
+        if (t >= T) break;
+        float* prow = gib + (int64_t)t * gi_ts;
+        if (!ci.dyn) {
+          const float v = gv[(HALO + K_HALF + r) * TC + cx];
+          prow[0] = accumulate ? prow[0] + v : v;
+        } else {
+#pragma unroll
+          for (int w = 0; w < GANTTS_MAX_WINDOWS; ++w) {
+            if (w < win.n) {
+              const int l = win.l[w], ntap = win.l[w] + win.u[w] + 1;
+              float v = 0.f;
+#pragma unroll
+              for (int kk = 0; kk < GANTTS_MAX_WINDOW_TAPS; ++kk)
+                if (kk < ntap) v = fmaf(win.coef[w][kk], zs[(HALO + r + kk - l) * TC + cx], v);
+              float* q = prow + w * ci.sd;
+              *q = accumulate ? *q + v : v;
+            }
+          }
+        }
+      }
     }
-    float* p = gib + (int64_t)t * gi_ts + ci.in_col + w * ci.sd;
-    *p = accumulate ? (*p + v) : v;
   }
 }
 

@@ -31,6 +31,7 @@ extern "C" {
 #define GANTTS_MAX_WINDOW_TAPS 5 /* l, u <= 2 */
 #define GANTTS_MLPG_HALF_TAPS 24 /* FIR half width K: P^-1 decays to 2.6e-10 at lag 24 */
 #define GANTTS_MAX_LAYERS 8
+#define GANTTS_MAX_COLS 256 /* static / adversarial column lists of the fused step */
 
 int gantts_version(void);                       /* 100 * major + minor */
 const char* gantts_last_error_string(void);     /* thread-local, never NULL */
@@ -229,6 +230,52 @@ int gantts_grad_sumsq(float* const* grads, const int64_t* sizes_host, int ntenso
 int gantts_clip_adagrad_step(float* const* params, float* const* grads, float* const* state_sums,
                              const int64_t* sizes_host, int ntensors, const float* sumsq_dev,
                              float max_norm, float lr, float weight_decay, float eps, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused GAN training step: one call enqueues the whole mini-batch of reference train.py:528-580
+ * (batch prologue :528-535, apply_generator :336-355, update_discriminator :245-279,
+ * update_generator :282-320, both clip_grad_norm_ + Adagrad steps) on `stream`, no host sync.
+ *
+ * MLP generator (g, linear output) and MLP discriminator (d, one sigmoid output, input = the
+ * `adv_cols` columns of the static features).  Weights (g.W/g.b, d.W/d.b) and the Adagrad
+ * accumulators are updated IN PLACE.  phases is a bit mask so that a data-parallel caller can
+ * all-reduce the gradient buffers (gantts_gan_step_grad_buffer) between the pieces:
+ *   1 = prologue, G forward, MLPG, D forward on [real | fake], loss_d backward  -> D gradients ready
+ *   2 = D clip+Adagrad, MGE/MSE/ADV losses, third D forward, loss_g backward    -> G gradients ready
+ *   4 = G clip+Adagrad, loss scalars
+ * inv_frames = 1 / (GLOBAL number of valid frames) (reference normaliser T = mask.sum()).
+ * losses_dev[12] = loss_d, loss_fake_d, loss_real_d, loss_mse, loss_mge, loss_adv, loss_g,
+ *                  real_correct, fake_correct, local frames, d_grad_norm, g_grad_norm.
+ */
+typedef struct {
+  int B, T;
+  gantts_mlp_t g;                          /* generator: dims[0] = linguistic width, dims[L] = acoustic width */
+  gantts_mlp_t d;                          /* discriminator: dims[0] = n_adv, dims[L] = 1, last_act = SIGMOID */
+  float* g_sumW[GANTTS_MAX_LAYERS];        /* Adagrad state_sum per parameter tensor */
+  float* g_sumb[GANTTS_MAX_LAYERS];
+  float* d_sumW[GANTTS_MAX_LAYERS];
+  float* d_sumb[GANTTS_MAX_LAYERS];
+  gantts_streams_t streams;                /* MLPG stream layout of the generator output */
+  gantts_windows_t windows;
+  const float* mlpg_table;                 /* device copy of gantts_mlpg_table(windows, T) */
+  int n_static;                            /* width of y_hat_static */
+  int n_static_cols;                       /* == n_static */
+  int static_cols[GANTTS_MAX_COLS];        /* columns of y forming y_static (get_static_features) */
+  int n_adv;
+  int adv_cols[GANTTS_MAX_COLS];           /* columns of y_(hat_)static fed to D (select + mask_nth) */
+  int d_conditioned;                       /* must be 0 (linguistic conditioning: use the modular path) */
+  float lr_g, lr_d, wd_g, wd_d, eps, max_norm;
+  float w_d, mse_w, mge_w, adv_w;
+} gantts_gan_step_t;
+
+size_t gantts_gan_step_workspace_bytes(const gantts_gan_step_t* cfg);
+/* Flat gradient buffer inside `workspace` (which: 0 = generator, 1 = discriminator). */
+int gantts_gan_step_grad_buffer(const gantts_gan_step_t* cfg, void* workspace, int which, float** ptr,
+                                int64_t* count);
+int gantts_gan_step(const gantts_gan_step_t* cfg, int phases, const float* x, const float* y,
+                    const int64_t* lengths_dev, float inv_frames, uint64_t seed, float* y_hat,
+                    float* y_hat_static, float* losses_dev, void* workspace, size_t workspace_bytes,
+                    void* stream);
 
 #ifdef __cplusplus
 }

@@ -528,3 +528,84 @@ def test_mlp_stack_sigmoid_single_output(dev, slope):
     else:
         errs = {n: _frob(a, b) for n, a, b in pairs}
         assert errs["y"] < 1e-4 and max(errs.values()) < 2e-2, errs
+
+
+# --------------------------------------------------------------------------- fused step
+def _fused_vs_oracle(dev, B, Tn, lens, g_dims, d_hidden, steps=2, mse_w=0.0):
+    import gantts_b200
+    from gantts_b200 import step as gstep, fused
+    torch.manual_seed(11)
+    mg = gantts_b200.models.MLP(g_dims[0], 187, len(g_dims) - 1, g_dims[1], dropout=0.0, last_sigmoid=False)
+    md = gantts_b200.models.MLP(58, 1, 3, d_hidden, dropout=0.0, last_sigmoid=True)
+    names = ["layers.%d" % i for i in range(len(g_dims) - 1)] + ["last_linear"]
+    dnames = ["layers.0", "layers.1", "layers.2", "last_linear"]
+    lay = lambda m, ns: [(m.state_dict()[n + ".weight"].clone(), m.state_dict()[n + ".bias"].clone()) for n in ns]
+    state = gp.GanStepState(lay(mg, names), lay(md, dnames))
+    R = torch.from_numpy(nnp.unit_variance_mlpg_matrix(WINDOWS, Tn))
+    mg.to(dev), md.to(dev)
+    fs = fused.FusedGanStep(mg, md, gstep.TTS_ACOUSTIC, B, Tn, w_d=1.0, mse_w=mse_w, mge_w=1.0)
+    worst = {}
+    for it in range(steps):
+        x = torch.rand(B, Tn, g_dims[0]) * 0.98 + 0.01
+        y = torch.randn(B, Tn, 187)
+        for b, n in enumerate(lens):
+            x[b, n:] = 0
+            y[b, n:] = 0
+        ref, yh_ref, ys_ref = gp.gan_step_mlp(state, x, y, lens, R, TTS_HP, mse_w=mse_w)
+        fs.step(x.to(dev), y.to(dev), torch.LongTensor(lens).to(dev), frames=sum(lens))
+        got = fs.loss_dict()
+        errs = {k: abs(got[k] - ref[k]) / abs(ref[k]) for k in ("loss_d", "loss_fake_d", "loss_real_d", "loss_mge",
+                                                                 "loss_mse", "loss_adv", "loss_g", "d_grad_norm",
+                                                                 "g_grad_norm")}
+        errs["y_hat"] = rel_err(npy(fs.y_hat), yh_ref.numpy())
+        errs["y_hat_static"] = rel_err(npy(fs.y_hat_static), ys_ref.numpy())
+        assert got["real_correct"] == ref["real_correct"] and got["fake_correct"] == ref["fake_correct"]
+        assert got["frames"] == float(sum(lens))
+        for k, v in errs.items():
+            worst[k] = max(worst.get(k, 0.0), v)
+    return worst, mg, md, state
+
+
+def test_fused_gan_step_small_vs_oracle(dev):
+    """gantts_gan_step (ONE C call per mini-batch) against the oracle port of train.py's step
+    functions: two consecutive mini-batches, ragged lengths, all losses / grad norms / outputs."""
+    worst, mg, md, state = _fused_vs_oracle(dev, 4, 30, [30, 27, 21, 16], [20, 32, 32, 32], 16)
+    assert max(worst.values()) < 1e-4, worst
+
+
+def test_fused_gan_step_cfg2_shapes_vs_oracle(dev):
+    """BASELINE cfg2 layer shapes (G 425-512-512-512-187, D 58-256-256-256-1), B=4 x T=250, mse_w>0."""
+    worst, mg, md, state = _fused_vs_oracle(dev, 4, 250, [250, 222, 180, 131], [425, 512, 512, 512], 256, steps=1,
+                                            mse_w=0.5)
+    assert max(worst.values()) < 1e-4, worst
+    # post-step weights (Adagrad's first step = lr * sign(g): ill-conditioned where g ~ 0, see above)
+    dW = np.abs(npy(mg.layers[1].weight) - state.g[1][0].detach().numpy())
+    assert np.median(dW) < 1e-6 and dW.max() <= 0.0201, (np.median(dW), dW.max())
+    dD = np.abs(npy(md.layers[1].weight) - state.d[1][0].detach().numpy())
+    assert np.median(dD) < 1e-6 and dD.max() <= 0.0201, (np.median(dD), dD.max())
+
+
+def test_fused_step_matches_modular_trainer_with_dropout(dev):
+    """Statistical check in TRAIN mode with dropout 0.5 (masks differ between the two paths by
+    construction): the fused step and GanTrainer see the same loss levels on the same batch."""
+    import gantts_b200
+    from gantts_b200 import step as gstep, fused
+    torch.manual_seed(3)
+    B, Tn = 8, 200
+    def models():
+        torch.manual_seed(5)
+        g = gantts_b200.models.MLP(425, 187, 3, 512, dropout=0.5, last_sigmoid=False).to(dev).train()
+        d = gantts_b200.models.MLP(58, 1, 3, 256, dropout=0.5, last_sigmoid=True).to(dev).train()
+        return g, d
+    x = torch.rand(B, Tn, 425, device=dev)
+    y = torch.randn(B, Tn, 187, device=dev)
+    lens = torch.full((B,), Tn, dtype=torch.int64, device=dev)
+    R = T(nnp.unit_variance_mlpg_matrix(WINDOWS, Tn), dev)
+    g1, d1 = models()
+    out, _, _ = gstep.GanTrainer(g1, d1, gstep.TTS_ACOUSTIC).step(x, y, lens, R)
+    g2, d2 = models()
+    fs = fused.FusedGanStep(g2, d2, gstep.TTS_ACOUSTIC, B, Tn)
+    fs.step(x, y, lens, frames=B * Tn)
+    got = fs.loss_dict()
+    for k in ("loss_d", "loss_mge", "loss_adv", "loss_g"):
+        assert abs(got[k] - float(out[k])) <= 0.03 * abs(float(out[k])), (k, got[k], float(out[k]))
