@@ -27,6 +27,7 @@ constexpr int TC_BM = 128;          // MMA M (TMEM lanes)
 constexpr int TC_BK = 64;           // reduction elements per stage (one 128B swizzle atom of bf16)
 constexpr int TC_MAX_STAGES = 4;
 constexpr uint32_t TC_A_PLANE = TC_BM * TC_BK * 2;   // 16 KB
+constexpr uint32_t TC_BIAS_SMEM = 4096;              // staged bias vector (<= 1024 columns)
 
 // Epilogue flavours (template parameter of the kernel).
 constexpr int EPI_F32 = 0;          // bias + {none | leaky+dropout | sigmoid} -> fp32 C (optionally +=)
@@ -50,9 +51,11 @@ struct GemmParams {
   // planes output (EPI_PLANES_*)
   __nv_bfloat16 *out_hi, *out_lo;
   int64_t out_pitch;
-  // saved activation (EPI_PLANES_BWD)
-  const __nv_bfloat16* h_hi;
-  int64_t h_pitch;
+  // activation-derivative code plane: 2 bits per element (bit0 = zero/dropped, bit1 = negative), one
+  // uint32 per (row, 16 columns).  Written by EPI_PLANES_FWD, read (prefetched) by EPI_PLANES_BWD.
+  uint32_t* code;
+  int64_t code_pitch;   // words per row
+  uint32_t bias_off;    // byte offset (from the aligned smem base) of the staged bias vector, 0 = none
   // MN-major only: column sums of A (= bias gradient) via an extra N=16 MMA against a tile of ones
   float* db;            // [num_z][rows_a] partial sums, or null
   uint32_t ones_off;    // byte offset of the 8 KB all-ones bf16 tile from the aligned smem base
@@ -85,18 +88,26 @@ __device__ __forceinline__ void store_planes8(const float* v, __nv_bfloat16* hi,
 }
 
 // One 16-column chunk of one output row: registers (fp32 accumulators) -> global.
+// Returns the derivative code word of the chunk (EPI_PLANES_FWD); `code_in` is the saved word (BWD).
 template <int EPI>
-__device__ __forceinline__ void epilogue_chunk16(const GemmParams& p, const uint32_t (&r)[16], int64_t row,
-                                                 int col, int z, const uint4& hv0, const uint4& hv1) {
+__device__ __forceinline__ uint32_t epilogue_chunk16(const GemmParams& p, const uint32_t (&r)[16], int64_t row,
+                                                     int col, int z, const float* __restrict__ bias_s,
+                                                     uint32_t code_in) {
+  uint32_t code = 0;
   float v[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
   if (EPI == EPI_F32) {
     float* crow = p.C + (int64_t)z * p.c_zstride + row * p.ldc;
     if (p.bias) {
+      if (bias_s) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j)
-        if (col + j < p.cols_b) v[j] += __ldg(p.bias + col + j);
+        for (int j = 0; j < 16; ++j) v[j] += bias_s[col + j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (col + j < p.cols_b) v[j] += __ldg(p.bias + col + j);
+      }
     }
     if (p.act == GANTTS_ACT_LEAKY_DROPOUT) {
 #pragma unroll
@@ -127,17 +138,16 @@ __device__ __forceinline__ void epilogue_chunk16(const GemmParams& p, const uint
     }
   } else if (EPI == EPI_PLANES_FWD) {
     // reference gantts/models.py:137-139: Dropout(LeakyReLU(Linear(x)))
+    if (bias_s) {
 #pragma unroll
-    for (int j = 0; j < 16; j += 4) {
-      const int c = col + j;
-      if (c + 3 < p.cols_b) {
-        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + c));
+      for (int j = 0; j < 16; j += 4) {
+        const float4 b4 = *reinterpret_cast<const float4*>(bias_s + col + j);   // broadcast LDS.128
         v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-      } else {
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-          if (c + e < p.cols_b) v[j + e] += __ldg(p.bias + c + e);
       }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (col + j < p.cols_b) v[j] += __ldg(p.bias + col + j);
     }
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], v[j] * p.slope);
@@ -150,33 +160,29 @@ __device__ __forceinline__ void epilogue_chunk16(const GemmParams& p, const uint
         v[j + 1] = (bits >> 16) >= p.thresh ? v[j + 1] * p.keep_scale : 0.f;
       }
     }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      if (v[j] == 0.f) code |= 1u << (2 * j);
+      if (v[j] < 0.f) code |= 2u << (2 * j);
+    }
     __nv_bfloat16* oh = p.out_hi + row * p.out_pitch + col;
     __nv_bfloat16* ol = p.out_lo + row * p.out_pitch + col;
     if (col + 8 <= p.out_pitch) store_planes8(v, oh, ol);
     if (col + 16 <= p.out_pitch) store_planes8(v + 8, oh + 8, ol + 8);
-  } else {  // EPI_PLANES_BWD: gz = g * act'(h), derivative recovered from the saved output's hi plane
+  } else {  // EPI_PLANES_BWD: gz = g * act'(h), derivative class from the saved 2-bit code
     const float dpos = p.keep_scale, dneg = p.slope * p.keep_scale;
     const float dzero = p.thresh ? 0.f : p.slope;
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      {
-        const uint4 hv = half ? hv1 : hv0;      // prefetched at tile start (zeros beyond the pitch)
-        const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const uint32_t lo16 = hw[i] & 0xffffu, hi16 = hw[i] >> 16;
-          const float d0 = (lo16 & 0x7fffu) == 0 ? dzero : ((lo16 & 0x8000u) ? dneg : dpos);
-          const float d1 = (hi16 & 0x7fffu) == 0 ? dzero : ((hi16 & 0x8000u) ? dneg : dpos);
-          v[8 * half + 2 * i] *= d0;
-          v[8 * half + 2 * i + 1] *= d1;
-        }
-      }
+    for (int j = 0; j < 16; ++j) {
+      const uint32_t cj = (code_in >> (2 * j)) & 3u;
+      v[j] *= (cj & 1u) ? dzero : ((cj & 2u) ? dneg : dpos);
     }
     __nv_bfloat16* oh = p.out_hi + row * p.out_pitch + col;
     __nv_bfloat16* ol = p.out_lo + row * p.out_pitch + col;
     if (col + 8 <= p.out_pitch) store_planes8(v, oh, ol);
     if (col + 16 <= p.out_pitch) store_planes8(v + 8, oh + 8, ol + 8);
   }
+  return code;
 }
 
 template <bool MN, int EPI>
@@ -212,6 +218,13 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
   if (warp == 1) {
     ptx::tmem_alloc(tmem_slot, p.tmem_cols);
     ptx::tmem_relinquish();
+  }
+  const float* bias_s = nullptr;
+  if (p.bias_off) {
+    float* bs = reinterpret_cast<float*>(smem_raw + (base + p.bias_off - raw));
+    const int nb = p.num_b * p.bn;                       // zero-padded to whole tiles
+    for (int i = threadIdx.x; i < nb; i += TC_THREADS) bs[i] = i < p.cols_b ? p.bias[i] : 0.f;
+    bias_s = bs;
   }
   if (MN && p.db) {
     // all-ones bf16 tile (any swizzle of a constant tile is the same tile)
@@ -321,6 +334,17 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
     const int q = warp & 3;
     const int chalf = (warp - 2) >> 2;
     const int cbeg = chalf * (p.bn >> 1), cend = cbeg + (p.bn >> 1);
+    uint32_t code_next[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+    if (EPI == EPI_PLANES_BWD && (int)blockIdx.x < total_tiles) {
+      const int nrem = blockIdx.x % tiles_ab;
+      const int64_t nrow = (int64_t)(nrem / p.num_b) * TC_BM + q * 32 + lane;
+      const int ncol0 = (nrem % p.num_b) * p.bn;
+      const uint32_t* cp = p.code + nrow * p.code_pitch + ((ncol0 + cbeg) >> 4);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        code_next[i] = (nrow < p.rows_a && cbeg + 16 * i < cend && ncol0 + cbeg + 16 * i < p.cols_b)
+                           ? __ldg(cp + i) : 0u;
+    }
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int z = tile / tiles_ab, rem = tile - z * tiles_ab;
@@ -330,41 +354,59 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
       const int64_t row = (int64_t)ta * TC_BM + q * 32 + lane;
       const int col0 = tb * p.bn;
       const bool row_ok = row < p.rows_a;
-      // EPI_PLANES_BWD: fetch this thread's slice of the saved activation BEFORE waiting for the
-      // accumulator, so the (row-strided, uncoalesced) loads overlap the MMAs of this tile.
-      uint4 hpre[16];
+      // EPI_PLANES_BWD: this thread's derivative codes (8 words) were prefetched one tile ahead.
+      uint32_t codes[8];
       if (EPI == EPI_PLANES_BWD) {
-        const __nv_bfloat16* hrow = p.h_hi + row * p.h_pitch + col0 + cbeg;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int c = col0 + cbeg + 8 * i;
-          hpre[i] = (row_ok && cbeg + 8 * i < cend && c + 8 <= p.h_pitch)
-                        ? __ldg(reinterpret_cast<const uint4*>(hrow + 8 * i))
-                        : make_uint4(0u, 0u, 0u, 0u);
+        for (int i = 0; i < 8; ++i) codes[i] = code_next[i];
+        // prefetch for the CTA's next tile
+        const int ntile = tile + gridDim.x;
+        if (ntile < total_tiles) {
+          const int nrem = ntile % tiles_ab;
+          const int64_t nrow = (int64_t)(nrem / p.num_b) * TC_BM + q * 32 + lane;
+          const int ncol0 = (nrem % p.num_b) * p.bn;
+          const uint32_t* cp = p.code + nrow * p.code_pitch + ((ncol0 + cbeg) >> 4);
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            code_next[i] = (nrow < p.rows_a && cbeg + 16 * i < cend && ncol0 + cbeg + 16 * i < p.cols_b)
+                               ? __ldg(cp + i) : 0u;
         }
       }
       ptx::mbar_wait(tfull0 + 8 * acc, aph);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256;
+      uint32_t code_out[8];
+      // TMEM loads are software-pipelined: the 32 columns of step ci+1 are in flight while step ci
+      // is processed (tcgen05.wait::ld only covers loads issued before it).
+      uint32_t ra[2][16], rb[2][16];
+      ptx::tmem_ld16(taddr + cbeg, ra[0]);
+      if (cbeg + 32 <= cend) ptx::tmem_ld16(taddr + cbeg + 16, rb[0]);
 #pragma unroll
       for (int ci = 0; ci < 4; ++ci) {
         const int c = cbeg + 32 * ci;
+        code_out[2 * ci] = code_out[2 * ci + 1] = 0u;
         if (c < cend) {
-          uint32_t r0[16], r1[16];
           const bool two = c + 32 <= cend;
-          ptx::tmem_ld16(taddr + c, r0);
-          if (two) ptx::tmem_ld16(taddr + c + 16, r1);
           ptx::tmem_ld_wait();
+          if (ci < 3 && c + 32 < cend) {
+            ptx::tmem_ld16(taddr + c + 32, ra[(ci + 1) & 1]);
+            if (c + 64 <= cend) ptx::tmem_ld16(taddr + c + 48, rb[(ci + 1) & 1]);
+          }
           if (row_ok) {
-            const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
             if (col0 + c < p.cols_b)
-              epilogue_chunk16<EPI>(p, r0, row, col0 + c, z, EPI == EPI_PLANES_BWD ? hpre[4 * ci] : z4,
-                                    EPI == EPI_PLANES_BWD ? hpre[4 * ci + 1] : z4);
+              code_out[2 * ci] = epilogue_chunk16<EPI>(p, ra[ci & 1], row, col0 + c, z, bias_s, codes[2 * ci]);
             if (two && col0 + c + 16 < p.cols_b)
-              epilogue_chunk16<EPI>(p, r1, row, col0 + c + 16, z, EPI == EPI_PLANES_BWD ? hpre[4 * ci + 2] : z4,
-                                    EPI == EPI_PLANES_BWD ? hpre[4 * ci + 3] : z4);
+              code_out[2 * ci + 1] =
+                  epilogue_chunk16<EPI>(p, rb[ci & 1], row, col0 + c + 16, z, bias_s, codes[2 * ci + 1]);
           }
         }
+      }
+      ptx::tmem_ld_wait();
+      if (EPI == EPI_PLANES_FWD && p.code != nullptr && row_ok) {
+        uint32_t* cp = p.code + row * p.code_pitch + ((col0 + cbeg) >> 4);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (cbeg + 16 * i < cend && col0 + cbeg + 16 * i < p.cols_b) cp[i] = code_out[i];
       }
       if (MN && p.db != nullptr && tb == 0 && chalf == 0) {
         uint32_t r0[16];
@@ -509,8 +551,8 @@ struct EpiArgs {
   // EPI_PLANES_*
   __nv_bfloat16 *out_hi = nullptr, *out_lo = nullptr;
   int64_t out_pitch = 0;
-  const __nv_bfloat16* h_hi = nullptr;
-  int64_t h_pitch = 0;
+  uint32_t* code = nullptr;           // derivative code plane (written by PLANES_FWD, read by PLANES_BWD)
+  int64_t code_pitch = 0;
   // math
   const float* bias = nullptr;
   int act = GANTTS_ACT_NONE;
@@ -526,8 +568,8 @@ static void fill_epilogue(GemmParams& p, const EpiArgs& e) {
   p.out_hi = e.out_hi;
   p.out_lo = e.out_lo;
   p.out_pitch = e.out_pitch;
-  p.h_hi = e.h_hi;
-  p.h_pitch = e.h_pitch;
+  p.code = e.code;
+  p.code_pitch = e.code_pitch;
   p.bias = e.bias;
   p.act = e.act;
   p.slope = e.slope;
@@ -539,7 +581,7 @@ static void fill_epilogue(GemmParams& p, const EpiArgs& e) {
 template <bool MN, int EPI>
 static int launch_kernel(const CUtensorMap& mAh, const CUtensorMap& mAl, const CUtensorMap& mBh,
                          const CUtensorMap& mBl, const GemmParams& p, cudaStream_t st) {
-  const size_t smem = (size_t)p.num_stages * p.stage_bytes + (MN ? 8192 : 0) + 1024 + 256;
+  const size_t smem = (size_t)p.num_stages * p.stage_bytes + (MN ? 8192 : 0) + 1024 + 256 + TC_BIAS_SMEM;
   static bool attr = false;
   if (!attr) {
     GANTTS_CUDA(cudaFuncSetAttribute(gemm_bf16x3_kernel<MN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -573,11 +615,14 @@ static int launch_gemm_kk(const Planes& A, const Planes& B, const EpiArgs& e, cu
   p.b_plane_bytes = ((uint32_t)p.bn * 128 + 1023) / 1024 * 1024;
   p.stage_bytes = 2 * TC_A_PLANE + 2 * p.b_plane_bytes;
   p.tx_bytes = 2 * TC_A_PLANE + 2 * (uint32_t)p.bn * 128;
-  p.num_stages = (int)((220 * 1024) / p.stage_bytes);
+  p.num_stages = (int)((216 * 1024) / p.stage_bytes);
   if (p.num_stages > TC_MAX_STAGES) p.num_stages = TC_MAX_STAGES;
   p.tmem_cols = 512;
   p.c_zstride = 0;
   fill_epilogue(p, e);
+  // bias staged in smem after the barrier block when it fits (padded to whole column tiles)
+  p.bias_off = (e.bias && (size_t)p.num_b * p.bn * sizeof(float) <= TC_BIAS_SMEM)
+                   ? (uint32_t)p.num_stages * p.stage_bytes + 256u : 0u;
   CUtensorMap mAh, mAl, mBh, mBl;
   int rc;
   if ((rc = make_map(&mAh, A.hi, A.rows, A.cols, A.pitch, TC_BM))) return rc;

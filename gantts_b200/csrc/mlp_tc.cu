@@ -71,6 +71,8 @@ static int colsum_planes(const Planes& G, float* gb, int accumulate, float* part
 }
 
 struct MlpTape {
+  uint32_t* code[GANTTS_MAX_LAYERS];   // code[l]: activation-derivative codes of H[l] (l >= 1), [M][code_pitch[l]]
+  int64_t code_pitch[GANTTS_MAX_LAYERS];
   Planes H[GANTTS_MAX_LAYERS];      // H[0] = input planes, H[l] = output of hidden layer l-1
   Planes W[GANTTS_MAX_LAYERS];      // [d_{l+1}][d_l]
   Planes Wt[GANTTS_MAX_LAYERS];     // [d_l][d_{l+1}]
@@ -95,6 +97,12 @@ static size_t carve_tape(const gantts_mlp_t* m, int64_t M, char* base, MlpTape* 
   for (int l = 0; l < m->num_layers; ++l) {
     Planes p = carve_planes(cur, M, m->dims[l]);
     if (t) t->H[l] = p;
+    const int64_t cp = (m->dims[l] + 15) / 16;
+    if (t) {
+      t->code[l] = reinterpret_cast<uint32_t*>(cur);
+      t->code_pitch[l] = cp;
+    }
+    if (l >= 1) cur += ((size_t)M * cp * sizeof(uint32_t) + 255) / 256 * 256;
   }
   for (int l = 0; l < m->num_layers; ++l) {
     Planes a = carve_planes(cur, m->dims[l + 1], m->dims[l]);
@@ -154,6 +162,8 @@ extern "C" int gantts_mlp_fwd(const gantts_mlp_t* m, const float* x, int64_t x_r
       e.out_hi = t.H[l + 1].hi;
       e.out_lo = t.H[l + 1].lo;
       e.out_pitch = t.H[l + 1].pitch;
+      e.code = t.code[l + 1];
+      e.code_pitch = t.code_pitch[l + 1];
       e.act = GANTTS_ACT_LEAKY_DROPOUT;
       e.slope = m->slope;
       e.p = m->dropout_p;
@@ -230,8 +240,8 @@ extern "C" int gantts_mlp_bwd(const gantts_mlp_t* m, const float* gy, int64_t gy
       e.out_hi = Gn.hi;
       e.out_lo = Gn.lo;
       e.out_pitch = Gn.pitch;
-      e.h_hi = t.H[l].hi;
-      e.h_pitch = t.H[l].pitch;
+      e.code = t.code[l];
+      e.code_pitch = t.code_pitch[l];
       e.slope = m->slope;
       e.p = m->dropout_p;
       if ((rc = launch_gemm_kk(G, t.Wt[l], e, st))) return rc;
