@@ -15,14 +15,15 @@
 // overlaps the MMAs of tile i+1.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
 namespace gantts {
 
-constexpr int TC_EPI_WARPS = 8;
-constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int TC_EPI_WARPS = 16;
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;   // warp 0 TMA, warp 1 MMA, warps 2..17 epilogue
 constexpr int TC_BM = 128;          // MMA M (TMEM lanes)
 constexpr int TC_BK = 64;           // reduction elements per stage (one 128B swizzle atom of bf16)
 constexpr int TC_MAX_STAGES = 4;
@@ -40,7 +41,7 @@ struct GemmParams {
   int64_t red;          // reduction extent
   int64_t red_chunk;    // reduction elements per z-slice (multiple of TC_BK)
   int num_a, num_b, num_z;
-  int bn;               // MMA N, multiple of 32, <= 256
+  int bn;               // MMA N, multiple of 64, <= 256
   int num_stages;
   uint32_t stage_bytes, b_plane_bytes, tx_bytes;
   uint32_t tmem_cols;
@@ -56,6 +57,7 @@ struct GemmParams {
   uint32_t* code;
   int64_t code_pitch;   // words per row
   uint32_t bias_off;    // byte offset (from the aligned smem base) of the staged bias vector, 0 = none
+  uint32_t dbg;         // experiment switches (env GANTTS_B200_DBG): 1 no plane stores, 2 no dropout, 4 no code
   // MN-major only: column sums of A (= bias gradient) via an extra N=16 MMA against a tile of ones
   float* db;            // [num_z][rows_a] partial sums, or null
   uint32_t ones_off;    // byte offset of the 8 KB all-ones bf16 tile from the aligned smem base
@@ -72,9 +74,14 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-// Split 8 fp32 values into bf16 hi/lo and store them as two 16-byte vectors.
-__device__ __forceinline__ void store_planes8(const float* v, __nv_bfloat16* hi, __nv_bfloat16* lo) {
-  uint32_t h[4], l[4];
+__device__ __forceinline__ void st_global_256(void* ptr, const uint32_t (&v)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(v[0]), "r"(v[1]),
+               "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+
+// Split 8 fp32 values into packed bf16 hi/lo words (4 words each).
+__device__ __forceinline__ void split8(const float* v, uint32_t* h, uint32_t* l) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const float a = v[2 * i], b = v[2 * i + 1];
@@ -83,8 +90,23 @@ __device__ __forceinline__ void store_planes8(const float* v, __nv_bfloat16* hi,
     h[i] = hp;
     l[i] = pack_bf16x2(a - ah, b - bh);
   }
-  *reinterpret_cast<uint4*>(hi) = make_uint4(h[0], h[1], h[2], h[3]);
-  *reinterpret_cast<uint4*>(lo) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// 16 fp32 values of one row -> hi/lo planes.  Fast path: one 256-bit store (a full 32 B sector) per
+// plane (sm_100 STG.256); `pitch` is a multiple of 16 elements and col a multiple of 16, so the
+// address is 32-byte aligned.  Tail: 16-byte stores up to the pitch.
+__device__ __forceinline__ void store_planes16(const float* v, __nv_bfloat16* hi, __nv_bfloat16* lo, int col,
+                                               int64_t pitch) {
+  uint32_t h[8], l[8];
+  split8(v, h, l);
+  split8(v + 8, h + 4, l + 4);
+  if (col + 16 <= pitch) {
+    st_global_256(hi, h);
+    st_global_256(lo, l);
+  } else if (col + 8 <= pitch) {
+    *reinterpret_cast<uint4*>(hi) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(lo) = make_uint4(l[0], l[1], l[2], l[3]);
+  }
 }
 
 // One 16-column chunk of one output row: registers (fp32 accumulators) -> global.
@@ -125,6 +147,13 @@ __device__ __forceinline__ uint32_t epilogue_chunk16(const GemmParams& p, const 
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] = 1.f / (1.f + expf(-v[j]));
     }
+    if (p.vec_ok == 2 && col + 15 < p.cols_b) {
+      uint32_t w0[8], w1[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { w0[j] = __float_as_uint(v[j]); w1[j] = __float_as_uint(v[8 + j]); }
+      st_global_256(crow + col, w0);
+      st_global_256(crow + col + 8, w1);
+    } else
 #pragma unroll
     for (int j = 0; j < 16; j += 4) {
       const int c = col + j;
@@ -151,7 +180,7 @@ __device__ __forceinline__ uint32_t epilogue_chunk16(const GemmParams& p, const 
     }
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], v[j] * p.slope);
-    if (p.thresh) {
+    if (p.thresh && !(p.dbg & 2)) {
       const uint32_t half_n = (uint32_t)(p.cols_b + 1) >> 1;
 #pragma unroll
       for (int j = 0; j < 16; j += 2) {
@@ -160,15 +189,23 @@ __device__ __forceinline__ uint32_t epilogue_chunk16(const GemmParams& p, const 
         v[j + 1] = (bits >> 16) >= p.thresh ? v[j + 1] * p.keep_scale : 0.f;
       }
     }
+    if (!(p.dbg & 4)) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      if (v[j] == 0.f) code |= 1u << (2 * j);
-      if (v[j] < 0.f) code |= 2u << (2 * j);
+      for (int j = 0; j < 16; ++j) {
+        if (v[j] == 0.f) code |= 1u << (2 * j);
+        if (v[j] < 0.f) code |= 2u << (2 * j);
+      }
     }
     __nv_bfloat16* oh = p.out_hi + row * p.out_pitch + col;
     __nv_bfloat16* ol = p.out_lo + row * p.out_pitch + col;
-    if (col + 8 <= p.out_pitch) store_planes8(v, oh, ol);
-    if (col + 16 <= p.out_pitch) store_planes8(v + 8, oh + 8, ol + 8);
+    if (p.dbg & 1) {
+      float acc = 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc += v[j];
+      if (acc == 123.456f) oh[0] = __float2bfloat16_rn(acc);
+    } else {
+      store_planes16(v, oh, ol, col, p.out_pitch);
+    }
   } else {  // EPI_PLANES_BWD: gz = g * act'(h), derivative class from the saved 2-bit code
     const float dpos = p.keep_scale, dneg = p.slope * p.keep_scale;
     const float dzero = p.thresh ? 0.f : p.slope;
@@ -179,8 +216,7 @@ __device__ __forceinline__ uint32_t epilogue_chunk16(const GemmParams& p, const 
     }
     __nv_bfloat16* oh = p.out_hi + row * p.out_pitch + col;
     __nv_bfloat16* ol = p.out_lo + row * p.out_pitch + col;
-    if (col + 8 <= p.out_pitch) store_planes8(v, oh, ol);
-    if (col + 16 <= p.out_pitch) store_planes8(v + 8, oh + 8, ol + 8);
+    store_planes16(v, oh, ol, col, p.out_pitch);
   }
   return code;
 }
@@ -307,7 +343,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
           const uint32_t sa_hi = base + s * p.stage_bytes, sa_lo = sa_hi + TC_A_PLANE;
           const uint32_t sb_hi = sa_lo + TC_A_PLANE, sb_lo = sb_hi + p.b_plane_bytes;
 #pragma unroll
-          for (int k = 0; k < TC_BK / 16; ++k) {
+          for (int k = 0; k < ((p.dbg & 16) ? 0 : TC_BK / 16); ++k) {
             const uint64_t da_hi = ptx::make_smem_desc(sa_hi + k * kstep, lbo, 1024);
             const uint64_t da_lo = ptx::make_smem_desc(sa_lo + k * kstep, lbo, 1024);
             const uint64_t db_hi = ptx::make_smem_desc(sb_hi + k * kstep, lbo, 1024);
@@ -328,20 +364,22 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
       }
     }
   } else {
-    // -------------------------------------------------------------- epilogue warps (2..9)
-    // warp w may access TMEM lanes 32*(w%4)..+31; warps 2-5 take the first half of the tile's
-    // columns, warps 6-9 the second half, so all four SM sub-partitions work on the epilogue.
+    // -------------------------------------------------------------- epilogue warps (2..17)
+    // warp w may access TMEM lanes 32*(w%4)..+31.  Sixteen warps: four per lane quarter, each taking
+    // one quarter of the tile's columns, i.e. four warps per SM sub-partition to hide the TMEM-load
+    // and shared-memory latencies of the element-wise epilogue by thread-level parallelism.
     const int q = warp & 3;
-    const int chalf = (warp - 2) >> 2;
-    const int cbeg = chalf * (p.bn >> 1), cend = cbeg + (p.bn >> 1);
-    uint32_t code_next[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+    const int chalf = (warp - 2) >> 2;                  // column quarter 0..3
+    const int cw = p.bn >> 2;                           // columns per warp (multiple of 16)
+    const int cbeg = chalf * cw, cend = cbeg + cw;
+    uint32_t code_next[4] = {0u, 0u, 0u, 0u};
     if (EPI == EPI_PLANES_BWD && (int)blockIdx.x < total_tiles) {
       const int nrem = blockIdx.x % tiles_ab;
       const int64_t nrow = (int64_t)(nrem / p.num_b) * TC_BM + q * 32 + lane;
       const int ncol0 = (nrem % p.num_b) * p.bn;
       const uint32_t* cp = p.code + nrow * p.code_pitch + ((ncol0 + cbeg) >> 4);
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < 4; ++i)
         code_next[i] = (nrow < p.rows_a && cbeg + 16 * i < cend && ncol0 + cbeg + 16 * i < p.cols_b)
                            ? __ldg(cp + i) : 0u;
     }
@@ -354,12 +392,11 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
       const int64_t row = (int64_t)ta * TC_BM + q * 32 + lane;
       const int col0 = tb * p.bn;
       const bool row_ok = row < p.rows_a;
-      // EPI_PLANES_BWD: this thread's derivative codes (8 words) were prefetched one tile ahead.
-      uint32_t codes[8];
+      // EPI_PLANES_BWD: this thread's derivative codes (4 words) were prefetched one tile ahead.
+      uint32_t codes[4];
       if (EPI == EPI_PLANES_BWD) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) codes[i] = code_next[i];
-        // prefetch for the CTA's next tile
+        for (int i = 0; i < 4; ++i) codes[i] = code_next[i];
         const int ntile = tile + gridDim.x;
         if (ntile < total_tiles) {
           const int nrem = ntile % tiles_ab;
@@ -367,7 +404,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
           const int ncol0 = (nrem % p.num_b) * p.bn;
           const uint32_t* cp = p.code + nrow * p.code_pitch + ((ncol0 + cbeg) >> 4);
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
+          for (int i = 0; i < 4; ++i)
             code_next[i] = (nrow < p.rows_a && cbeg + 16 * i < cend && ncol0 + cbeg + 16 * i < p.cols_b)
                                ? __ldg(cp + i) : 0u;
         }
@@ -375,38 +412,35 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
       ptx::mbar_wait(tfull0 + 8 * acc, aph);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256;
-      uint32_t code_out[8];
-      // TMEM loads are software-pipelined: the 32 columns of step ci+1 are in flight while step ci
-      // is processed (tcgen05.wait::ld only covers loads issued before it).
-      uint32_t ra[2][16], rb[2][16];
-      ptx::tmem_ld16(taddr + cbeg, ra[0]);
-      if (cbeg + 32 <= cend) ptx::tmem_ld16(taddr + cbeg + 16, rb[0]);
+      uint32_t code_out[4];
 #pragma unroll
-      for (int ci = 0; ci < 4; ++ci) {
+      for (int ci = 0; ci < 2; ++ci) {
         const int c = cbeg + 32 * ci;
         code_out[2 * ci] = code_out[2 * ci + 1] = 0u;
-        if (c < cend) {
+        if (c < cend && !(p.dbg & 8)) {
+          uint32_t r0[16], r1[16];
           const bool two = c + 32 <= cend;
+          ptx::tmem_ld16(taddr + c, r0);
+          if (two) ptx::tmem_ld16(taddr + c + 16, r1);
           ptx::tmem_ld_wait();
-          if (ci < 3 && c + 32 < cend) {
-            ptx::tmem_ld16(taddr + c + 32, ra[(ci + 1) & 1]);
-            if (c + 64 <= cend) ptx::tmem_ld16(taddr + c + 48, rb[(ci + 1) & 1]);
-          }
           if (row_ok) {
             if (col0 + c < p.cols_b)
-              code_out[2 * ci] = epilogue_chunk16<EPI>(p, ra[ci & 1], row, col0 + c, z, bias_s, codes[2 * ci]);
+              code_out[2 * ci] = epilogue_chunk16<EPI>(p, r0, row, col0 + c, z, bias_s, codes[2 * ci]);
             if (two && col0 + c + 16 < p.cols_b)
-              code_out[2 * ci + 1] =
-                  epilogue_chunk16<EPI>(p, rb[ci & 1], row, col0 + c + 16, z, bias_s, codes[2 * ci + 1]);
+              code_out[2 * ci + 1] = epilogue_chunk16<EPI>(p, r1, row, col0 + c + 16, z, bias_s, codes[2 * ci + 1]);
           }
         }
       }
-      ptx::tmem_ld_wait();
       if (EPI == EPI_PLANES_FWD && p.code != nullptr && row_ok) {
         uint32_t* cp = p.code + row * p.code_pitch + ((col0 + cbeg) >> 4);
+        if (cw == 64 && (p.code_pitch & 3) == 0) {
+          // whole 16-byte group inside the (4-word padded) row: one vector store
+          *reinterpret_cast<uint4*>(cp) = make_uint4(code_out[0], code_out[1], code_out[2], code_out[3]);
+        } else {
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          if (cbeg + 16 * i < cend && col0 + cbeg + 16 * i < p.cols_b) cp[i] = code_out[i];
+          for (int i = 0; i < 4; ++i)
+            if (cbeg + 16 * i < cend && col0 + cbeg + 16 * i < p.cols_b) cp[i] = code_out[i];
+        }
       }
       if (MN && p.db != nullptr && tb == 0 && chalf == 0) {
         uint32_t r0[16];
@@ -500,7 +534,7 @@ static int num_sms() {
   return n;
 }
 
-static inline int64_t pitch_for(int64_t cols) { return (cols + 7) / 8 * 8; }
+static inline int64_t pitch_for(int64_t cols) { return (cols + 15) / 16 * 16; }   // 32-byte rows
 static inline size_t plane_bytes(int64_t rows, int64_t cols) {
   return ((size_t)rows * pitch_for(cols) * 2 + 255) / 256 * 256;
 }
@@ -534,10 +568,10 @@ static int launch_split(const float* src, int64_t rs, int64_t rows, int cols, co
 }
 
 static int pick_bn(int n) {
-  int bn = (n + 31) / 32 * 32;
+  int bn = (n + 63) / 64 * 64;
   if (bn <= 256) return bn;
   int tiles = (n + 255) / 256;
-  bn = ((n + tiles - 1) / tiles + 31) / 32 * 32;
+  bn = ((n + tiles - 1) / tiles + 63) / 64 * 64;
   return bn;
 }
 
@@ -565,6 +599,7 @@ static void fill_epilogue(GemmParams& p, const EpiArgs& e) {
   p.ldc = e.ldc;
   p.accumulate = e.accumulate;
   p.vec_ok = (!e.accumulate && e.C && (e.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(e.C) & 15) == 0) ? 1 : 0;
+  if (p.vec_ok && (e.ldc & 7) == 0 && (reinterpret_cast<uintptr_t>(e.C) & 31) == 0) p.vec_ok = 2;   // STG.256
   p.out_hi = e.out_hi;
   p.out_lo = e.out_lo;
   p.out_pitch = e.out_pitch;
@@ -576,6 +611,12 @@ static void fill_epilogue(GemmParams& p, const EpiArgs& e) {
   p.keep_scale = e.p > 0.f ? 1.f / (1.f - e.p) : 1.f;
   p.thresh = e.p > 0.f ? (uint32_t)(e.p * 65536.f + 0.5f) : 0u;
   p.seed = e.seed;
+  static int dbg = -1;
+  if (dbg < 0) {
+    const char* v = getenv("GANTTS_B200_DBG");
+    dbg = v ? atoi(v) : 0;
+  }
+  p.dbg = (uint32_t)dbg;
 }
 
 template <bool MN, int EPI>

@@ -55,6 +55,38 @@ colsum_planes_partial_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bf
   }
 }
 
+// All weight matrices of an MLP -> bf16 hi/lo planes, both [N][K] (forward operand) and transposed
+// [K][N] (operand of gx = gz W), in ONE launch.
+struct WeightSplitList {
+  int n;
+  const float* W[GANTTS_MAX_LAYERS];
+  int N[GANTTS_MAX_LAYERS], K[GANTTS_MAX_LAYERS];
+  __nv_bfloat16 *hi[GANTTS_MAX_LAYERS], *lo[GANTTS_MAX_LAYERS];       // [N][pitch]
+  __nv_bfloat16 *thi[GANTTS_MAX_LAYERS], *tlo[GANTTS_MAX_LAYERS];     // [K][tpitch]
+  int64_t pitch[GANTTS_MAX_LAYERS], tpitch[GANTTS_MAX_LAYERS];
+  int64_t off[GANTTS_MAX_LAYERS + 1];
+};
+
+__global__ void split_weights_kernel(WeightSplitList wl) {
+  const int64_t total = wl.off[wl.n];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int l = 0;
+    while (l + 1 < wl.n && i >= wl.off[l + 1]) ++l;
+    const int64_t j = i - wl.off[l];
+    const int K = wl.K[l];
+    const int64_t r = j / K;
+    const int c = (int)(j - r * K);
+    const float v = wl.W[l][j];
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(h));
+    wl.hi[l][r * wl.pitch[l] + c] = h;
+    wl.lo[l][r * wl.pitch[l] + c] = lo;
+    wl.thi[l][(int64_t)c * wl.tpitch[l] + r] = h;
+    wl.tlo[l][(int64_t)c * wl.tpitch[l] + r] = lo;
+  }
+}
+
 constexpr int MLP_COLSUM_CHUNKS = 128;
 
 static int colsum_planes(const Planes& G, float* gb, int accumulate, float* partial, cudaStream_t st) {
@@ -97,7 +129,7 @@ static size_t carve_tape(const gantts_mlp_t* m, int64_t M, char* base, MlpTape* 
   for (int l = 0; l < m->num_layers; ++l) {
     Planes p = carve_planes(cur, M, m->dims[l]);
     if (t) t->H[l] = p;
-    const int64_t cp = (m->dims[l] + 15) / 16;
+    const int64_t cp = ((m->dims[l] + 15) / 16 + 3) / 4 * 4;   // words per row, padded to 16 B
     if (t) {
       t->code[l] = reinterpret_cast<uint32_t*>(cur);
       t->code_pitch[l] = cp;
@@ -150,9 +182,27 @@ extern "C" int gantts_mlp_fwd(const gantts_mlp_t* m, const float* x, int64_t x_r
   carve_tape(m, M, reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(tape) + 255) / 256 * 256), &t);
   const int L = m->num_layers;
   if ((rc = launch_split(x, x_rs, M, m->dims[0], t.H[0], 0, st))) return rc;
-  for (int l = 0; l < L; ++l) {
-    if ((rc = launch_split(m->W[l], m->dims[l], m->dims[l + 1], m->dims[l], t.W[l], 0, st))) return rc;
-    if ((rc = launch_split(m->W[l], m->dims[l], m->dims[l + 1], m->dims[l], t.Wt[l], 1, st))) return rc;
+  {
+    WeightSplitList wl;
+    wl.n = L;
+    wl.off[0] = 0;
+    for (int l = 0; l < L; ++l) {
+      wl.W[l] = m->W[l];
+      wl.N[l] = m->dims[l + 1];
+      wl.K[l] = m->dims[l];
+      wl.hi[l] = t.W[l].hi;
+      wl.lo[l] = t.W[l].lo;
+      wl.pitch[l] = t.W[l].pitch;
+      wl.thi[l] = t.Wt[l].hi;
+      wl.tlo[l] = t.Wt[l].lo;
+      wl.tpitch[l] = t.Wt[l].pitch;
+      wl.off[l + 1] = wl.off[l] + (int64_t)m->dims[l + 1] * m->dims[l];
+    }
+    int nb = (int)((wl.off[L] + 1023) / 1024);
+    if (nb > num_sms() * 4) nb = num_sms() * 4;
+    if (nb < 1) nb = 1;
+    split_weights_kernel<<<nb, 256, 0, st>>>(wl);
+    GANTTS_LAUNCH_CHECK("split_weights_kernel");
   }
   for (int l = 0; l < L; ++l) {
     EpiArgs e;
