@@ -38,24 +38,26 @@ struct ColList {
 
 __global__ void gather_cols_list_kernel(const float* __restrict__ in, int64_t in_rs, float* __restrict__ out,
                                         int64_t out_rs, ColList cols, int64_t rows) {
-  const int64_t total = rows * cols.n;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    int64_t r = i / cols.n;
-    int j = (int)(i - r * cols.n);
-    out[r * out_rs + j] = in[r * in_rs + cols.c[j]];
-  }
+  __shared__ int sc[GANTTS_MAX_COLS];
+  for (int i = threadIdx.x; i < cols.n; i += blockDim.x) sc[i] = cols.c[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < rows; r += nwarps)
+    for (int j = lane; j < cols.n; j += 32) out[r * out_rs + j] = in[r * in_rs + sc[j]];
 }
 
 __global__ void scatter_cols_list_add_kernel(const float* __restrict__ go, int64_t go_rs, float* __restrict__ gi,
                                              int64_t gi_rs, ColList cols, int64_t rows) {
-  const int64_t total = rows * cols.n;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    int64_t r = i / cols.n;
-    int j = (int)(i - r * cols.n);
-    gi[r * gi_rs + cols.c[j]] += go[r * go_rs + j];
-  }
+  __shared__ int sc[GANTTS_MAX_COLS];
+  for (int i = threadIdx.x; i < cols.n; i += blockDim.x) sc[i] = cols.c[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < rows; r += nwarps)
+    for (int j = lane; j < cols.n; j += 32) gi[r * gi_rs + sc[j]] += go[r * go_rs + j];
 }
 
 __global__ void set_scales_kernel(float* scal, float inv_frames, float adv_w, float mge_w, float mse_w) {

@@ -466,17 +466,32 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
 __global__ void split_planes_kernel(const float* __restrict__ src, int64_t rs, int64_t rows, int cols,
                                     __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
                                     int64_t pitch, int transpose) {
-  const int64_t total = rows * cols;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    int64_t r = i / cols;
-    int c = (int)(i - r * cols);
-    float v = src[r * rs + c];
-    __nv_bfloat16 h = __float2bfloat16_rn(v);
-    __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
-    int64_t o = transpose ? ((int64_t)c * pitch + r) : (r * pitch + c);
-    hi[o] = h;
-    lo[o] = l;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  if (!transpose) {
+    // one warp per row, each lane converts PAIRS of columns -> 4-byte stores, 128 B per warp store
+    for (int64_t r = warp; r < rows; r += nwarps) {
+      const float* sr = src + r * rs;
+      uint32_t* hr = reinterpret_cast<uint32_t*>(hi + r * pitch);
+      uint32_t* lr = reinterpret_cast<uint32_t*>(lo + r * pitch);
+#pragma unroll 2
+      for (int c = 2 * lane; c < cols; c += 64) {
+        const float a = sr[c], b = (c + 1 < cols) ? sr[c + 1] : 0.f;
+        const uint32_t hp = pack_bf16x2(a, b);
+        const float ah = __uint_as_float(hp << 16), bh = __uint_as_float(hp & 0xffff0000u);
+        hr[c >> 1] = hp;
+        lr[c >> 1] = pack_bf16x2(a - ah, b - bh);
+      }
+    }
+  } else {
+    for (int64_t r = warp; r < rows; r += nwarps)
+      for (int c = lane; c < cols; c += 32) {
+        const float v = src[r * rs + c];
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        hi[(int64_t)c * pitch + r] = h;
+        lo[(int64_t)c * pitch + r] = __float2bfloat16_rn(v - __bfloat162float(h));
+      }
   }
 }
 

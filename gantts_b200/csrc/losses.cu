@@ -30,15 +30,20 @@ masked_sse_partial_kernel(const float* __restrict__ a, int64_t a_rs, const float
                           RedWs* ws) {
   __shared__ float sm[RED_NV * 32];
   float v[RED_NV] = {0.f, 0.f, 0.f, 0.f};
-  const int64_t total = rows * D;
-  for (int64_t i = (int64_t)blockIdx.x * RED_THREADS + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * RED_THREADS) {
-    int64_t r = i / D;
-    int d = (int)(i - r * D);
-    float m = mask[r];
-    float x = a[r * a_rs + d] * m - b[r * b_rs + d] * m;
-    v[0] = fmaf(x, x, v[0]);
-    if (d == 0) v[1] += m;
+  // one warp per row (lanes stride over the columns: coalesced, no integer division)
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * RED_THREADS + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * RED_THREADS) >> 5;
+  for (int64_t r = warp; r < rows; r += nwarps) {
+    const float m = mask[r];
+    const float* ar = a + r * a_rs;
+    const float* br = b + r * b_rs;
+#pragma unroll 4
+    for (int d = lane; d < D; d += 32) {
+      const float x = ar[d] * m - br[d] * m;
+      v[0] = fmaf(x, x, v[0]);
+    }
+    if (lane == 0) v[1] += m;
   }
   block_sum<RED_NV>(v, sm);
   if (threadIdx.x == 0) {
@@ -66,15 +71,19 @@ masked_sse_bwd_kernel(const float* __restrict__ a, int64_t a_rs, const float* __
                       const float* __restrict__ scale, float* __restrict__ ga, int64_t ga_rs,
                       int accumulate) {
   const float s2 = 2.f * scale[0];
-  const int64_t total = rows * D;
-  for (int64_t i = (int64_t)blockIdx.x * RED_THREADS + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * RED_THREADS) {
-    int64_t r = i / D;
-    int d = (int)(i - r * D);
-    float m = mask[r];
-    float g = s2 * (a[r * a_rs + d] * m - b[r * b_rs + d] * m) * m;
-    float* p = ga + r * ga_rs + d;
-    *p = accumulate ? (*p + g) : g;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * RED_THREADS + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * RED_THREADS) >> 5;
+  for (int64_t r = warp; r < rows; r += nwarps) {
+    const float m = mask[r];
+    const float* ar = a + r * a_rs;
+    const float* br = b + r * b_rs;
+    float* gr = ga + r * ga_rs;
+#pragma unroll 4
+    for (int d = lane; d < D; d += 32) {
+      const float g = s2 * (ar[d] * m - br[d] * m) * m;
+      gr[d] = accumulate ? gr[d] + g : g;
+    }
   }
 }
 
@@ -113,25 +122,21 @@ __global__ void masked_bce_bwd_kernel(const float* __restrict__ Dv, const float*
 __global__ void gather_cols_kernel(const float* __restrict__ in, int64_t in_rs, float* __restrict__ out,
                                    int64_t out_rs, const int32_t* __restrict__ cols, int ncols,
                                    int64_t rows) {
-  const int64_t total = rows * ncols;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    int64_t r = i / ncols;
-    int j = (int)(i - r * ncols);
-    out[r * out_rs + j] = in[r * in_rs + cols[j]];
-  }
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < rows; r += nwarps)
+    for (int j = lane; j < ncols; j += 32) out[r * out_rs + j] = in[r * in_rs + cols[j]];
 }
 
 __global__ void scatter_cols_add_kernel(const float* __restrict__ go, int64_t go_rs,
                                         float* __restrict__ gi, int64_t gi_rs,
                                         const int32_t* __restrict__ cols, int ncols, int64_t rows) {
-  const int64_t total = rows * ncols;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    int64_t r = i / ncols;
-    int j = (int)(i - r * ncols);
-    gi[r * gi_rs + cols[j]] += go[r * go_rs + j];   // cols are distinct => no race
-  }
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < rows; r += nwarps)
+    for (int j = lane; j < ncols; j += 32) gi[r * gi_rs + cols[j]] += go[r * go_rs + j];   // cols distinct
 }
 
 static inline int grid_for(int64_t work, int threads) {

@@ -15,20 +15,37 @@ __global__ void grad_out_to_planes_kernel(const float* __restrict__ gy, int64_t 
                                           const float* __restrict__ y, int64_t y_rs, int64_t rows, int cols,
                                           __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
                                           int64_t pitch, int sigmoid) {
-  const int64_t total = rows * cols;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    int64_t r = i / cols;
-    int c = (int)(i - r * cols);
-    float v = gy[r * gy_rs + c];
-    if (sigmoid) {
-      float yy = y[r * y_rs + c];
-      v *= yy * (1.f - yy);
+  if (cols < 32) {     // narrow outputs (the discriminator's single column): one thread per element
+    const int64_t total = rows * cols;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t r = i / cols;
+      const int c = (int)(i - r * cols);
+      float v = gy[r * gy_rs + c];
+      if (sigmoid) {
+        const float yy = y[r * y_rs + c];
+        v *= yy * (1.f - yy);
+      }
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      hi[r * pitch + c] = h;
+      lo[r * pitch + c] = __float2bfloat16_rn(v - __bfloat162float(h));
     }
-    __nv_bfloat16 h = __float2bfloat16_rn(v);
-    hi[r * pitch + c] = h;
-    lo[r * pitch + c] = __float2bfloat16_rn(v - __bfloat162float(h));
+    return;
   }
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < rows; r += nwarps)
+    for (int c = lane; c < cols; c += 32) {
+      float v = gy[r * gy_rs + c];
+      if (sigmoid) {
+        const float yy = y[r * y_rs + c];
+        v *= yy * (1.f - yy);
+      }
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      hi[r * pitch + c] = h;
+      lo[r * pitch + c] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
 }
 
 // Column sums of a planes matrix (hi + lo): partial[chunk][col].
