@@ -221,7 +221,10 @@ __device__ __forceinline__ uint32_t epilogue_chunk16(const GemmParams& p, const 
   return code;
 }
 
-template <bool MN, int EPI>
+// CL = thread-block cluster size along the output rows (1 or 2).  With CL = 2 the two CTAs of a cluster
+// work on adjacent row tiles of the SAME column tile: each loads its own A tile and HALF of the B tile,
+// multicast to both (halves the dominant L2 -> SM traffic, the re-fetch of the weights per row tile).
+template <bool MN, int EPI, int CL>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                    const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
@@ -239,7 +242,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.num_stages; ++s) {
       ptx::mbar_init(full0 + 8 * s, 1);
-      ptx::mbar_init(empty0 + 8 * s, 1);
+      ptx::mbar_init(empty0 + 8 * s, CL);          // released by the MMA issuer of every CTA in the cluster
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(tfull0 + 8 * a, 1);
@@ -270,19 +273,27 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (CL > 1) ptx::cluster_sync();                 // peers' barriers are initialised before any remote arrive
   ptx::tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
 
-  const int total_tiles = p.num_a * p.num_b * p.num_z;
-  const int tiles_ab = p.num_a * p.num_b;
+  // Work decomposition.  CL = 1: CTA b takes tiles b, b+grid, ...  CL = 2: cluster c takes PAIR tiles
+  // c, c+nclusters, ...; a pair tile is two adjacent row tiles of one column tile, CTA rank r gets
+  // row tile 2*pa + r.  Both CTAs of a cluster walk the same sequence in lockstep.
+  const int crank = CL > 1 ? (int)ptx::cluster_ctarank() : 0;
+  const int num_a_units = CL > 1 ? (p.num_a + CL - 1) / CL : p.num_a;
+  const int tiles_ab = num_a_units * p.num_b;
+  const int total_tiles = tiles_ab * p.num_z;
+  const int first_tile = CL > 1 ? (int)blockIdx.x / CL : (int)blockIdx.x;
+  const int tile_step = CL > 1 ? (int)gridDim.x / CL : (int)gridDim.x;
 
   if (warp == 0) {
     if (lane == 0) {
       // ------------------------------------------------------------ TMA producer
       uint32_t s = 0, ph = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
         const int z = tile / tiles_ab, rem = tile - z * tiles_ab;
-        const int ta = rem / p.num_b, tb = rem - ta * p.num_b;
+        const int ta = (rem / p.num_b) * CL + crank, tb = rem % p.num_b;
         const int64_t r_beg = (int64_t)z * p.red_chunk;
         const int64_t r_end = r_beg + p.red_chunk < p.red ? r_beg + p.red_chunk : p.red;
         const int a0 = ta * TC_BM, b0 = tb * p.bn;
@@ -292,7 +303,15 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
           ptx::mbar_expect_tx(fb, p.tx_bytes);
           const uint32_t sa_hi = base + s * p.stage_bytes, sa_lo = sa_hi + TC_A_PLANE;
           const uint32_t sb_hi = sa_lo + TC_A_PLANE, sb_lo = sb_hi + p.b_plane_bytes;
-          if (!MN) {
+          if (!MN && CL > 1) {
+            // own A tile; own half of the B tile (box = bn/2 rows) multicast to both CTAs
+            const uint32_t hoff = (uint32_t)crank * (uint32_t)(p.bn / 2) * 128u;
+            const int bh0 = b0 + crank * (p.bn / 2);
+            ptx::tma_load_2d(sa_hi, &tmAh, fb, (int32_t)r0, a0);
+            ptx::tma_load_2d_mcast(sb_hi + hoff, &tmBh, fb, (int32_t)r0, bh0, (uint16_t)0x3);
+            ptx::tma_load_2d(sa_lo, &tmAl, fb, (int32_t)r0, a0);
+            ptx::tma_load_2d_mcast(sb_lo + hoff, &tmBl, fb, (int32_t)r0, bh0, (uint16_t)0x3);
+          } else if (!MN) {
             ptx::tma_load_2d(sa_hi, &tmAh, fb, (int32_t)r0, a0);
             ptx::tma_load_2d(sb_hi, &tmBh, fb, (int32_t)r0, b0);
             ptx::tma_load_2d(sa_lo, &tmAl, fb, (int32_t)r0, a0);
@@ -321,7 +340,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
       const uint32_t kstep = MN ? 2048u : 32u;
       uint32_t s = 0, ph = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++it) {
         const int z = tile / tiles_ab;
         const int64_t r_beg = (int64_t)z * p.red_chunk;
         const int64_t r_end = r_beg + p.red_chunk < p.red ? r_beg + p.red_chunk : p.red;
@@ -332,7 +351,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
         ptx::mbar_wait(tempty0 + 8 * acc, aph ^ 1);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256;
-        const int rem_i = tile - z * tiles_ab;
+        const int rem_i = tile - z * tiles_ab;   // (MN kernels run with CL = 1)
         const bool do_db = MN && p.db != nullptr && (rem_i % p.num_b) == 0;
         const uint32_t idesc_db = ptx::make_idesc_bf16(TC_BM, 16, 1, 1);
         const uint64_t d_ones = ptx::make_smem_desc(ones_base, lbo, 1024);
@@ -357,7 +376,9 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
             ptx::mma_bf16_ss(d_tmem, da_hi, db_lo, idesc, 1);
             ptx::mma_bf16_ss(d_tmem, da_lo, db_hi, idesc, 1);
           }
-          ptx::mma_commit(empty0 + 8 * s);        // frees the smem stage once these MMAs retire
+          // frees the smem stage (in every CTA of the cluster: the peer multicasts into it too)
+          if (CL > 1) ptx::mma_commit_mcast(empty0 + 8 * s, (uint16_t)0x3);
+          else ptx::mma_commit(empty0 + 8 * s);
           if (++s == (uint32_t)p.num_stages) { s = 0; ph ^= 1; }
         }
         ptx::mma_commit(tfull0 + 8 * acc);        // accumulator ready for the epilogue
@@ -373,9 +394,9 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
     const int cw = p.bn >> 2;                           // columns per warp (multiple of 16)
     const int cbeg = chalf * cw, cend = cbeg + cw;
     uint32_t code_next[4] = {0u, 0u, 0u, 0u};
-    if (EPI == EPI_PLANES_BWD && (int)blockIdx.x < total_tiles) {
-      const int nrem = blockIdx.x % tiles_ab;
-      const int64_t nrow = (int64_t)(nrem / p.num_b) * TC_BM + q * 32 + lane;
+    if (EPI == EPI_PLANES_BWD && first_tile < total_tiles) {
+      const int nrem = first_tile % tiles_ab;
+      const int64_t nrow = (int64_t)((nrem / p.num_b) * CL + crank) * TC_BM + q * 32 + lane;
       const int ncol0 = (nrem % p.num_b) * p.bn;
       const uint32_t* cp = p.code + nrow * p.code_pitch + ((ncol0 + cbeg) >> 4);
 #pragma unroll
@@ -384,9 +405,9 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
                            ? __ldg(cp + i) : 0u;
     }
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++it) {
       const int z = tile / tiles_ab, rem = tile - z * tiles_ab;
-      const int ta = rem / p.num_b, tb = rem - ta * p.num_b;
+      const int ta = (rem / p.num_b) * CL + crank, tb = rem % p.num_b;
       const int acc = MN ? 0 : (it & 1);
       const uint32_t aph = MN ? (it & 1) : ((it >> 1) & 1);
       const int64_t row = (int64_t)ta * TC_BM + q * 32 + lane;
@@ -397,10 +418,10 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
       if (EPI == EPI_PLANES_BWD) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) codes[i] = code_next[i];
-        const int ntile = tile + gridDim.x;
+        const int ntile = tile + tile_step;
         if (ntile < total_tiles) {
           const int nrem = ntile % tiles_ab;
-          const int64_t nrow = (int64_t)(nrem / p.num_b) * TC_BM + q * 32 + lane;
+          const int64_t nrow = (int64_t)((nrem / p.num_b) * CL + crank) * TC_BM + q * 32 + lane;
           const int ncol0 = (nrem % p.num_b) * p.bn;
           const uint32_t* cp = p.code + nrow * p.code_pitch + ((ncol0 + cbeg) >> 4);
 #pragma unroll
@@ -455,6 +476,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (CL > 1) ptx::cluster_sync();                 // no CTA leaves while its peer may still signal / multicast into it
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, p.tmem_cols);
@@ -583,9 +605,15 @@ static int launch_split(const float* src, int64_t rs, int64_t rows, int cols, co
 }
 
 static int pick_bn(int n) {
+  static int cap = -1;
+  if (cap < 0) {
+    const char* e = getenv("GANTTS_B200_BN");
+    cap = e ? atoi(e) : 256;
+    if (cap < 64 || cap > 256 || cap % 64) cap = 256;
+  }
   int bn = (n + 63) / 64 * 64;
-  if (bn <= 256) return bn;
-  int tiles = (n + 255) / 256;
+  if (bn <= cap) return bn;
+  int tiles = (n + cap - 1) / cap;
   bn = ((n + tiles - 1) / tiles + 63) / 64 * 64;
   return bn;
 }
@@ -634,23 +662,55 @@ static void fill_epilogue(GemmParams& p, const EpiArgs& e) {
   p.dbg = (uint32_t)dbg;
 }
 
-template <bool MN, int EPI>
+template <bool MN, int EPI, int CL>
 static int launch_kernel(const CUtensorMap& mAh, const CUtensorMap& mAl, const CUtensorMap& mBh,
                          const CUtensorMap& mBl, const GemmParams& p, cudaStream_t st) {
   const size_t smem = (size_t)p.num_stages * p.stage_bytes + (MN ? 8192 : 0) + 1024 + 256 + TC_BIAS_SMEM;
   static bool attr = false;
   if (!attr) {
-    GANTTS_CUDA(cudaFuncSetAttribute(gemm_bf16x3_kernel<MN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    GANTTS_CUDA(cudaFuncSetAttribute(gemm_bf16x3_kernel<MN, EPI, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      227 * 1024));
     attr = true;
   }
-  const int total = p.num_a * p.num_b * p.num_z;
-  const int grid = total < num_sms() ? total : num_sms();
+  const int units = ((p.num_a + CL - 1) / CL) * p.num_b * p.num_z;     // tiles (CL=1) or pair tiles (CL=2)
+  int grid = units * CL < num_sms() ? units * CL : num_sms() / CL * CL;
   prof_begin(MN ? PROF_GEMM_MN : PROF_GEMM_KK, 2.0 * (double)p.rows_a * p.cols_b * (double)p.red, st);
-  gemm_bf16x3_kernel<MN, EPI><<<grid, TC_THREADS, smem, st>>>(mAh, mAl, mBh, mBl, p);
+  if (CL == 1) {
+    gemm_bf16x3_kernel<MN, EPI, CL><<<grid, TC_THREADS, smem, st>>>(mAh, mAl, mBh, mBl, p);
+  } else {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CL;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16x3_kernel<MN, EPI, CL>, mAh, mAl, mBh, mBl, p);
+    if (e != cudaSuccess) {
+      prof_end(st);
+      return cuda_fail(e, "cudaLaunchKernelEx(gemm cluster)");
+    }
+  }
   prof_end(st);
   GANTTS_LAUNCH_CHECK("gemm_bf16x3_kernel");
   return GANTTS_OK;
+}
+
+static int use_cluster() {
+  static int v = -1;
+  if (v < 0) {
+    // Measured on B200 (profiles/r01_gemm_experiments.md): multicasting the B tile across a 2-CTA cluster
+    // does not help -- the limiter is the per-SM L2->SM ingest rate (~38 B/clk), which multicast does not
+    // reduce -- so the default stays 1; GANTTS_B200_CLUSTER=2 keeps the (tested) path selectable.
+    const char* e = getenv("GANTTS_B200_CLUSTER");
+    v = e ? atoi(e) : 1;
+  }
+  return v;
 }
 
 // out[rows_a][cols_b] = epi(A * B^T)   (K-major planes A [rows_a][red], B [cols_b][red]).
@@ -679,16 +739,25 @@ static int launch_gemm_kk(const Planes& A, const Planes& B, const EpiArgs& e, cu
   // bias staged in smem after the barrier block when it fits (padded to whole column tiles)
   p.bias_off = (e.bias && (size_t)p.num_b * p.bn * sizeof(float) <= TC_BIAS_SMEM)
                    ? (uint32_t)p.num_stages * p.stage_bytes + 256u : 0u;
+  // 2-CTA clusters (B tile multicast) when there are at least two row tiles
+  const bool cl2 = use_cluster() == 2 && p.num_a >= 2;
   CUtensorMap mAh, mAl, mBh, mBl;
   int rc;
   if ((rc = make_map(&mAh, A.hi, A.rows, A.cols, A.pitch, TC_BM))) return rc;
   if ((rc = make_map(&mAl, A.lo, A.rows, A.cols, A.pitch, TC_BM))) return rc;
-  if ((rc = make_map(&mBh, B.hi, B.rows, B.cols, B.pitch, p.bn))) return rc;
-  if ((rc = make_map(&mBl, B.lo, B.rows, B.cols, B.pitch, p.bn))) return rc;
+  if ((rc = make_map(&mBh, B.hi, B.rows, B.cols, B.pitch, cl2 ? p.bn / 2 : p.bn))) return rc;
+  if ((rc = make_map(&mBl, B.lo, B.rows, B.cols, B.pitch, cl2 ? p.bn / 2 : p.bn))) return rc;
+  if (cl2) {
+    switch (e.epi) {
+      case EPI_F32: return launch_kernel<false, EPI_F32, 2>(mAh, mAl, mBh, mBl, p, st);
+      case EPI_PLANES_FWD: return launch_kernel<false, EPI_PLANES_FWD, 2>(mAh, mAl, mBh, mBl, p, st);
+      case EPI_PLANES_BWD: return launch_kernel<false, EPI_PLANES_BWD, 2>(mAh, mAl, mBh, mBl, p, st);
+    }
+  }
   switch (e.epi) {
-    case EPI_F32: return launch_kernel<false, EPI_F32>(mAh, mAl, mBh, mBl, p, st);
-    case EPI_PLANES_FWD: return launch_kernel<false, EPI_PLANES_FWD>(mAh, mAl, mBh, mBl, p, st);
-    case EPI_PLANES_BWD: return launch_kernel<false, EPI_PLANES_BWD>(mAh, mAl, mBh, mBl, p, st);
+    case EPI_F32: return launch_kernel<false, EPI_F32, 1>(mAh, mAl, mBh, mBl, p, st);
+    case EPI_PLANES_FWD: return launch_kernel<false, EPI_PLANES_FWD, 1>(mAh, mAl, mBh, mBl, p, st);
+    case EPI_PLANES_BWD: return launch_kernel<false, EPI_PLANES_BWD, 1>(mAh, mAl, mBh, mBl, p, st);
   }
   set_error("gemm_kk: bad epilogue %d", e.epi);
   return GANTTS_E_BADARG;
@@ -753,7 +822,7 @@ static int launch_gemm_mn(const Planes& A, const Planes& B, float* C, float* gb,
   if ((rc = make_map(&mAl, A.lo, A.rows, A.cols, A.pitch, TC_BK))) return rc;
   if ((rc = make_map(&mBh, B.hi, B.rows, B.cols, B.pitch, TC_BK))) return rc;
   if ((rc = make_map(&mBl, B.lo, B.rows, B.cols, B.pitch, TC_BK))) return rc;
-  if ((rc = launch_kernel<true, EPI_F32>(mAh, mAl, mBh, mBl, p, st))) return rc;
+  if ((rc = launch_kernel<true, EPI_F32, 1>(mAh, mAl, mBh, mBl, p, st))) return rc;
   if (!direct) {
     splitk_reduce_kernel<<<(unsigned)((n + 1023) / 1024), 256, 0, st>>>(partial, splits, n, C, accumulate);
     GANTTS_LAUNCH_CHECK("splitk_reduce_kernel(tc gW)");
