@@ -111,6 +111,11 @@ SIGNATURES = {
     "gantts_gan_step_grad_buffer": (_i, [ctypes.POINTER(GanStepT), _vp, _i, ctypes.POINTER(ctypes.c_void_p),
                                          ctypes.POINTER(ctypes.c_int64)]),
     "gantts_gan_step": (_i, [ctypes.POINTER(GanStepT), _i, _vp, _vp, _vp, _f, _u64, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "gantts_lstm_workspace_bytes": (_sz, []),
+    "gantts_lstm_layer_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "gantts_lstm_layer_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "gantts_lstm_hprev": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "gantts_dropout": (_i, [_vp, _vp, _i64, _i, _f, _u64, _vp]),
     "gantts_optim_workspace_bytes": (_sz, []),
     "gantts_grad_sumsq": (_i, [_vp, _vp, _i, _vp, _vp, _sz, _vp]),
     "gantts_clip_adagrad_step": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _f, _f, _f, _f, _vp]),

@@ -9,3 +9,4 @@
 #include "linear.cu"
 #include "optim.cu"
 #include "gan_step.cu"
+#include "lstm.cu"

@@ -6,6 +6,7 @@ from torch import nn
 from . import _lib
 from . import config
 from . import ops
+from . import rnn
 
 
 class AbstractModel(object):
@@ -80,3 +81,63 @@ class In2OutHighwayNet(AbstractModel, nn.Module):
         h = _mlp(x, self.H, self.last_linear, self.dropout_p, self.training, _lib.ACT_NONE, self.engine)
         Gx = ops.unit_variance_mlpg(R, h)
         return h, ops.highway_combine(x_static, Tx, Gx)
+
+
+class In2OutRNNHighwayNet(AbstractModel, nn.Module):
+    """LSTM variant of the highway network (reference gantts/models.py:72-118).  NOTE: like the
+    reference it returns its INPUT ``x`` as the first output (``:118``).
+    state_dict keys: ``T.*``, ``lstm.weight_ih_l{k}[_reverse]`` ..., ``hidden2out.*``."""
+
+    def __init__(self, in_dim=118, out_dim=118, static_dim=118 // 2,
+                 num_hidden=3, hidden_dim=512, bidirectional=False, dropout=0.5):
+        super(In2OutRNNHighwayNet, self).__init__()
+        self.static_dim = static_dim
+        self.num_direction = 2 if bidirectional else 1
+        self.T = nn.Linear(static_dim, static_dim)
+        self.lstm = nn.LSTM(in_dim, hidden_dim, num_hidden, batch_first=True,
+                            bidirectional=bidirectional, dropout=dropout)
+        self.hidden2out = nn.Linear(hidden_dim * self.num_direction, out_dim)
+        self.engine = None
+
+    def include_parameter_generation(self):
+        return True
+
+    def forward(self, x, R, lengths=None):
+        x = x.unsqueeze(0) if x.dim() == 2 else x
+        x_static = x[:, :, :self.static_dim]
+        Tx = ops.linear_act(x_static, self.T.weight, self.T.bias, _lib.ACT_SIGMOID, engine=self.engine)
+        output = rnn.lstm_forward(self.lstm, x, lengths, self.training, self.engine)
+        output = ops.linear_act(output, self.hidden2out.weight, self.hidden2out.bias, _lib.ACT_NONE,
+                                engine=self.engine)
+        Gx = ops.unit_variance_mlpg(R, output)
+        return x, ops.highway_combine(x_static, Tx, Gx)
+
+
+class _LSTMNet(AbstractModel, nn.Module):
+    """pack -> nn.LSTM -> pad -> Linear (-> sigmoid), reference gantts/models.py:170-213."""
+    _rnn_attr = "lstm"
+
+    def __init__(self, in_dim=118, out_dim=118, num_hidden=2, hidden_dim=256,
+                 bidirectional=False, dropout=0, last_sigmoid=False):
+        super(_LSTMNet, self).__init__()
+        self.num_direction = 2 if bidirectional else 1
+        setattr(self, self._rnn_attr, nn.LSTM(in_dim, hidden_dim, num_hidden, batch_first=True,
+                                              bidirectional=bidirectional, dropout=dropout))
+        self.hidden2out = nn.Linear(hidden_dim * self.num_direction, out_dim)
+        self.last_sigmoid = last_sigmoid
+        self.engine = None
+
+    def forward(self, sequence, lengths):
+        output = rnn.lstm_forward(getattr(self, self._rnn_attr), sequence, lengths, self.training, self.engine)
+        act = _lib.ACT_SIGMOID if self.last_sigmoid else _lib.ACT_NONE
+        return ops.linear_act(output, self.hidden2out.weight, self.hidden2out.bias, act, engine=self.engine)
+
+
+class LSTMRNN(_LSTMNet):
+    """reference gantts/models.py:193-213; state_dict prefix ``lstm.``."""
+    _rnn_attr = "lstm"
+
+
+class GRURNN(_LSTMNet):
+    """reference gantts/models.py:170-190 -- despite the name an nn.LSTM stored as ``.gru``."""
+    _rnn_attr = "gru"

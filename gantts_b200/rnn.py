@@ -1,0 +1,138 @@
+"""nn.LSTM replacement on the native kernels: input projections of all time steps as one tensor-core
+GEMM, the recurrence in gantts_lstm_layer_fwd/bwd (persistent cooperative kernel), packed-sequence
+semantics of reference gantts/models.py:101-112,182-187,205-210 (pack_padded_sequence ->
+nn.LSTM -> pad_packed_sequence) without packing: outputs beyond each length are zero, the reverse
+direction starts at the last valid frame."""
+import ctypes
+
+import torch
+
+from . import _lib
+from . import config
+from . import ops
+
+
+class _LSTMLayer(torch.autograd.Function):
+    """One (bi)directional LSTM layer.  W_ih: [ndir*4H, I] (direction-stacked), W_hh: [ndir, 4H, H],
+    bias: [ndir*4H] (= b_ih + b_hh)."""
+
+    @staticmethod
+    def forward(ctx, x, lengths, W_ih, W_hh, bias, engine):
+        ops.require_cuda(x, W_ih, W_hh, bias)
+        lib = _lib.load()
+        B, T, I = x.shape
+        ndir, G4, H = W_hh.shape
+        x2 = x.contiguous().view(B * T, I)
+        W_ih, W_hh, bias = W_ih.contiguous(), W_hh.contiguous(), bias.contiguous()
+        dev = x.device
+        xproj = torch.empty(B * T, ndir * G4, dtype=torch.float32, device=dev)
+        ws = ops.workspace(lib.gantts_linear_workspace_bytes(B * T, ndir * G4, I, engine), dev)
+        _lib.check(lib.gantts_linear_fwd(x2.data_ptr(), I, W_ih.data_ptr(), bias.data_ptr(), xproj.data_ptr(),
+                                         ndir * G4, B * T, ndir * G4, I, _lib.ACT_NONE, 0.0, 0.0, 0, engine,
+                                         ws.data_ptr(), ws.numel(), ops._stream()))
+        h = torch.empty(B, T, ndir * H, dtype=torch.float32, device=dev)
+        gates = torch.zeros(ndir, B, T, G4, dtype=torch.float32, device=dev)
+        cells = torch.zeros(ndir, B, T, H, dtype=torch.float32, device=dev)
+        bar = ops.workspace(lib.gantts_lstm_workspace_bytes(), dev, "lstm_bar")
+        _lib.check(lib.gantts_lstm_layer_fwd(xproj.data_ptr(), W_hh.data_ptr(), lengths.data_ptr(), h.data_ptr(),
+                                             gates.data_ptr(), cells.data_ptr(), B, T, H, ndir, bar.data_ptr(),
+                                             bar.numel(), ops._stream()))
+        ctx.save_for_backward(x2, lengths, W_ih, W_hh, h, gates, cells)
+        ctx.engine, ctx.dims = engine, (B, T, I, H, ndir, bias is not None)
+        return h
+
+    @staticmethod
+    def backward(ctx, dh):
+        lib = _lib.load()
+        x2, lengths, W_ih, W_hh, h, gates, cells = ctx.saved_tensors
+        B, T, I, H, ndir, _ = ctx.dims
+        G4, dev, eng = 4 * H, dh.device, ctx.engine
+        dh = dh.contiguous()
+        dxproj = torch.empty(B * T, ndir * G4, dtype=torch.float32, device=dev)
+        bar = ops.workspace(lib.gantts_lstm_workspace_bytes(), dev, "lstm_bar")
+        _lib.check(lib.gantts_lstm_layer_bwd(dh.data_ptr(), W_hh.data_ptr(), lengths.data_ptr(), gates.data_ptr(),
+                                             cells.data_ptr(), dxproj.data_ptr(), B, T, H, ndir, bar.data_ptr(),
+                                             bar.numel(), ops._stream()))
+        M = B * T
+        need_gx = ctx.needs_input_grad[0]
+        gx = torch.empty(M, I, dtype=torch.float32, device=dev) if need_gx else None
+        gW_ih = torch.empty_like(W_ih)
+        gb = torch.empty(ndir * G4, dtype=torch.float32, device=dev)
+        gz = torch.empty(M, ndir * G4, dtype=torch.float32, device=dev)
+        ws = ops.workspace(lib.gantts_linear_workspace_bytes(M, ndir * G4, max(I, H), eng), dev)
+        # dx, dW_ih, dbias from the direction-stacked projection (act NONE: gz = dxproj)
+        _lib.check(lib.gantts_linear_bwd(dxproj.data_ptr(), ndir * G4, dxproj.data_ptr(), ndir * G4, x2.data_ptr(), I,
+                                         W_ih.data_ptr(), gz.data_ptr(), gx.data_ptr() if gx is not None else None, I,
+                                         gW_ih.data_ptr(), gb.data_ptr(), M, ndir * G4, I, _lib.ACT_NONE, 0.0, 0.0, 0,
+                                         eng, ws.data_ptr(), ws.numel(), ops._stream()))
+        # dW_hh[dir] = dxproj_dir^T h_prev
+        gW_hh = torch.empty_like(W_hh)
+        hprev = torch.empty(M, H, dtype=torch.float32, device=dev)
+        gzd = torch.empty(M, G4, dtype=torch.float32, device=dev)
+        for d in range(ndir):
+            _lib.check(lib.gantts_lstm_hprev(h.data_ptr(), lengths.data_ptr(), hprev.data_ptr(), B, T, H, ndir, d,
+                                             ops._stream()))
+            dxd = dxproj[:, d * G4:(d + 1) * G4]
+            _lib.check(lib.gantts_linear_bwd(dxd.data_ptr(), ndir * G4, dxd.data_ptr(), ndir * G4, hprev.data_ptr(), H,
+                                             W_hh[d].data_ptr(), gzd.data_ptr(), None, H, gW_hh[d].data_ptr(), None,
+                                             M, G4, H, _lib.ACT_NONE, 0.0, 0.0, 0, eng, ws.data_ptr(), ws.numel(),
+                                             ops._stream()))
+        return (gx.view(B, T, I) if gx is not None else None), None, gW_ih, gW_hh, gb, None
+
+
+class _Dropout(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, p, seed):
+        ops.require_cuda(x)
+        lib = _lib.load()
+        x = x.contiguous()
+        y = torch.empty_like(x)
+        cols = x.shape[-1]
+        _lib.check(lib.gantts_dropout(x.data_ptr(), y.data_ptr(), x.numel() // cols, cols, p, seed, ops._stream()))
+        ctx.cfg = (p, seed)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = _lib.load()
+        p, seed = ctx.cfg
+        gy = gy.contiguous()
+        gx = torch.empty_like(gy)
+        cols = gy.shape[-1]
+        _lib.check(lib.gantts_dropout(gy.data_ptr(), gx.data_ptr(), gy.numel() // cols, cols, p, seed, ops._stream()))
+        return gx, None, None
+
+
+def lengths_tensor(lengths, B, T, device):
+    """Accepts what the reference passes as `lengths` (list of ints / 0-d tensors, LongTensor, None)."""
+    if lengths is None:
+        return torch.full((B,), T, dtype=torch.int64, device=device)
+    if torch.is_tensor(lengths):
+        return lengths.to(device=device, dtype=torch.int64).contiguous().view(-1)
+    return torch.tensor([int(v) for v in lengths], dtype=torch.int64, device=device)
+
+
+def lstm_forward(lstm, x, lengths, training, engine=None):
+    """Run the weights of a torch ``nn.LSTM`` (batch_first) through the native kernels.
+    x: (B, T, I) CUDA; returns (B, T_out, dirs*H) with T_out = max(lengths) like pad_packed_sequence."""
+    if not lstm.batch_first:
+        raise RuntimeError("gantts_b200: only batch_first LSTMs are supported")
+    eng = config.engine_id(engine)
+    B, T, _ = x.shape
+    lens = lengths_tensor(lengths, B, T, x.device)
+    ndir = 2 if lstm.bidirectional else 1
+    h = x
+    for k in range(lstm.num_layers):
+        sfx = ["", "_reverse"][:ndir]
+        W_ih = torch.cat([getattr(lstm, "weight_ih_l%d%s" % (k, s)) for s in sfx], 0)
+        W_hh = torch.stack([getattr(lstm, "weight_hh_l%d%s" % (k, s)) for s in sfx], 0)
+        bias = torch.cat([getattr(lstm, "bias_ih_l%d%s" % (k, s)) + getattr(lstm, "bias_hh_l%d%s" % (k, s))
+                          for s in sfx], 0)
+        h = _LSTMLayer.apply(h, lens, W_ih, W_hh, bias, eng)
+        if training and lstm.dropout > 0 and k + 1 < lstm.num_layers:
+            h = _Dropout.apply(h, float(lstm.dropout), ops.draw_seed())
+    if lengths is not None:
+        t_out = int(max(int(v) for v in lengths)) if not torch.is_tensor(lengths) else int(lengths.max().item())
+        if t_out < T:
+            h = h[:, :t_out]
+    return h

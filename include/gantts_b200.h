@@ -232,6 +232,35 @@ int gantts_clip_adagrad_step(float* const* params, float* const* grads, float* c
                              float max_norm, float lr, float weight_decay, float eps, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * LSTM layer with packed-sequence semantics (reference gantts/models.py:84-85 In2OutRNNHighwayNet,
+ * :175-176 GRURNN -- an nn.LSTM --, :198-199 LSTMRNN; pack_padded_sequence / pad_packed_sequence at
+ * :101-112,182-187,205-210).  Gate order i,f,g,o and weight layout of torch.nn.LSTM.
+ *
+ * xproj  [B][T][ndir*4H] = x W_ih^T + b_ih + b_hh for every time step (one tensor-core GEMM, e.g.
+ *        gantts_linear_fwd with the direction-stacked W_ih), direction-major columns.
+ * W_hh   [ndir][4H][H].   lengths_dev int64[B] (any order).   ndir = 1 or 2 (bidirectional).
+ * h_out  [B][T][ndir*H]: hidden states, ZERO for t >= lengths[b]; the reverse direction starts at
+ *        t = lengths[b]-1.   gates [ndir][B][T][4H] / cells [ndir][B][T][H]: saved for the backward.
+ * One cooperative launch runs all T steps of both directions (persistent CTAs, W_hh slices resident in
+ * shared memory, one grid barrier per step).  workspace: gantts_lstm_workspace_bytes() bytes.
+ */
+size_t gantts_lstm_workspace_bytes(void);
+int gantts_lstm_layer_fwd(const float* xproj, const float* W_hh, const int64_t* lengths_dev, float* h_out,
+                          float* gates, float* cells, int B, int T, int H, int ndir, void* workspace,
+                          size_t workspace_bytes, void* stream);
+/* dxproj [B][T][ndir*4H] = dL/d(xproj) by back-propagation through time from dh_out = dL/dh_out. */
+int gantts_lstm_layer_bwd(const float* dh_out, const float* W_hh, const int64_t* lengths_dev,
+                          const float* gates, const float* cells, float* dxproj, int B, int T, int H,
+                          int ndir, void* workspace, size_t workspace_bytes, void* stream);
+/* hprev[b][t][:] = h_out[b][t-1 (dir 0) | t+1 (dir 1)][dir*H:(dir+1)*H], zero at the first step of each
+ * sequence and beyond its length: the right operand of dW_hh[dir] = dxproj_dir^T hprev. */
+int gantts_lstm_hprev(const float* h_out, const int64_t* lengths_dev, float* hprev, int B, int T, int H,
+                      int ndir, int dir, void* stream);
+/* y = keep ? x/(1-p) : 0 with the counter-hash mask (inter-layer dropout of nn.LSTM(dropout=p)); applying
+ * the same call to the gradient is the backward. */
+int gantts_dropout(const float* x, float* y, int64_t rows, int cols, float p, uint64_t seed, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Fused GAN training step: one call enqueues the whole mini-batch of reference train.py:528-580
  * (batch prologue :528-535, apply_generator :336-355, update_discriminator :245-279,
  * update_generator :282-320, both clip_grad_norm_ + Adagrad steps) on `stream`, no host sync.

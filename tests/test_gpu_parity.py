@@ -609,3 +609,80 @@ def test_fused_step_matches_modular_trainer_with_dropout(dev):
     got = fs.loss_dict()
     for k in ("loss_d", "loss_mge", "loss_adv", "loss_g"):
         assert abs(got[k] - float(out[k])) <= 0.03 * abs(float(out[k])), (k, got[k], float(out[k]))
+
+
+# --------------------------------------------------------------------------------- LSTM
+def _lstm_case(dev, B, Tn, I, H, layers, bidir, lens, engine="tc"):
+    import gantts_b200
+    torch.manual_seed(13)
+    ref = torch.nn.LSTM(I, H, layers, batch_first=True, bidirectional=bidir)
+    h2o = torch.nn.Linear(H * (2 if bidir else 1), 9)
+    x = torch.randn(B, Tn, I)
+    for b, n in enumerate(lens):
+        x[b, n:] = 0
+    xr = x.clone().requires_grad_(True)
+    packed = torch.nn.utils.rnn.pack_padded_sequence(xr, lens, batch_first=True)
+    out, _ = ref(packed)
+    out, _ = torch.nn.utils.rnn.pad_packed_sequence(out, batch_first=True)
+    yr = h2o(out)
+    g = torch.randn_like(yr)
+    yr.backward(g)
+    m = gantts_b200.models.LSTMRNN(I, 9, layers, H, bidirectional=bidir, dropout=0.0)
+    m.lstm.load_state_dict(ref.state_dict())
+    m.hidden2out.load_state_dict(h2o.state_dict())
+    m.to(dev).train()
+    m.engine = engine
+    xg = x.to(dev).requires_grad_(True)
+    yg = m(xg, lens)
+    yg.backward(g.to(dev))
+    errs = {"y": rel_err(npy(yg), npy(yr)), "gx": rel_err(npy(xg.grad), npy(xr.grad))}
+    for (k, pg), (_, pr) in zip(m.lstm.named_parameters(), ref.named_parameters()):
+        errs[k] = rel_err(npy(pg.grad), npy(pr.grad))
+    errs["h2o"] = rel_err(npy(m.hidden2out.weight.grad), npy(h2o.weight.grad))
+    assert yg.shape == yr.shape
+    return errs
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_lstm_golden_forward(dev, golden_models, engine):
+    import gantts_b200
+    g = golden_models
+    m = gantts_b200.models.LSTMRNN(in_dim=12, out_dim=9, num_hidden=2, hidden_dim=16, bidirectional=True, dropout=0.0)
+    m.load_state_dict({k[len("lstm_"):]: torch.from_numpy(g[k]) for k in g.files
+                       if k.startswith("lstm_lstm.") or k.startswith("lstm_hidden2out.")})
+    m.to(dev).eval()
+    m.engine = engine
+    y = m(T(g["lstm_x"], dev), [int(v) for v in g["lstm_lengths"]])
+    assert rel_err(npy(y), g["lstm_y"]) < TOL[engine]
+    assert list(m.state_dict())[:4] == ["lstm.weight_ih_l0", "lstm.weight_hh_l0", "lstm.bias_ih_l0", "lstm.bias_hh_l0"]
+
+
+@pytest.mark.parametrize("B,Tn,I,H,layers,bidir,lens", [
+    (3, 14, 12, 16, 2, True, [14, 9, 6]),
+    (2, 7, 5, 8, 1, False, [7, 7]),
+    (5, 33, 20, 64, 3, True, [33, 30, 21, 8, 1]),
+    (17, 40, 24, 32, 2, True, [40] * 9 + [25] * 8),
+])
+def test_lstm_fwd_bwd_vs_torch_cpu(dev, B, Tn, I, H, layers, bidir, lens):
+    """Packed-sequence (bi)LSTM stacks, forward + all gradients vs torch CPU nn.LSTM (the oracle the
+    reference itself uses, models.py:198-213)."""
+    errs = _lstm_case(dev, B, Tn, I, H, layers, bidir, lens)
+    assert max(errs.values()) < 2e-4, errs
+
+
+def test_lstm_cfg3_width(dev):
+    """VC BiLSTM width of BASELINE cfg3 (in 177, H 512, bidirectional) on a short batch."""
+    errs = _lstm_case(dev, 4, 60, 177, 512, 1, True, [60, 51, 40, 33])
+    assert max(errs.values()) < 2e-4, errs
+
+
+def test_in2out_rnn_highway_returns_input(dev):
+    import gantts_b200
+    m = gantts_b200.models.In2OutRNNHighwayNet(in_dim=30, out_dim=30, static_dim=10, num_hidden=1, hidden_dim=16,
+                                               bidirectional=True, dropout=0.0).to(dev)
+    x = torch.randn(2, 21, 30, device=dev)
+    R = T(nnp.unit_variance_mlpg_matrix(WINDOWS, 21), dev)
+    y, ys = m(x, R, lengths=[21, 17])
+    assert y is x and ys.shape == (2, 21, 10)
+    g = gantts_b200.models.GRURNN(in_dim=6, out_dim=4, num_hidden=1, hidden_dim=8).to(dev)
+    assert "gru.weight_ih_l0" in g.state_dict() and g(torch.randn(2, 5, 6, device=dev), [5, 3]).shape == (2, 5, 4)
