@@ -10,3 +10,4 @@
 #include "optim.cu"
 #include "gan_step.cu"
 #include "lstm.cu"
+#include "sru.cu"

@@ -141,3 +141,25 @@ class LSTMRNN(_LSTMNet):
 class GRURNN(_LSTMNet):
     """reference gantts/models.py:170-190 -- despite the name an nn.LSTM stored as ``.gru``."""
     _rnn_attr = "gru"
+
+
+class SRURNN(AbstractModel, nn.Module):
+    """SRU generator (reference gantts/models.py:144-167; the hparams default for TTS).  The upstream
+    ``cuda_functional.SRU`` is replaced by ``gantts_b200.rnn.SRU`` (same recurrence, parameters under
+    ``gru.rnn_lst.{i}.weight/bias``); like the reference it IGNORES ``lengths``."""
+
+    def __init__(self, in_dim=118, out_dim=118, num_hidden=2, hidden_dim=256,
+                 bidirectional=False, dropout=0, last_sigmoid=False,
+                 use_relu=0, rnn_dropout=0.0):
+        super(SRURNN, self).__init__()
+        self.num_direction = 2 if bidirectional else 1
+        self.gru = rnn.SRU(in_dim, hidden_dim, num_hidden, bidirectional=bidirectional, dropout=dropout,
+                           use_relu=use_relu, rnn_dropout=rnn_dropout)
+        self.hidden2out = nn.Linear(hidden_dim * self.num_direction, out_dim)
+        self.last_sigmoid = last_sigmoid
+        self.engine = None
+
+    def forward(self, sequence, lengths):
+        output = self.gru(sequence, engine=self.engine)
+        act = _lib.ACT_SIGMOID if self.last_sigmoid else _lib.ACT_NONE
+        return ops.linear_act(output, self.hidden2out.weight, self.hidden2out.bias, act, engine=self.engine)

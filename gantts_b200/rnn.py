@@ -136,3 +136,95 @@ def lstm_forward(lstm, x, lengths, training, engine=None):
         if t_out < T:
             h = h[:, :t_out]
     return h
+
+
+# ------------------------------------------------------------------------------------ SRU
+class _SRUScan(torch.autograd.Function):
+    """h, = SRU v1 scan over u = x W (see csrc/sru.cu).  u: (B,T,ncols*k); x_hw: (B,T,ncols) or None."""
+
+    @staticmethod
+    def forward(ctx, u, x_hw, bias, mask_h, d, k, bidir, act):
+        ops.require_cuda(u, bias)
+        lib = _lib.load()
+        B, T, _ = u.shape
+        ncols = d * (2 if bidir else 1)
+        u = u.contiguous()
+        xh = x_hw.contiguous() if x_hw is not None else None
+        mh = mask_h.contiguous() if mask_h is not None else None
+        h = torch.empty(B, T, ncols, dtype=torch.float32, device=u.device)
+        c = torch.empty(B, T, ncols, dtype=torch.float32, device=u.device)
+        _lib.check(lib.gantts_sru_fwd(u.data_ptr(), xh.data_ptr() if xh is not None else None, bias.data_ptr(),
+                                      mh.data_ptr() if mh is not None else None, h.data_ptr(), c.data_ptr(),
+                                      B, T, d, k, int(bidir), act, ops._stream()))
+        ctx.save_for_backward(u, xh if xh is not None else u.new_empty(0), bias,
+                              mh if mh is not None else u.new_empty(0), c)
+        ctx.cfg = (d, k, bidir, act, xh is not None, mh is not None)
+        return h
+
+    @staticmethod
+    def backward(ctx, dh):
+        lib = _lib.load()
+        u, xh, bias, mh, c = ctx.saved_tensors
+        d, k, bidir, act, has_x, has_m = ctx.cfg
+        B, T, _ = u.shape
+        ncols = d * (2 if bidir else 1)
+        dh = dh.contiguous()
+        du = torch.empty_like(u)
+        dx = torch.zeros(B, T, ncols, dtype=torch.float32, device=u.device) if has_x else None
+        part = torch.empty(B, 2 * ncols, dtype=torch.float32, device=u.device)
+        _lib.check(lib.gantts_sru_bwd(u.data_ptr(), xh.data_ptr() if has_x else None, bias.data_ptr(),
+                                      mh.data_ptr() if has_m else None, c.data_ptr(), dh.data_ptr(), du.data_ptr(),
+                                      dx.data_ptr() if has_x else None, part.data_ptr(), B, T, d, k, int(bidir), act,
+                                      ops._stream()))
+        return du, dx, part.sum(0), None, None, None, None, None
+
+
+class SRUCell(torch.nn.Module):
+    """Parameters of one SRU layer with the shapes/initialisation of the upstream 2017 implementation:
+    weight (n_in, dirs*n_out*k), bias (dirs*n_out*2); k = 3 when n_in == dirs*n_out else 4."""
+
+    def __init__(self, n_in, n_out, dropout=0.0, rnn_dropout=0.0, bidirectional=False, use_tanh=1, use_relu=0):
+        super(SRUCell, self).__init__()
+        self.n_in, self.n_out, self.bidirectional = n_in, n_out, bidirectional
+        self.dropout, self.rnn_dropout = dropout, rnn_dropout
+        self.activation_type = 2 if use_relu else (1 if use_tanh else 0)
+        out_size = n_out * 2 if bidirectional else n_out
+        self.k = 4 if n_in != out_size else 3
+        self.weight = torch.nn.Parameter(torch.empty(n_in, out_size * self.k))
+        self.bias = torch.nn.Parameter(torch.zeros(out_size * 2))
+        val_range = (3.0 / n_in) ** 0.5
+        torch.nn.init.uniform_(self.weight, -val_range, val_range)
+
+    def forward(self, x, engine=None):
+        """x: (B, T, n_in) -> (B, T, dirs*n_out)."""
+        B, T, _ = x.shape
+        ncols = self.n_out * (2 if self.bidirectional else 1)
+        if self.training and self.rnn_dropout > 0:        # variational: one mask per sequence, shared over time
+            ones = torch.ones(B, 1, self.n_in, device=x.device)
+            x = x * _Dropout.apply(ones, float(self.rnn_dropout), ops.draw_seed())
+        u = ops.linear_act(x, self.weight.t().contiguous(), None, _lib.ACT_NONE, engine=engine)
+        mask_h = None
+        if self.training and self.dropout > 0:
+            mask_h = _Dropout.apply(torch.ones(B, ncols, device=x.device), float(self.dropout), ops.draw_seed())
+        x_hw = x if self.k == 3 else None
+        return _SRUScan.apply(u, x_hw, self.bias, mask_h, self.n_out, self.k, self.bidirectional,
+                              self.activation_type)
+
+
+class SRU(torch.nn.Module):
+    """Stack of SRU layers (``rnn_lst``) like upstream ``cuda_functional.SRU``; batch-first here."""
+
+    def __init__(self, input_size, hidden_size, num_layers=2, dropout=0.0, rnn_dropout=0.0, bidirectional=False,
+                 use_tanh=1, use_relu=0):
+        super(SRU, self).__init__()
+        self.rnn_lst = torch.nn.ModuleList()
+        out_size = hidden_size * 2 if bidirectional else hidden_size
+        for i in range(num_layers):
+            self.rnn_lst.append(SRUCell(input_size if i == 0 else out_size, hidden_size,
+                                        dropout=dropout if i + 1 != num_layers else 0.0, rnn_dropout=rnn_dropout,
+                                        bidirectional=bidirectional, use_tanh=use_tanh, use_relu=use_relu))
+
+    def forward(self, x, engine=None):
+        for cell in self.rnn_lst:
+            x = cell(x, engine=engine)
+        return x

@@ -261,6 +261,22 @@ int gantts_lstm_hprev(const float* h_out, const int64_t* lengths_dev, float* hpr
 int gantts_dropout(const float* x, float* y, int64_t rows, int cols, float p, uint64_t seed, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * SRU v1 scan (third-party cuda_functional.SRU imported by reference gantts/models.py:144-167 SRURNN;
+ * github.com/taolei87/sru is not vendored and untested by the reference: parity unpinned).
+ * u [B][T][ncols*k] = x W (tensor-core GEMM by the caller), ncols = d * (bidir ? 2 : 1), k = 3 or 4 values per
+ * column (k fastest): candidate, forget pre-activation, reset pre-activation[, highway input];
+ * x [B][T][ncols] is the highway input when k == 3; bias [2*ncols] = forget | reset; mask_h [B][ncols]
+ * optional (already scaled) output dropout mask shared over time; act: 0 identity, 1 tanh, 2 relu.
+ * Outputs h, c [B][T][ncols].  Backward: du [B][T][ncols*k], dx += (k == 3), dbias_part [B][2*ncols]
+ * (sum over B gives the bias gradient).
+ */
+int gantts_sru_fwd(const float* u, const float* x, const float* bias, const float* mask_h, float* h, float* c,
+                   int B, int T, int d, int k, int bidir, int act, void* stream);
+int gantts_sru_bwd(const float* u, const float* x, const float* bias, const float* mask_h, const float* c,
+                   const float* dh, float* du, float* dx, float* dbias_part, int B, int T, int d, int k,
+                   int bidir, int act, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Fused GAN training step: one call enqueues the whole mini-batch of reference train.py:528-580
  * (batch prologue :528-535, apply_generator :336-355, update_discriminator :245-279,
  * update_generator :282-320, both clip_grad_norm_ + Adagrad steps) on `stream`, no host sync.

@@ -284,7 +284,7 @@ def sru_layer_forward(x, W, b, bidirectional=False, use_tanh=False, use_relu=Tru
             f = torch.sigmoid(u[..., 1] + bias[di, 0])
             r = torch.sigmoid(u[..., 2] + bias[di, 1])
             c = f * c + (1 - f) * u[..., 0]
-            xp = x[t] if k == 3 else u[..., 3]
+            xp = x[t][:, di * d:(di + 1) * d] if k == 3 else u[..., 3]
             hs[t] = r * act(c) + (1 - r) * xp
         outs.append(torch.stack(hs, 0))
     return torch.cat(outs, -1)

@@ -686,3 +686,44 @@ def test_in2out_rnn_highway_returns_input(dev):
     assert y is x and ys.shape == (2, 21, 10)
     g = gantts_b200.models.GRURNN(in_dim=6, out_dim=4, num_hidden=1, hidden_dim=8).to(dev)
     assert "gru.weight_ih_l0" in g.state_dict() and g(torch.randn(2, 5, 6, device=dev), [5, 3]).shape == (2, 5, 4)
+
+
+# ---------------------------------------------------------------------------------- SRU
+@pytest.mark.parametrize("n_in,d,bidir,relu", [(24, 12, True, 1), (20, 16, False, 0), (32, 16, True, 0), (16, 16, False, 1)])
+def test_sru_layer_vs_port(dev, n_in, d, bidir, relu):
+    """SRU v1 layer (k = 3 and k = 4, uni/bidirectional) forward + gradients against the torch
+    restatement in oracle/gantts_port.py (parity unpinned: the upstream package is not vendored)."""
+    from gantts_b200 import rnn
+    torch.manual_seed(17)
+    B, Tn = 3, 11
+    cell = rnn.SRUCell(n_in, d, bidirectional=bidir, use_tanh=0 if relu else 1, use_relu=relu)
+    cell.bias.data.uniform_(-0.5, 0.5)
+    x = torch.randn(B, Tn, n_in)
+    xr = x.clone().requires_grad_(True)
+    Wr = cell.weight.detach().clone().requires_grad_(True)
+    br = cell.bias.detach().clone().requires_grad_(True)
+    dirs = 2 if bidir else 1
+    # port layout: bias (dirs, 2, d) = [f | r] per direction; module layout: [f(all cols) | r(all cols)]
+    bport = torch.stack([br[:dirs * d].view(dirs, d), br[dirs * d:].view(dirs, d)], 1).reshape(-1)
+    yr = gp.sru_layer_forward(xr.transpose(0, 1), Wr, bport, bidirectional=bidir, use_tanh=not relu, use_relu=bool(relu))
+    yr = yr.transpose(0, 1)
+    g = torch.randn_like(yr)
+    yr.backward(g)
+    cell.to(dev).eval()
+    xg = x.to(dev).requires_grad_(True)
+    yg = cell(xg, engine="simt")
+    yg.backward(g.to(dev))
+    errs = {"y": rel_err(npy(yg), npy(yr)), "gx": rel_err(npy(xg.grad), npy(xr.grad)),
+            "gW": rel_err(npy(cell.weight.grad), npy(Wr.grad)), "gb": rel_err(npy(cell.bias.grad), npy(br.grad))}
+    assert max(errs.values()) < 2e-5, errs
+
+
+def test_srurnn_model(dev):
+    import gantts_b200
+    m = gantts_b200.models.SRURNN(in_dim=20, out_dim=7, num_hidden=3, hidden_dim=16, bidirectional=True,
+                                  dropout=0.2, use_relu=1, rnn_dropout=0.2).to(dev).train()
+    assert "gru.rnn_lst.0.weight" in m.state_dict() and m.gru.rnn_lst[0].k == 4 and m.gru.rnn_lst[1].k == 3
+    x = torch.randn(4, 30, 20, device=dev, requires_grad=True)
+    y = m(x, [30, 28, 11, 5])            # lengths ignored, like the reference
+    y.sum().backward()
+    assert y.shape == (4, 30, 7) and x.grad is not None and m.gru.rnn_lst[2].weight.grad is not None
