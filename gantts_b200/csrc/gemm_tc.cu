@@ -779,9 +779,62 @@ static size_t mn_partial_bytes(int64_t red, int rows_a, int cols_b, int* splits_
   return ((size_t)splits * ((size_t)rows_a * cols_b + rows_a) * sizeof(float) + 255) / 256 * 256;
 }
 
-// gb (optional) receives the column sums of A (the bias gradient) from the same launch.
+// Deferred deterministic split reductions: several (partial -> out) jobs summed by ONE launch.
+constexpr int REDUCE_MAX_JOBS = 2 * GANTTS_MAX_LAYERS;
+struct ReduceList {
+  int n = 0;
+  const float* partial[REDUCE_MAX_JOBS];
+  float* out[REDUCE_MAX_JOBS];
+  int splits[REDUCE_MAX_JOBS];
+  int64_t len[REDUCE_MAX_JOBS];
+  int64_t off[REDUCE_MAX_JOBS + 1];
+};
+
+__global__ void multi_reduce_kernel(ReduceList rl, int accumulate) {
+  const int64_t total4 = rl.off[rl.n];                        // in units of 4 elements
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int j = 0;
+    while (j + 1 < rl.n && i >= rl.off[j + 1]) ++j;
+    const int64_t e = (i - rl.off[j]) * 4, n = rl.len[j];
+    const float* part = rl.partial[j];
+    float* out = rl.out[j];
+    if (e + 3 < n && (n & 3) == 0) {
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+      for (int z = 0; z < rl.splits[j]; ++z) {
+        const float4 v = *reinterpret_cast<const float4*>(part + (int64_t)z * n + e);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      }
+      float4* o = reinterpret_cast<float4*>(out + e);
+      if (accumulate) { const float4 c = *o; s.x += c.x; s.y += c.y; s.z += c.z; s.w += c.w; }
+      *o = s;
+    } else {
+      for (int64_t q = e; q < e + 4 && q < n; ++q) {
+        float s = 0.f;
+        for (int z = 0; z < rl.splits[j]; ++z) s += part[(int64_t)z * n + q];
+        out[q] = accumulate ? out[q] + s : s;
+      }
+    }
+  }
+}
+
+static int flush_reduce(ReduceList& rl, int accumulate, cudaStream_t st) {
+  if (rl.n == 0) return GANTTS_OK;
+  rl.off[0] = 0;
+  for (int j = 0; j < rl.n; ++j) rl.off[j + 1] = rl.off[j] + (rl.len[j] + 3) / 4;
+  int nb = (int)((rl.off[rl.n] + 255) / 256);
+  if (nb > num_sms() * 8) nb = num_sms() * 8;
+  multi_reduce_kernel<<<nb, 256, 0, st>>>(rl, accumulate);
+  GANTTS_LAUNCH_CHECK("multi_reduce_kernel");
+  rl.n = 0;
+  return GANTTS_OK;
+}
+
+// gb (optional) receives the column sums of A (the bias gradient) from the same launch.  With `defer`
+// the split reductions are queued (the partial buffer must then stay untouched until flush_reduce).
 static int launch_gemm_mn(const Planes& A, const Planes& B, float* C, float* gb, int accumulate, float* partial,
-                          cudaStream_t st) {
+                          cudaStream_t st, ReduceList* defer = nullptr) {
   GemmParams p{};
   p.rows_a = A.cols;
   p.cols_b = (int)B.cols;
@@ -824,6 +877,15 @@ static int launch_gemm_mn(const Planes& A, const Planes& B, float* C, float* gb,
   if ((rc = make_map(&mBl, B.lo, B.rows, B.cols, B.pitch, TC_BK))) return rc;
   if ((rc = launch_kernel<true, EPI_F32, 1>(mAh, mAl, mBh, mBl, p, st))) return rc;
   if (!direct) {
+    if (defer && defer->n + 2 <= REDUCE_MAX_JOBS) {
+      int j = defer->n++;
+      defer->partial[j] = partial; defer->out[j] = C; defer->splits[j] = splits; defer->len[j] = n;
+      if (gb) {
+        j = defer->n++;
+        defer->partial[j] = db_partial; defer->out[j] = gb; defer->splits[j] = splits; defer->len[j] = p.rows_a;
+      }
+      return GANTTS_OK;
+    }
     splitk_reduce_kernel<<<(unsigned)((n + 1023) / 1024), 256, 0, st>>>(partial, splits, n, C, accumulate);
     GANTTS_LAUNCH_CHECK("splitk_reduce_kernel(tc gW)");
     if (gb) {

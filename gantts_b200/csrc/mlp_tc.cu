@@ -177,10 +177,8 @@ extern "C" size_t gantts_mlp_workspace_bytes(const gantts_mlp_t* m, int64_t M) {
   int maxd = 0;
   size_t part = 0;
   for (int l = 0; l <= m->num_layers; ++l) maxd = m->dims[l] > maxd ? m->dims[l] : maxd;
-  for (int l = 0; l < m->num_layers; ++l) {
-    size_t p = mn_partial_bytes(M, m->dims[l + 1], m->dims[l], nullptr, nullptr);
-    part = p > part ? p : part;
-  }
+  for (int l = 0; l < m->num_layers; ++l)       // one partial region per layer: reductions are deferred
+    part += mn_partial_bytes(M, m->dims[l + 1], m->dims[l], nullptr, nullptr) + 256;
   return 4 * plane_bytes(M, maxd) + part + (size_t)MLP_COLSUM_CHUNKS * maxd * sizeof(float) + 2048;
 }
 
@@ -277,7 +275,8 @@ extern "C" int gantts_mlp_bwd(const gantts_mlp_t* m, const float* gy, int64_t gy
   cur += 2 * plane_bytes(M, maxd);
   float* colpart = reinterpret_cast<float*>(cur);
   cur += ((size_t)MLP_COLSUM_CHUNKS * maxd * sizeof(float) + 255) / 256 * 256;
-  float* partial = reinterpret_cast<float*>(cur);
+  char* partial_cur = cur;
+  ReduceList rl;
 
   int pp = 0;
   char* c0 = gbuf[pp];
@@ -294,8 +293,11 @@ extern "C" int gantts_mlp_bwd(const gantts_mlp_t* m, const float* gy, int64_t gy
   for (int l = L - 1; l >= 0; --l) {
     float* gbl = (gb && gb[l]) ? gb[l] : nullptr;
     if (gW && gW[l]) {
-      // gW_l and (via the ones-MMA) gb_l from one launch
-      if ((rc = launch_gemm_mn(G, t.H[l], gW[l], gbl, accumulate, partial, st))) return rc;
+      // gW_l and (via the ones-MMA) gb_l from one launch; the split reductions of all layers are
+      // summed by a single launch at the end
+      float* partial = reinterpret_cast<float*>(partial_cur);
+      partial_cur += mn_partial_bytes(M, m->dims[l + 1], m->dims[l], nullptr, nullptr) + 256;
+      if ((rc = launch_gemm_mn(G, t.H[l], gW[l], gbl, accumulate, partial, st, &rl))) return rc;
     } else if (gbl) {
       if ((rc = colsum_planes(G, gbl, accumulate, colpart, st))) return rc;
     }
@@ -323,5 +325,5 @@ extern "C" int gantts_mlp_bwd(const gantts_mlp_t* m, const float* gy, int64_t gy
       if ((rc = launch_gemm_kk(G, t.Wt[0], e, st))) return rc;
     }
   }
-  return GANTTS_OK;
+  return flush_reduce(rl, accumulate, st);
 }
