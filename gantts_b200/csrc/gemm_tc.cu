@@ -483,6 +483,212 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
   }
 }
 
+// ---------------------------------------------------------------------------- CTA-pair kernel
+// K-major GEMM on CTA pairs (cluster of 2, tcgen05 cta_group::2): one MMA of M = 256 spans both SMs.  Each
+// CTA loads its own 128 rows of A and only HALF of the B tile, so the per-SM operand ingest per unit of MMA
+// work drops by a third against the single-CTA kernel (the measured limiter, profiles/r01_gemm_experiments.md)
+// and the smem stage shrinks to 64 KB (3 stages).  Leader = cluster rank 0: it alone issues the MMAs; its
+// `full` barriers collect the TMA bytes of BOTH CTAs; commits are multicast to both CTAs' barriers; the
+// peer's epilogue warps release the accumulator on the leader's barrier with a remote arrive.
+template <int EPI>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+                 const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
+                 const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = ptx::smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t bar_base = base + p.num_stages * p.stage_bytes;
+  const uint32_t full0 = bar_base, empty0 = bar_base + 8 * TC_MAX_STAGES;
+  const uint32_t tfull0 = bar_base + 16 * TC_MAX_STAGES, tempty0 = tfull0 + 16;
+  const uint32_t tmem_slot = tempty0 + 16;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = ptx::cluster_ctarank();
+  const bool leader = crank == 0;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.num_stages; ++s) {
+      ptx::mbar_init(full0 + 8 * s, 1);
+      ptx::mbar_init(empty0 + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(tfull0 + 8 * a, 1);
+      ptx::mbar_init(tempty0 + 8 * a, 2 * TC_EPI_WARPS);      // both CTAs' epilogue warps (leader's copy is used)
+    }
+    ptx::fence_barrier_init();
+    ptx::prefetch_tensormap(&tmAh);
+    ptx::prefetch_tensormap(&tmAl);
+    ptx::prefetch_tensormap(&tmBh);
+    ptx::prefetch_tensormap(&tmBl);
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc_pair(tmem_slot, p.tmem_cols);
+    ptx::tmem_relinquish_pair();
+  }
+  const float* bias_s = nullptr;
+  if (p.bias_off) {
+    float* bs = reinterpret_cast<float*>(smem_raw + (base + p.bias_off - raw));
+    const int nb = p.num_b * p.bn;
+    for (int i = threadIdx.x; i < nb; i += TC_THREADS) bs[i] = i < p.cols_b ? p.bias[i] : 0.f;
+    bias_s = bs;
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+
+  const int num_pairs = (p.num_a + 1) / 2;
+  const int total_tiles = num_pairs * p.num_b;
+  const int first_tile = (int)blockIdx.x / 2, tile_step = (int)gridDim.x / 2;
+  const int half_bn = p.bn / 2;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------------------------------------ TMA producer (both CTAs)
+      uint32_t s = 0, ph = 0;
+      for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
+        const int ta = (tile / p.num_b) * 2 + (int)crank, tb = tile % p.num_b;
+        const int a0 = ta * TC_BM, b0 = tb * p.bn + (int)crank * half_bn;
+        for (int64_t r0 = 0; r0 < p.red; r0 += TC_BK) {
+          ptx::mbar_wait(empty0 + 8 * s, ph ^ 1);
+          const uint32_t fb_local = full0 + 8 * s;
+          if (leader) ptx::mbar_expect_tx(fb_local, 2 * p.tx_bytes);   // bytes of both CTAs land on this barrier
+          const uint32_t fb = ptx::mapa(fb_local, 0);
+          const uint32_t sa_hi = base + s * p.stage_bytes, sa_lo = sa_hi + TC_A_PLANE;
+          const uint32_t sb_hi = sa_lo + TC_A_PLANE, sb_lo = sb_hi + p.b_plane_bytes;
+          ptx::tma_load_2d_pair(sa_hi, &tmAh, fb, (int32_t)r0, a0);
+          ptx::tma_load_2d_pair(sb_hi, &tmBh, fb, (int32_t)r0, b0);
+          ptx::tma_load_2d_pair(sa_lo, &tmAl, fb, (int32_t)r0, a0);
+          ptx::tma_load_2d_pair(sb_lo, &tmBl, fb, (int32_t)r0, b0);
+          if (++s == (uint32_t)p.num_stages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      // ------------------------------------------------------------ MMA issuer (leader CTA, one thread)
+      const uint32_t idesc = ptx::make_idesc_bf16(2 * TC_BM, p.bn, 0, 0);
+      uint32_t s = 0, ph = 0;
+      int it = 0;
+      for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++it) {
+        const int acc = it & 1;
+        const uint32_t aph = (it >> 1) & 1;
+        ptx::mbar_wait(tempty0 + 8 * acc, aph ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        uint32_t first = 0;
+        for (int64_t r0 = 0; r0 < p.red; r0 += TC_BK) {
+          ptx::mbar_wait(full0 + 8 * s, ph);
+          ptx::tc_fence_after();
+          const uint32_t sa_hi = base + s * p.stage_bytes, sa_lo = sa_hi + TC_A_PLANE;
+          const uint32_t sb_hi = sa_lo + TC_A_PLANE, sb_lo = sb_hi + p.b_plane_bytes;
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            const uint64_t da_hi = ptx::make_smem_desc(sa_hi + k * 32u, 0u, 1024);
+            const uint64_t da_lo = ptx::make_smem_desc(sa_lo + k * 32u, 0u, 1024);
+            const uint64_t db_hi = ptx::make_smem_desc(sb_hi + k * 32u, 0u, 1024);
+            const uint64_t db_lo = ptx::make_smem_desc(sb_lo + k * 32u, 0u, 1024);
+            ptx::mma_bf16_ss_pair(d_tmem, da_hi, db_hi, idesc, first);
+            first = 1;
+            ptx::mma_bf16_ss_pair(d_tmem, da_hi, db_lo, idesc, 1);
+            ptx::mma_bf16_ss_pair(d_tmem, da_lo, db_hi, idesc, 1);
+          }
+          ptx::mma_commit_pair(empty0 + 8 * s, (uint16_t)0x3);     // frees the stage in both CTAs
+          if (++s == (uint32_t)p.num_stages) { s = 0; ph ^= 1; }
+        }
+        ptx::mma_commit_pair(tfull0 + 8 * acc, (uint16_t)0x3);      // accumulators ready in both CTAs
+      }
+    }
+  } else {
+    // -------------------------------------------------------------- epilogue warps (both CTAs, own 128 rows)
+    const int q = warp & 3;
+    const int chalf = (warp - 2) >> 2;
+    const int cw = p.bn >> 2;
+    const int cbeg = chalf * cw, cend = cbeg + cw;
+    uint32_t code_next[4] = {0u, 0u, 0u, 0u};
+    if (EPI == EPI_PLANES_BWD && first_tile < total_tiles) {
+      const int64_t nrow = (int64_t)((first_tile / p.num_b) * 2 + (int)crank) * TC_BM + q * 32 + lane;
+      const int ncol0 = (first_tile % p.num_b) * p.bn;
+      const uint32_t* cp = p.code + nrow * p.code_pitch + ((ncol0 + cbeg) >> 4);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        code_next[i] = (nrow < p.rows_a && cbeg + 16 * i < cend && ncol0 + cbeg + 16 * i < p.cols_b)
+                           ? __ldg(cp + i) : 0u;
+    }
+    int it = 0;
+    for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++it) {
+      const int ta = (tile / p.num_b) * 2 + (int)crank, tb = tile % p.num_b;
+      const int acc = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      const int64_t row = (int64_t)ta * TC_BM + q * 32 + lane;
+      const int col0 = tb * p.bn;
+      const bool row_ok = row < p.rows_a;
+      uint32_t codes[4];
+      if (EPI == EPI_PLANES_BWD) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) codes[i] = code_next[i];
+        const int ntile = tile + tile_step;
+        if (ntile < total_tiles) {
+          const int64_t nrow = (int64_t)((ntile / p.num_b) * 2 + (int)crank) * TC_BM + q * 32 + lane;
+          const int ncol0 = (ntile % p.num_b) * p.bn;
+          const uint32_t* cp = p.code + nrow * p.code_pitch + ((ncol0 + cbeg) >> 4);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            code_next[i] = (nrow < p.rows_a && cbeg + 16 * i < cend && ncol0 + cbeg + 16 * i < p.cols_b)
+                               ? __ldg(cp + i) : 0u;
+        }
+      }
+      ptx::mbar_wait(tfull0 + 8 * acc, aph);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256;
+      uint32_t code_out[4];
+#pragma unroll
+      for (int ci = 0; ci < 2; ++ci) {
+        const int c = cbeg + 32 * ci;
+        code_out[2 * ci] = code_out[2 * ci + 1] = 0u;
+        if (c < cend) {
+          uint32_t r0[16], r1[16];
+          const bool two = c + 32 <= cend;
+          ptx::tmem_ld16(taddr + c, r0);
+          if (two) ptx::tmem_ld16(taddr + c + 16, r1);
+          ptx::tmem_ld_wait();
+          if (row_ok) {
+            if (col0 + c < p.cols_b)
+              code_out[2 * ci] = epilogue_chunk16<EPI>(p, r0, row, col0 + c, 0, bias_s, codes[2 * ci]);
+            if (two && col0 + c + 16 < p.cols_b)
+              code_out[2 * ci + 1] = epilogue_chunk16<EPI>(p, r1, row, col0 + c + 16, 0, bias_s, codes[2 * ci + 1]);
+          }
+        }
+      }
+      if (EPI == EPI_PLANES_FWD && p.code != nullptr && row_ok) {
+        uint32_t* cp = p.code + row * p.code_pitch + ((col0 + cbeg) >> 4);
+        if (cw == 64 && (p.code_pitch & 3) == 0) {
+          *reinterpret_cast<uint4*>(cp) = make_uint4(code_out[0], code_out[1], code_out[2], code_out[3]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (cbeg + 16 * i < cend && col0 + cbeg + 16 * i < p.cols_b) cp[i] = code_out[i];
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        // the leader's MMA issuer owns the accumulator hand-back of BOTH CTAs
+        if (leader) ptx::mbar_arrive(tempty0 + 8 * acc);
+        else ptx::mbar_arrive_cluster(ptx::mapa(tempty0 + 8 * acc, 0));
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc_pair(tmem_base, p.tmem_cols);
+  }
+}
+
 // ---------------------------------------------------------------------------- operand planes
 // fp32 [rows][cols] (row stride rs) -> bf16 hi/lo planes [rows][pitch]; transpose: out[c][r] = in[r][c].
 __global__ void split_planes_kernel(const float* __restrict__ src, int64_t rs, int64_t rows, int cols,
@@ -701,14 +907,47 @@ static int launch_kernel(const CUtensorMap& mAh, const CUtensorMap& mAl, const C
   return GANTTS_OK;
 }
 
+template <int EPI>
+static int launch_pair_kernel(const CUtensorMap& mAh, const CUtensorMap& mAl, const CUtensorMap& mBh,
+                              const CUtensorMap& mBl, const GemmParams& p, cudaStream_t st) {
+  const size_t smem = (size_t)p.num_stages * p.stage_bytes + 1024 + 256 + TC_BIAS_SMEM;
+  static bool attr = false;
+  if (!attr) {
+    GANTTS_CUDA(cudaFuncSetAttribute(gemm_pair_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr = true;
+  }
+  const int units = ((p.num_a + 1) / 2) * p.num_b;
+  const int grid = units * 2 < num_sms() ? units * 2 : num_sms() / 2 * 2;
+  prof_begin(PROF_GEMM_KK, 2.0 * (double)p.rows_a * p.cols_b * (double)p.red, st);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_pair_kernel<EPI>, mAh, mAl, mBh, mBl, p);
+  prof_end(st);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(gemm pair)");
+  GANTTS_LAUNCH_CHECK("gemm_pair_kernel");
+  return GANTTS_OK;
+}
+
 static int use_cluster() {
   static int v = -1;
   if (v < 0) {
-    // Measured on B200 (profiles/r01_gemm_experiments.md): multicasting the B tile across a 2-CTA cluster
-    // does not help -- the limiter is the per-SM L2->SM ingest rate (~38 B/clk), which multicast does not
-    // reduce -- so the default stays 1; GANTTS_B200_CLUSTER=2 keeps the (tested) path selectable.
+    // 0 (default) = auto: CTA-pair MMA (cta_group::2, mode 3) for wide outputs (>= 2 column tiles), single
+    // CTA otherwise -- measured on B200 (profiles/r01_gemm_experiments.md): pairs are ~7 % faster on the
+    // 512-wide generator layers and ~5 % slower on the 256-wide discriminator layers.  1 = always single
+    // CTA, 2 = 2-CTA cluster with B-tile multicast (no gain: multicast does not reduce the per-SM ingest),
+    // 3 = always CTA pairs.
     const char* e = getenv("GANTTS_B200_CLUSTER");
-    v = e ? atoi(e) : 1;
+    v = e ? atoi(e) : 0;
   }
   return v;
 }
@@ -739,6 +978,27 @@ static int launch_gemm_kk(const Planes& A, const Planes& B, const EpiArgs& e, cu
   // bias staged in smem after the barrier block when it fits (padded to whole column tiles)
   p.bias_off = (e.bias && (size_t)p.num_b * p.bn * sizeof(float) <= TC_BIAS_SMEM)
                    ? (uint32_t)p.num_stages * p.stage_bytes + 256u : 0u;
+  // GANTTS_B200_CLUSTER=3: CTA-pair MMA (cta_group::2), each CTA holds half of the B tile
+  if ((use_cluster() == 3 || (use_cluster() == 0 && p.num_b >= 2)) && p.num_a >= 2) {
+    p.b_plane_bytes = ((uint32_t)(p.bn / 2) * 128 + 1023) / 1024 * 1024;
+    p.stage_bytes = 2 * TC_A_PLANE + 2 * p.b_plane_bytes;
+    p.tx_bytes = 2 * TC_A_PLANE + 2 * (uint32_t)(p.bn / 2) * 128;
+    p.num_stages = (int)((216 * 1024) / p.stage_bytes);
+    if (p.num_stages > TC_MAX_STAGES) p.num_stages = TC_MAX_STAGES;
+    p.bias_off = (e.bias && (size_t)p.num_b * p.bn * sizeof(float) <= TC_BIAS_SMEM)
+                     ? (uint32_t)p.num_stages * p.stage_bytes + 256u : 0u;
+    CUtensorMap mAh, mAl, mBh, mBl;
+    int rc;
+    if ((rc = make_map(&mAh, A.hi, A.rows, A.cols, A.pitch, TC_BM))) return rc;
+    if ((rc = make_map(&mAl, A.lo, A.rows, A.cols, A.pitch, TC_BM))) return rc;
+    if ((rc = make_map(&mBh, B.hi, B.rows, B.cols, B.pitch, p.bn / 2))) return rc;
+    if ((rc = make_map(&mBl, B.lo, B.rows, B.cols, B.pitch, p.bn / 2))) return rc;
+    switch (e.epi) {
+      case EPI_F32: return launch_pair_kernel<EPI_F32>(mAh, mAl, mBh, mBl, p, st);
+      case EPI_PLANES_FWD: return launch_pair_kernel<EPI_PLANES_FWD>(mAh, mAl, mBh, mBl, p, st);
+      case EPI_PLANES_BWD: return launch_pair_kernel<EPI_PLANES_BWD>(mAh, mAl, mBh, mBl, p, st);
+    }
+  }
   // 2-CTA clusters (B tile multicast) when there are at least two row tiles
   const bool cl2 = use_cluster() == 2 && p.num_a >= 2;
   CUtensorMap mAh, mAl, mBh, mBl;
