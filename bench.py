@@ -54,30 +54,71 @@ def make_batches(w, seed, n, pinned):
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region (NVML polling thread; falls back to an
+    `nvidia-smi -lms 100` subprocess when the NVML bindings are unavailable)."""
 
     QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.nvml = index, [], None, None
+        self.sm, self.mask, self.max_mhz, self._stop = [], 0, None, False
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            # CUDA_VISIBLE_DEVICES-relative index -> NVML handle through the PCI bus id
+            bus = torch.cuda.get_device_properties(self.index).pci_bus_id if hasattr(
+                torch.cuda.get_device_properties(self.index), "pci_bus_id") else None
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.index) if bus is None else None
+            if self.handle is None:
+                for i in range(pynvml.nvmlDeviceGetCount()):
+                    h = pynvml.nvmlDeviceGetHandleByIndex(i)
+                    if pynvml.nvmlDeviceGetPciInfo(h).bus == bus:
+                        self.handle = h
+                        break
+                if self.handle is None:
+                    self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        while not self._stop:
+            try:
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+                self.mask |= int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+            except Exception:
+                pass
+            time.sleep(0.005)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self._stop = True
+            self.thread.join(timeout=1.0)
+            reasons = sorted(v for k, v in self.REASONS.items() if self.mask & k)
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                    "reasons": reasons, "samples": len(self.sm), "how": "NVML poll every 5 ms"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -100,7 +141,7 @@ class ClockSampler(object):
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "how": "nvidia-smi -lms 100"}
 
 
 # ------------------------------------------------------------------------------ CPU baseline

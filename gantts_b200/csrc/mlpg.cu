@@ -80,13 +80,31 @@ mlpg_fwd_kernel(const float* __restrict__ in, int64_t in_bs, int64_t in_ts,
     int r = i / GROW, j = i - r * GROW, t = t0 + r;
     gs[i] = (t < T && j < NTAPS) ? table[(int64_t)t * NTAPS + j] : 0.f;
   }
-  // Phase 1: b = W^T mu over [t0-K, t0+TT+K) (or the raw input for static streams).  Each thread
-  // owns ONE column (stream lookup hoisted) and strides over rows; the tap loops are fully unrolled
-  // and predicated so the (coalesced, 128 B per warp) loads of a row are independent.
+  // Phase 1: b = W^T mu over [t0-K, t0+TT+K) (or the raw input for static streams).  Each thread owns ONE
+  // column (stream lookup hoisted) and strides over rows; the non-zero window taps are compacted once per
+  // block into a small shared table (7 taps for the hparams windows), so a row costs 7 coalesced loads.
+  __shared__ int tap_dt[GANTTS_MAX_WINDOWS * GANTTS_MAX_WINDOW_TAPS];
+  __shared__ int tap_w[GANTTS_MAX_WINDOWS * GANTTS_MAX_WINDOW_TAPS];
+  __shared__ float tap_c[GANTTS_MAX_WINDOWS * GANTTS_MAX_WINDOW_TAPS];
+  __shared__ int tap_n;
+  if (threadIdx.x == 0) {
+    int n = 0;
+    for (int w = 0; w < win.n; ++w)
+      for (int kk = 0; kk <= win.l[w] + win.u[w]; ++kk)
+        if (win.coef[w][kk] != 0.f) {
+          tap_dt[n] = -(kk - win.l[w]);
+          tap_w[n] = w;
+          tap_c[n] = win.coef[w][kk];
+          ++n;
+        }
+    tap_n = n;
+  }
+  __syncthreads();
   {
     const int cx = threadIdx.x & (TC - 1), rg = threadIdx.x / TC;
     const ColInfo ci = find_col(st, c0 + cx);
     const float* colp = inb + (ci.in_col >= 0 ? ci.in_col : 0);
+    const int ntap = tap_n;
 #pragma unroll 2
     for (int r = rg; r < TT + 2 * K_HALF; r += MLPG_THREADS / TC) {
       const int t = t0 - K_HALF + r;
@@ -95,18 +113,9 @@ mlpg_fwd_kernel(const float* __restrict__ in, int64_t in_bs, int64_t in_ts,
         if (!ci.dyn) {
           v = colp[(int64_t)t * in_ts];
         } else {
-#pragma unroll
-          for (int w = 0; w < GANTTS_MAX_WINDOWS; ++w) {
-            if (w < win.n) {
-              const int l = win.l[w], ntap = win.l[w] + win.u[w] + 1;
-#pragma unroll
-              for (int kk = 0; kk < GANTTS_MAX_WINDOW_TAPS; ++kk) {
-                const int tt = t - (kk - l);
-                const float cf = win.coef[w][kk];
-                if (kk < ntap && cf != 0.f && tt >= 0 && tt < T)
-                  v = fmaf(cf, colp[(int64_t)tt * in_ts + w * ci.sd], v);
-              }
-            }
+          for (int i = 0; i < ntap; ++i) {
+            const int tt = t + tap_dt[i];
+            if (tt >= 0 && tt < T) v = fmaf(tap_c[i], colp[(int64_t)tt * in_ts + tap_w[i] * ci.sd], v);
           }
         }
       }

@@ -727,3 +727,84 @@ def test_srurnn_model(dev):
     y = m(x, [30, 28, 11, 5])            # lengths ignored, like the reference
     y.sum().backward()
     assert y.shape == (4, 30, 7) and x.grad is not None and m.gru.rnn_lst[2].weight.grad is not None
+
+
+# ------------------------------------------------------------------------ drop-in mode
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("tag,cond", [("u_", False), ("c_", True)])
+def test_dropin_trainpy_semantics_golden(dev, golden_step, engine, tag, cond):
+    """DROP-IN mode: the reference's own per-batch logic (tests/trainpy_mirror.py = train.py:528-580 with its
+    inline torch BCE, clip_grad_norm_ and torch.optim.Adagrad) running on the `gantts` alias package
+    (B200 modules, MLPG, losses, nnmnkwii shim) reproduces the golden vectors of the unmodified reference."""
+    import sys, os
+    from conftest import ROOT
+    sys.path.insert(1, os.path.join(ROOT, "compat"))
+    import gantts
+    from gantts_b200 import step as gstep
+    from nnmnkwii.paramgen import unit_variance_mlpg_matrix      # compat shim (memoised)
+    import trainpy_mirror
+    g = golden_step
+    mg = _golden_mlp(g, tag + "g0_", 20, 187, 32, False, dev, engine)
+    md = _golden_mlp(g, tag + "d0_", 58 + (20 if cond else 0), 1, 16, True, dev, engine)
+    assert type(mg) is gantts.models.MLP
+    hp = gstep.HParams(gstep.TTS_ACOUSTIC, discriminator_linguistic_condition=cond)
+    og = torch.optim.Adagrad(mg.parameters(), lr=0.01, weight_decay=1e-7)
+    od = torch.optim.Adagrad(md.parameters(), lr=0.01, weight_decay=1e-7)
+    R = torch.from_numpy(unit_variance_mlpg_matrix(hp.windows, 30)).to(dev)          # train.py:510-513
+    tol = TOL[engine]
+    for it in range(2):
+        p = "%sit%d_" % (tag, it)
+        lens = [int(v) for v in g[p + "lengths"]]
+        losses, counts, y_hat, y_hat_static = trainpy_mirror.train_step(
+            mg, md, og, od, T(g[p + "x"], dev), T(g[p + "y"], dev), torch.LongTensor(lens).to(dev), R, hp)
+        assert np.allclose(losses, g[p + "losses"], rtol=tol, atol=0), (losses, g[p + "losses"])
+        assert counts == list(g[p + "counts"])
+        assert rel_err(npy(y_hat), g[p + "y_hat"]) < tol
+        assert rel_err(npy(y_hat_static), g[p + "y_hat_static"]) < tol
+        if engine == "simt":
+            for m, pre in ((mg, "g_"), (md, "d_")):
+                for k, v in m.state_dict().items():
+                    assert rel_err(npy(v), g[p + pre + k]) < 5 * tol, (pre, k)
+
+
+def test_compat_R_matrix_matches_oracle_dense(dev):
+    """compat nnmnkwii.paramgen.unit_variance_mlpg_matrix (assembled from the library's P^-1 rows) equals the
+    dense (W^T W)^-1 W^T of the oracle to fp32 rounding, and is accepted by the CUDA MLPG's R validation."""
+    import sys, os
+    from conftest import ROOT
+    sys.path.insert(1, os.path.join(ROOT, "compat"))
+    from nnmnkwii.paramgen import unit_variance_mlpg_matrix
+    from nnmnkwii.autograd import unit_variance_mlpg
+    for Tn in (5, 64, 200):
+        a, b = unit_variance_mlpg_matrix(WINDOWS, Tn), nnp.unit_variance_mlpg_matrix(WINDOWS, Tn)
+        assert np.abs(a - b).max() < 2e-7
+    x = torch.randn(2, 200, 177, device=dev)
+    R = torch.from_numpy(unit_variance_mlpg_matrix(WINDOWS, 200)).to(dev)
+    ref = nnp.unit_variance_mlpg(torch.from_numpy(nnp.unit_variance_mlpg_matrix(WINDOWS, 200)), x.cpu())
+    assert rel_err(npy(unit_variance_mlpg(R, x)), npy(ref)) < 5e-6
+
+
+# --------------------------------------------------------------------------- edge cases
+def test_edge_shapes(dev):
+    """Smallest and most ragged inputs: B=1, T=1, length-1 utterances, single-row GEMMs."""
+    import gantts_b200
+    from gantts_b200 import step as gstep, fused
+    m = gantts_b200.models.MLP(5, 3, 2, 8, dropout=0.0, last_sigmoid=False).to(dev)
+    y = m(torch.randn(1, 1, 5, device=dev))
+    assert y.shape == (1, 1, 3) and bool(torch.isfinite(y).all())
+    crit = gantts_b200.seqloss.MaskedMSELoss()
+    a = torch.randn(3, 4, 2, device=dev, requires_grad=True)
+    l = crit(a, torch.zeros(3, 4, 2, device=dev), lengths=torch.LongTensor([4, 1, 1]).to(dev))
+    l.backward()
+    assert float(a.grad[1, 1:].abs().max()) == 0.0 and float(a.grad[1, 0].abs().max()) > 0
+    torch.manual_seed(1)
+    mg = gantts_b200.models.MLP(9, 187, 1, 16, dropout=0.0, last_sigmoid=False).to(dev)
+    md = gantts_b200.models.MLP(58, 1, 1, 8, dropout=0.0, last_sigmoid=True).to(dev)
+    fs = fused.FusedGanStep(mg, md, gstep.TTS_ACOUSTIC, 1, 3)
+    fs.step(torch.rand(1, 3, 9, device=dev), torch.randn(1, 3, 187, device=dev),
+            torch.LongTensor([2]).to(dev), frames=2)
+    v = fs.loss_dict()
+    assert v["frames"] == 2.0 and all(np.isfinite(list(v.values())))
+    lstm = gantts_b200.models.LSTMRNN(4, 2, 1, 8, bidirectional=True).to(dev)
+    out = lstm(torch.randn(2, 3, 4, device=dev), [3, 1])
+    assert out.shape == (2, 3, 2) and float(out[1, 1:].abs().sum()) == float((lstm.hidden2out.bias.abs().sum() * 2))
