@@ -298,7 +298,6 @@ def run_b200_arm(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    lib.gantts_profile_enable(1)
     launches0 = lib.gantts_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -308,14 +307,20 @@ def run_b200_arm(args):
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     launches = lib.gantts_launch_count() - launches0
-    lib.gantts_profile_enable(0)
     clocks = sampler.stop() if rank == 0 else None
-    import ctypes
-    pms, pwork, pn = (ctypes.c_double * 8)(), (ctypes.c_double * 8)(), (ctypes.c_longlong * 8)()
-    _lib.check(lib.gantts_profile_collect(pms, pwork, pn))
     ms_per_step = ms_total / args.steps
     value = frames_per_step / (ms_per_step * 1e-3)
     loss_g = float(out["loss_g"])
+    # ---------------- roofline pass: the same K steps again with CUDA events around every GEMM / MLPG launch
+    # (kept out of the region `value` is timed on: the event records sit between consecutive kernels)
+    import ctypes
+    lib.gantts_profile_enable(1)
+    for i in range(args.steps):
+        trainer.step(*resident[i % NUM_BATCHES], lengths, R)
+    torch.cuda.synchronize()
+    lib.gantts_profile_enable(0)
+    pms, pwork, pn = (ctypes.c_double * 8)(), (ctypes.c_double * 8)(), (ctypes.c_longlong * 8)()
+    _lib.check(lib.gantts_profile_collect(pms, pwork, pn))
 
     # ---------------- e2e: host buffers in, losses out, copies inside the timed region
     copy_stream = torch.cuda.Stream(device=dev)
@@ -383,8 +388,9 @@ def run_b200_arm(args):
     roofline = {"kernel": kinds[dom], "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": ach / peak_tf, "traffic": traffic, "peak_source": peak_src,
                 "note": "achieved = algorithmic fp32-equivalent FLOPs (2MNK per GEMM) / CUDA-event time of the "
-                        "launches; the bf16x3 split executes 3 tensor-core MMAs per algorithmic product, so "
-                        "executed bf16 pipe rate = 3 x achieved",
+                        "launches (second pass of the same K steps with an event pair around every launch); the "
+                        "bf16x3 split executes 3 tensor-core MMAs per algorithmic product, so executed bf16 pipe "
+                        "rate = 3 x achieved",
                 "tensor_pipe_frac_executed": 3.0 * ach / peak_tf,
                 "share_of_step": (pms[dom] / args.steps) / ms_per_step,
                 "kernels": per_kind}

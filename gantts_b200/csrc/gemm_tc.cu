@@ -258,6 +258,10 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
     ptx::tmem_alloc(tmem_slot, p.tmem_cols);
     ptx::tmem_relinquish();
   }
+  // PDL: let the next GEMM of the stream set itself up while this one drains; nothing produced by the
+  // previous kernel is read before the dependency wait.
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   const float* bias_s = nullptr;
   if (p.bias_off) {
     float* bs = reinterpret_cast<float*>(smem_raw + (base + p.bias_off - raw));
@@ -525,6 +529,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant
     ptx::tmem_alloc_pair(tmem_slot, p.tmem_cols);
     ptx::tmem_relinquish_pair();
   }
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   const float* bias_s = nullptr;
   if (p.bias_off) {
     float* bs = reinterpret_cast<float*>(smem_raw + (base + p.bias_off - raw));
@@ -868,6 +874,15 @@ static void fill_epilogue(GemmParams& p, const EpiArgs& e) {
   p.dbg = (uint32_t)dbg;
 }
 
+static int use_pdl() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GANTTS_B200_PDL");
+    v = e ? atoi(e) : 1;
+  }
+  return v;
+}
+
 template <bool MN, int EPI, int CL>
 static int launch_kernel(const CUtensorMap& mAh, const CUtensorMap& mAl, const CUtensorMap& mBh,
                          const CUtensorMap& mBl, const GemmParams& p, cudaStream_t st) {
@@ -881,25 +896,32 @@ static int launch_kernel(const CUtensorMap& mAh, const CUtensorMap& mAl, const C
   const int units = ((p.num_a + CL - 1) / CL) * p.num_b * p.num_z;     // tiles (CL=1) or pair tiles (CL=2)
   int grid = units * CL < num_sms() ? units * CL : num_sms() / CL * CL;
   prof_begin(MN ? PROF_GEMM_MN : PROF_GEMM_KK, 2.0 * (double)p.rows_a * p.cols_b * (double)p.red, st);
-  if (CL == 1) {
-    gemm_bf16x3_kernel<MN, EPI, CL><<<grid, TC_THREADS, smem, st>>>(mAh, mAl, mBh, mBl, p);
-  } else {
+  {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3(TC_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = CL;
-    at[0].val.clusterDim.y = 1;
-    at[0].val.clusterDim.z = 1;
+    cudaLaunchAttribute at[2];
+    int na = 0;
+    if (use_pdl()) {
+      at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[na].val.programmaticStreamSerializationAllowed = 1;
+      ++na;
+    }
+    if (CL > 1) {
+      at[na].id = cudaLaunchAttributeClusterDimension;
+      at[na].val.clusterDim.x = CL;
+      at[na].val.clusterDim.y = 1;
+      at[na].val.clusterDim.z = 1;
+      ++na;
+    }
     cfg.attrs = at;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = na;
     cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16x3_kernel<MN, EPI, CL>, mAh, mAl, mBh, mBl, p);
     if (e != cudaSuccess) {
       prof_end(st);
-      return cuda_fail(e, "cudaLaunchKernelEx(gemm cluster)");
+      return cuda_fail(e, "cudaLaunchKernelEx(gemm)");
     }
   }
   prof_end(st);
@@ -924,13 +946,20 @@ static int launch_pair_kernel(const CUtensorMap& mAh, const CUtensorMap& mAl, co
   cfg.blockDim = dim3(TC_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = 2;
-  at[0].val.clusterDim.y = 1;
-  at[0].val.clusterDim.z = 1;
+  cudaLaunchAttribute at[2];
+  int na = 0;
+  at[na].id = cudaLaunchAttributeClusterDimension;
+  at[na].val.clusterDim.x = 2;
+  at[na].val.clusterDim.y = 1;
+  at[na].val.clusterDim.z = 1;
+  ++na;
+  if (use_pdl()) {
+    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = at;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = na;
   cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_pair_kernel<EPI>, mAh, mAl, mBh, mBl, p);
   prof_end(st);
   if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(gemm pair)");

@@ -33,23 +33,20 @@ struct LstmParams {
   int B, T, H, ndir, slices;
 };
 
-// Barrier among the `n` CTAs of one direction (all co-resident: cooperative launch).
+// Barrier among the `n` CTAs of one direction (all co-resident: cooperative launch).  One monotonically
+// increasing arrival counter per direction: the k-th barrier completes when it reaches k * n -- no reset,
+// no generation word, one atomic + one polling load per CTA and step.
 __device__ __forceinline__ void dir_barrier(unsigned int* bar, unsigned int n, unsigned int& gen) {
   __syncthreads();
   if (threadIdx.x == 0) {
+    const unsigned int target = (gen + 1) * n;
     __threadfence();
-    const unsigned int target = gen + 1;
-    if (atomicAdd(bar, 1u) == n - 1) {
-      atomicExch(bar, 0u);
-      __threadfence();
-      atomicExch(bar + 1, target);
-    } else {
-      const long long t0 = clock64();
-      while (*reinterpret_cast<volatile unsigned int*>(bar + 1) != target) {
-        if (clock64() - t0 > 8000000000LL) {
-          printf("gantts_b200: lstm grid barrier timeout (block %d)\n", blockIdx.x);
-          __trap();
-        }
+    atomicAdd(bar, 1u);
+    const long long t0 = clock64();
+    while (*reinterpret_cast<volatile unsigned int*>(bar) < target) {
+      if (clock64() - t0 > 8000000000LL) {
+        printf("gantts_b200: lstm grid barrier timeout (block %d)\n", blockIdx.x);
+        __trap();
       }
     }
     __threadfence();
@@ -101,6 +98,16 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_fwd_kernel(const LstmPar
         reinterpret_cast<float4*>(hs)[bb * (H / 4) + k4] = v;
       }
       __syncthreads();
+      // input projections of this step (independent of the recurrence): issue the loads now so that
+      // their latency hides under the mat-vec
+      float xq[4] = {0.f, 0.f, 0.f, 0.f};
+      if (tid < LSTM_BC * HS) {
+        const int bb = tid / HS, u = tid - bb * HS, b = cb + bb;
+        if (b < p.B && u0 + u < H && (int64_t)t < p.lengths[b]) {
+          const float* xp = p.xproj + ((int64_t)b * p.T + t) * ldx + dir * 4 * H + u0 + u;
+          xq[0] = xp[0]; xq[1] = xp[H]; xq[2] = xp[2 * H]; xq[3] = xp[3 * H];
+        }
+      }
       float acc[BPT];
 #pragma unroll
       for (int j = 0; j < BPT; ++j) acc[j] = 0.f;
@@ -123,11 +130,10 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_fwd_kernel(const LstmPar
           const int64_t row = (int64_t)b * p.T + t;
           float hval = 0.f;
           if (valid) {
-            const float* xp = p.xproj + row * ldx + dir * 4 * H + u0 + u;
-            const float gi = sigmoidf_(pre[bb * R + 0 * HS + u] + xp[0]);
-            const float gf = sigmoidf_(pre[bb * R + 1 * HS + u] + xp[H]);
-            const float gg = tanhf(pre[bb * R + 2 * HS + u] + xp[2 * H]);
-            const float go = sigmoidf_(pre[bb * R + 3 * HS + u] + xp[3 * H]);
+            const float gi = sigmoidf_(pre[bb * R + 0 * HS + u] + xq[0]);
+            const float gf = sigmoidf_(pre[bb * R + 1 * HS + u] + xq[1]);
+            const float gg = tanhf(pre[bb * R + 2 * HS + u] + xq[2]);
+            const float go = sigmoidf_(pre[bb * R + 3 * HS + u] + xq[3]);
             const float c = gf * cst[b * HS + u] + gi * gg;
             cst[b * HS + u] = c;
             hval = go * tanhf(c);

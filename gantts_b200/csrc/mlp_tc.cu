@@ -48,6 +48,16 @@ __global__ void grad_out_to_planes_kernel(const float* __restrict__ gy, int64_t 
     }
 }
 
+// out[i] (+)= sum_z partial[z * stride + off + i], i < n
+__global__ void splitk_reduce_strided_kernel(const float* __restrict__ partial, int nsplit, int stride, int off, int n,
+                                             float* __restrict__ out, int accumulate) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int z = 0; z < nsplit; ++z) s += partial[(int64_t)z * stride + off + i];
+  out[i] = accumulate ? out[i] + s : s;
+}
+
 // Column sums of a planes matrix (hi + lo): partial[chunk][col].
 __global__ void __launch_bounds__(256)
 colsum_planes_partial_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
@@ -103,6 +113,104 @@ __global__ void split_weights_kernel(WeightSplitList wl) {
     wl.tlo[l][(int64_t)c * wl.tpitch[l] + r] = lo;
   }
 }
+
+// ---------------------------------------------------------------------------- single-output last layer
+// The discriminator ends in Linear(256 -> 1) + sigmoid (reference gantts/models.py:140-141 with out_dim=1):
+// a GEMV, not a GEMM.  Forward: one warp per row reads the row's hi/lo planes once (HBM-bound) and
+// produces y.  Backward: gz = gy * act'(y) per row; gW = sum_m gz[m] H[m][:], gb = sum gz (two-stage
+// deterministic reduction) and the NEXT gradient planes gZ_prev = (gz w^T) * act'(H) directly.
+constexpr int GEMV_THREADS = 256;
+constexpr int GEMV_MAX_K = 1024;
+
+__global__ void __launch_bounds__(GEMV_THREADS)
+gemv_fwd_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, int64_t pitch,
+                const float* __restrict__ w, const float* __restrict__ b, float* __restrict__ y, int64_t y_rs,
+                int64_t M, int K, int sigmoid) {
+  __shared__ float ws[GEMV_MAX_K];
+  for (int i = threadIdx.x; i < K; i += GEMV_THREADS) ws[i] = w[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * GEMV_THREADS + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * GEMV_THREADS) >> 5;
+  const float bias = b[0];
+  for (int64_t r = warp; r < M; r += nwarps) {
+    const uint32_t* hr = reinterpret_cast<const uint32_t*>(hi + r * pitch);
+    const uint32_t* lr = reinterpret_cast<const uint32_t*>(lo + r * pitch);
+    float acc = 0.f;
+    for (int c = 2 * lane; c < K; c += 64) {
+      const uint32_t h2 = hr[c >> 1], l2 = lr[c >> 1];
+      const float a0 = __uint_as_float(h2 << 16) + __uint_as_float(l2 << 16);
+      const float a1 = __uint_as_float(h2 & 0xffff0000u) + __uint_as_float(l2 & 0xffff0000u);
+      acc = fmaf(a0, ws[c], acc);
+      if (c + 1 < K) acc = fmaf(a1, ws[c + 1], acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      float z = acc + bias;
+      y[r * y_rs] = sigmoid ? 1.f / (1.f + expf(-z)) : z;
+    }
+  }
+}
+
+// partial[block][0..K) = sum over the block's rows of gz[m] * H[m][:], partial[block][K] = sum gz.
+__global__ void __launch_bounds__(GEMV_THREADS)
+gemv_bwd_kernel(const float* __restrict__ gy, int64_t gy_rs, const float* __restrict__ y, int64_t y_rs,
+                const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, int64_t pitch,
+                const uint32_t* __restrict__ code, int64_t code_pitch, const float* __restrict__ w,
+                __nv_bfloat16* __restrict__ ghi, __nv_bfloat16* __restrict__ glo, int64_t gpitch,
+                float* __restrict__ partial, int64_t M, int K, int sigmoid, float dpos, float dneg, float dzero,
+                int want_gw) {
+  __shared__ float ws[GEMV_MAX_K];
+  __shared__ float gws[GEMV_THREADS / 32][GEMV_MAX_K + 1];
+  for (int i = threadIdx.x; i < K; i += GEMV_THREADS) ws[i] = w[i];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int i = lane; i <= K; i += 32) gws[wid][i] = 0.f;
+  __syncthreads();
+  const int64_t warp = ((int64_t)blockIdx.x * GEMV_THREADS + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * GEMV_THREADS) >> 5;
+  float gsum = 0.f;
+  for (int64_t r = warp; r < M; r += nwarps) {
+    float g = gy[r * gy_rs];
+    if (sigmoid) {
+      const float yy = y[r * y_rs];
+      g *= yy * (1.f - yy);
+    }
+    gsum += g;
+    const uint32_t* hr = reinterpret_cast<const uint32_t*>(hi + r * pitch);
+    const uint32_t* lr = reinterpret_cast<const uint32_t*>(lo + r * pitch);
+    uint32_t* gh = reinterpret_cast<uint32_t*>(ghi + r * gpitch);
+    uint32_t* gl = reinterpret_cast<uint32_t*>(glo + r * gpitch);
+    for (int c = 2 * lane; c < K; c += 64) {
+      if (want_gw) {
+        const uint32_t h2 = hr[c >> 1], l2 = lr[c >> 1];
+        const float a0 = __uint_as_float(h2 << 16) + __uint_as_float(l2 << 16);
+        const float a1 = __uint_as_float(h2 & 0xffff0000u) + __uint_as_float(l2 & 0xffff0000u);
+        gws[wid][c] = fmaf(g, a0, gws[wid][c]);
+        if (c + 1 < K) gws[wid][c + 1] = fmaf(g, a1, gws[wid][c + 1]);
+      }
+      // gZ_prev = (g * w) * act'(H), derivative class from the 2-bit code plane
+      const uint32_t cw = code[r * code_pitch + (c >> 4)];
+      const uint32_t c0 = (cw >> (2 * (c & 15))) & 3u, c1 = (cw >> (2 * ((c + 1) & 15))) & 3u;
+      const float v0 = g * ws[c] * ((c0 & 1u) ? dzero : ((c0 & 2u) ? dneg : dpos));
+      const float v1 = (c + 1 < K) ? g * ws[c + 1] * ((c1 & 1u) ? dzero : ((c1 & 2u) ? dneg : dpos)) : 0.f;
+      const uint32_t hp = pack_bf16x2(v0, v1);
+      gh[c >> 1] = hp;
+      gl[c >> 1] = pack_bf16x2(v0 - __uint_as_float(hp << 16), v1 - __uint_as_float(hp & 0xffff0000u));
+    }
+  }
+  if (want_gw) {
+    if (lane == 0) gws[wid][K] = gsum;
+    __syncthreads();
+    for (int i = threadIdx.x; i <= K; i += GEMV_THREADS) {
+      float s = 0.f;
+#pragma unroll
+      for (int q = 0; q < GEMV_THREADS / 32; ++q) s += gws[q][i];
+      partial[(int64_t)blockIdx.x * (K + 1) + i] = s;
+    }
+  }
+}
+
+constexpr int GEMV_BLOCKS = 148 * 2;
 
 constexpr int MLP_COLSUM_CHUNKS = 128;
 
@@ -179,7 +287,8 @@ extern "C" size_t gantts_mlp_workspace_bytes(const gantts_mlp_t* m, int64_t M) {
   for (int l = 0; l <= m->num_layers; ++l) maxd = m->dims[l] > maxd ? m->dims[l] : maxd;
   for (int l = 0; l < m->num_layers; ++l)       // one partial region per layer: reductions are deferred
     part += mn_partial_bytes(M, m->dims[l + 1], m->dims[l], nullptr, nullptr) + 256;
-  return 4 * plane_bytes(M, maxd) + part + (size_t)MLP_COLSUM_CHUNKS * maxd * sizeof(float) + 2048;
+  return 4 * plane_bytes(M, maxd) + part + (size_t)MLP_COLSUM_CHUNKS * maxd * sizeof(float) +
+         (size_t)GEMV_BLOCKS * (GEMV_MAX_K + 1) * sizeof(float) + 4096;
 }
 
 extern "C" int gantts_mlp_fwd(const gantts_mlp_t* m, const float* x, int64_t x_rs, int64_t M, float* y,
@@ -234,6 +343,13 @@ extern "C" int gantts_mlp_fwd(const gantts_mlp_t* m, const float* x, int64_t x_r
       e.p = m->dropout_p;
       e.seed = layer_seed(m->seed, l);
     } else {
+      if (m->dims[L] == 1 && L >= 2 && m->dims[l] <= GEMV_MAX_K && (m->dims[l] & 1) == 0) {
+        // single-output last layer: GEMV + sigmoid, one warp per row
+        gemv_fwd_kernel<<<GEMV_BLOCKS, GEMV_THREADS, 0, st>>>(t.H[l].hi, t.H[l].lo, t.H[l].pitch, m->W[l], m->b[l], y,
+                                                              y_rs, M, m->dims[l], m->last_act == GANTTS_ACT_SIGMOID);
+        GANTTS_LAUNCH_CHECK("gemv_fwd_kernel");
+        continue;
+      }
       e.epi = EPI_F32;
       e.C = y;
       e.ldc = y_rs;
@@ -278,9 +394,40 @@ extern "C" int gantts_mlp_bwd(const gantts_mlp_t* m, const float* gy, int64_t gy
   char* partial_cur = cur;
   ReduceList rl;
 
+  float* gemv_part = reinterpret_cast<float*>(partial_cur);
+  partial_cur += ((size_t)GEMV_BLOCKS * (GEMV_MAX_K + 1) * sizeof(float) + 255) / 256 * 256;
   int pp = 0;
+  int l_start = L - 1;
   char* c0 = gbuf[pp];
   Planes G = carve_planes(c0, M, m->dims[L]);
+  if (m->dims[L] == 1 && L >= 2 && m->dims[L - 1] <= GEMV_MAX_K && (m->dims[L - 1] & 1) == 0) {
+    // single-output last layer: gW/gb by block partials, and the previous layer's gradient planes directly
+    const int K1 = m->dims[L - 1];
+    char* cg = gbuf[pp];
+    G = carve_planes(cg, M, K1);
+    const float ks = m->dropout_p > 0.f ? 1.f / (1.f - m->dropout_p) : 1.f;
+    const int want = (gW && gW[L - 1]) || (gb && gb[L - 1]);
+    gemv_bwd_kernel<<<GEMV_BLOCKS, GEMV_THREADS, 0, st>>>(
+        gy, gy_rs, y, y_rs, t.H[L - 1].hi, t.H[L - 1].lo, t.H[L - 1].pitch, t.code[L - 1], t.code_pitch[L - 1],
+        m->W[L - 1], G.hi, G.lo, G.pitch, gemv_part, M, K1, m->last_act == GANTTS_ACT_SIGMOID ? 1 : 0, ks,
+        m->slope * ks, m->dropout_p > 0.f ? 0.f : m->slope, want);
+    GANTTS_LAUNCH_CHECK("gemv_bwd_kernel");
+    if (want) {
+      // partial rows are [K1 weights | 1 bias]: reduce them with the deferred list (strided views are not
+      // supported there), so use two plain reductions
+      if (gW && gW[L - 1]) {
+        // gather the weight part: partial is [blocks][K1+1]; reduce column-wise
+        splitk_reduce_strided_kernel<<<(K1 + 255) / 256, 256, 0, st>>>(gemv_part, GEMV_BLOCKS, K1 + 1, 0, K1, gW[L - 1],
+                                                                     accumulate);
+        GANTTS_LAUNCH_CHECK("splitk_reduce_strided_kernel(gW)");
+      }
+      if (gb && gb[L - 1]) {
+        splitk_reduce_strided_kernel<<<1, 256, 0, st>>>(gemv_part, GEMV_BLOCKS, K1 + 1, K1, 1, gb[L - 1], accumulate);
+        GANTTS_LAUNCH_CHECK("splitk_reduce_strided_kernel(gb)");
+      }
+    }
+    l_start = L - 2;
+  } else
   {
     int64_t total = M * m->dims[L];
     int nb = (int)((total + 1023) / 1024);
@@ -290,7 +437,7 @@ extern "C" int gantts_mlp_bwd(const gantts_mlp_t* m, const float* gy, int64_t gy
                                                   m->last_act == GANTTS_ACT_SIGMOID ? 1 : 0);
     GANTTS_LAUNCH_CHECK("grad_out_to_planes_kernel");
   }
-  for (int l = L - 1; l >= 0; --l) {
+  for (int l = l_start; l >= 0; --l) {
     float* gbl = (gb && gb[l]) ? gb[l] : nullptr;
     if (gW && gW[l]) {
       // gW_l and (via the ones-MMA) gb_l from one launch; the split reductions of all layers are

@@ -98,6 +98,13 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap
       : "memory");
 }
 
+// ------------------------------------------------------------------ programmatic dependent launch
+// launch_dependents: the next kernel in the stream (if it was launched with programmatic stream
+// serialisation) may start its CTAs as SMs free up; grid_dep_wait: block until every prerequisite grid has
+// completed and its writes are visible.  Both are no-ops when the kernel was launched without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ------------------------------------------------------------------ clusters
 // shared::cluster address of the same shared-memory offset in CTA `rank` of the cluster
 __device__ __forceinline__ uint32_t mapa(uint32_t smem_addr, uint32_t rank) {
