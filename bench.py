@@ -231,8 +231,8 @@ def workload_config(w, engine):
 def run_b200_arm(args):
     import __graft_entry__
     from gantts_b200 import parallel
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout (one JSON line only)
+    # stdout carries exactly ONE JSON line: NCCL's banner / debug output goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     rank, world, local = parallel.init_from_env()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the B200 arm has no CPU fallback")

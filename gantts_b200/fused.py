@@ -125,6 +125,9 @@ class FusedGanStep(object):
         if not lengths.is_cuda or lengths.dtype != torch.int64:
             raise RuntimeError("FusedGanStep: lengths must be a CUDA int64 tensor")
         self.cfg.adv_w = float(adv_w)
+        for desc, layers in ((self.cfg.g, self._g_layers), (self.cfg.d, self._d_layers)):
+            for i, l in enumerate(layers):      # parameters may have been re-allocated (load_state_dict keeps them)
+                desc.W[i], desc.b[i] = l.weight.data_ptr(), l.bias.data_ptr()
         seed = (self._seed + self._step) & ((1 << 61) - 1)
         self._step += 1
         inv = 1.0 / float(frames)
