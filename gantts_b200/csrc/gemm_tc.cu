@@ -25,9 +25,8 @@ namespace gantts {
 constexpr int TC_EPI_WARPS = 16;
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;   // warp 0 TMA, warp 1 MMA, warps 2..17 epilogue
 constexpr int TC_BM = 128;          // MMA M (TMEM lanes)
-constexpr int TC_BK = 64;           // reduction elements per stage (one 128B swizzle atom of bf16)
-constexpr int TC_MAX_STAGES = 4;
-constexpr uint32_t TC_A_PLANE = TC_BM * TC_BK * 2;   // 16 KB
+constexpr int TC_BK = 64;           // default reduction elements per stage (p.bk: 64, or 32 for deeper pipelines)
+constexpr int TC_MAX_STAGES = 8;
 constexpr uint32_t TC_BIAS_SMEM = 4096;              // staged bias vector (<= 1024 columns)
 
 // Epilogue flavours (template parameter of the kernel).
@@ -44,6 +43,10 @@ struct GemmParams {
   int bn;               // MMA N, multiple of 64, <= 256
   int num_stages;
   uint32_t stage_bytes, b_plane_bytes, tx_bytes;
+  int bk;               // reduction elements per smem stage: 64 (SWIZZLE_128B K-major rows) or 32 (SWIZZLE_64B)
+  uint32_t a_plane;     // bytes of one A plane tile in a stage
+  uint32_t atom_bytes;  // MN-major: bytes of one 64-wide atom ([bk rows][128 B]) = its LBO
+  uint32_t sbo, kstep, desc_layout;
   uint32_t tmem_cols;
   // EPI_F32 output
   float* C;
@@ -301,15 +304,15 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
         const int64_t r_beg = (int64_t)z * p.red_chunk;
         const int64_t r_end = r_beg + p.red_chunk < p.red ? r_beg + p.red_chunk : p.red;
         const int a0 = ta * TC_BM, b0 = tb * p.bn;
-        for (int64_t r0 = r_beg; r0 < r_end; r0 += TC_BK) {
+        for (int64_t r0 = r_beg; r0 < r_end; r0 += p.bk) {
           ptx::mbar_wait(empty0 + 8 * s, ph ^ 1);
           const uint32_t fb = full0 + 8 * s;
           ptx::mbar_expect_tx(fb, p.tx_bytes);
-          const uint32_t sa_hi = base + s * p.stage_bytes, sa_lo = sa_hi + TC_A_PLANE;
-          const uint32_t sb_hi = sa_lo + TC_A_PLANE, sb_lo = sb_hi + p.b_plane_bytes;
+          const uint32_t sa_hi = base + s * p.stage_bytes, sa_lo = sa_hi + p.a_plane;
+          const uint32_t sb_hi = sa_lo + p.a_plane, sb_lo = sb_hi + p.b_plane_bytes;
           if (!MN && CL > 1) {
             // own A tile; own half of the B tile (box = bn/2 rows) multicast to both CTAs
-            const uint32_t hoff = (uint32_t)crank * (uint32_t)(p.bn / 2) * 128u;
+            const uint32_t hoff = (uint32_t)crank * (uint32_t)(p.bn / 2) * (uint32_t)(p.bk * 2);
             const int bh0 = b0 + crank * (p.bn / 2);
             ptx::tma_load_2d(sa_hi, &tmAh, fb, (int32_t)r0, a0);
             ptx::tma_load_2d_mcast(sb_hi + hoff, &tmBh, fb, (int32_t)r0, bh0, (uint16_t)0x3);
@@ -321,15 +324,15 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
             ptx::tma_load_2d(sa_lo, &tmAl, fb, (int32_t)r0, a0);
             ptx::tma_load_2d(sb_lo, &tmBl, fb, (int32_t)r0, b0);
           } else {
-            // 64-wide MN atoms, each [TC_BK reduction rows][128 B]
+            // 64-wide MN atoms, each [bk reduction rows][128 B]
             for (int j = 0; j < TC_BM / 64; ++j) {
-              ptx::tma_load_2d(sa_hi + j * 8192, &tmAh, fb, a0 + 64 * j, (int32_t)r0);
-              ptx::tma_load_2d(sa_lo + j * 8192, &tmAl, fb, a0 + 64 * j, (int32_t)r0);
+              ptx::tma_load_2d(sa_hi + j * p.atom_bytes, &tmAh, fb, a0 + 64 * j, (int32_t)r0);
+              ptx::tma_load_2d(sa_lo + j * p.atom_bytes, &tmAl, fb, a0 + 64 * j, (int32_t)r0);
             }
             const int nb_atoms = (p.bn + 63) / 64;
             for (int j = 0; j < nb_atoms; ++j) {
-              ptx::tma_load_2d(sb_hi + j * 8192, &tmBh, fb, b0 + 64 * j, (int32_t)r0);
-              ptx::tma_load_2d(sb_lo + j * 8192, &tmBl, fb, b0 + 64 * j, (int32_t)r0);
+              ptx::tma_load_2d(sb_hi + j * p.atom_bytes, &tmBh, fb, b0 + 64 * j, (int32_t)r0);
+              ptx::tma_load_2d(sb_lo + j * p.atom_bytes, &tmBl, fb, b0 + 64 * j, (int32_t)r0);
             }
           }
           if (++s == (uint32_t)p.num_stages) { s = 0; ph ^= 1; }
@@ -340,8 +343,8 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
     if (lane == 0) {
       // ------------------------------------------------------------ MMA issuer (one thread)
       const uint32_t idesc = ptx::make_idesc_bf16(TC_BM, p.bn, MN ? 1 : 0, MN ? 1 : 0);
-      const uint32_t lbo = MN ? 8192u : 0u;
-      const uint32_t kstep = MN ? 2048u : 32u;
+      const uint32_t lbo = MN ? p.atom_bytes : 0u;
+      const uint32_t kstep = p.kstep, sbo = p.sbo, lay = p.desc_layout;
       uint32_t s = 0, ph = 0;
       int it = 0;
       for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++it) {
@@ -358,19 +361,18 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
         const int rem_i = tile - z * tiles_ab;   // (MN kernels run with CL = 1)
         const bool do_db = MN && p.db != nullptr && (rem_i % p.num_b) == 0;
         const uint32_t idesc_db = ptx::make_idesc_bf16(TC_BM, 16, 1, 1);
-        const uint64_t d_ones = ptx::make_smem_desc(ones_base, lbo, 1024);
+        const uint64_t d_ones = ptx::make_smem_desc(ones_base, 8192u, 1024);
         uint32_t first = 0;
-        for (int64_t r0 = r_beg; r0 < r_end; r0 += TC_BK) {
+        for (int64_t r0 = r_beg; r0 < r_end; r0 += p.bk) {
           ptx::mbar_wait(full0 + 8 * s, ph);
           ptx::tc_fence_after();
-          const uint32_t sa_hi = base + s * p.stage_bytes, sa_lo = sa_hi + TC_A_PLANE;
-          const uint32_t sb_hi = sa_lo + TC_A_PLANE, sb_lo = sb_hi + p.b_plane_bytes;
-#pragma unroll
-          for (int k = 0; k < ((p.dbg & 16) ? 0 : TC_BK / 16); ++k) {
-            const uint64_t da_hi = ptx::make_smem_desc(sa_hi + k * kstep, lbo, 1024);
-            const uint64_t da_lo = ptx::make_smem_desc(sa_lo + k * kstep, lbo, 1024);
-            const uint64_t db_hi = ptx::make_smem_desc(sb_hi + k * kstep, lbo, 1024);
-            const uint64_t db_lo = ptx::make_smem_desc(sb_lo + k * kstep, lbo, 1024);
+          const uint32_t sa_hi = base + s * p.stage_bytes, sa_lo = sa_hi + p.a_plane;
+          const uint32_t sb_hi = sa_lo + p.a_plane, sb_lo = sb_hi + p.b_plane_bytes;
+          for (int k = 0; k < ((p.dbg & 16) ? 0 : p.bk / 16); ++k) {
+            const uint64_t da_hi = ptx::make_smem_desc(sa_hi + k * kstep, lbo, sbo, lay);
+            const uint64_t da_lo = ptx::make_smem_desc(sa_lo + k * kstep, lbo, sbo, lay);
+            const uint64_t db_hi = ptx::make_smem_desc(sb_hi + k * kstep, lbo, sbo, lay);
+            const uint64_t db_lo = ptx::make_smem_desc(sb_lo + k * kstep, lbo, sbo, lay);
             ptx::mma_bf16_ss(d_tmem, da_hi, db_hi, idesc, first);
             if (do_db) {
               ptx::mma_bf16_ss(tmem_base + 256, da_hi, d_ones, idesc_db, first);
@@ -556,13 +558,13 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant
       for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
         const int ta = (tile / p.num_b) * 2 + (int)crank, tb = tile % p.num_b;
         const int a0 = ta * TC_BM, b0 = tb * p.bn + (int)crank * half_bn;
-        for (int64_t r0 = 0; r0 < p.red; r0 += TC_BK) {
+        for (int64_t r0 = 0; r0 < p.red; r0 += p.bk) {
           ptx::mbar_wait(empty0 + 8 * s, ph ^ 1);
           const uint32_t fb_local = full0 + 8 * s;
           if (leader) ptx::mbar_expect_tx(fb_local, 2 * p.tx_bytes);   // bytes of both CTAs land on this barrier
           const uint32_t fb = ptx::mapa(fb_local, 0);
-          const uint32_t sa_hi = base + s * p.stage_bytes, sa_lo = sa_hi + TC_A_PLANE;
-          const uint32_t sb_hi = sa_lo + TC_A_PLANE, sb_lo = sb_hi + p.b_plane_bytes;
+          const uint32_t sa_hi = base + s * p.stage_bytes, sa_lo = sa_hi + p.a_plane;
+          const uint32_t sb_hi = sa_lo + p.a_plane, sb_lo = sb_hi + p.b_plane_bytes;
           ptx::tma_load_2d_pair(sa_hi, &tmAh, fb, (int32_t)r0, a0);
           ptx::tma_load_2d_pair(sb_hi, &tmBh, fb, (int32_t)r0, b0);
           ptx::tma_load_2d_pair(sa_lo, &tmAl, fb, (int32_t)r0, a0);
@@ -584,17 +586,16 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256;
         uint32_t first = 0;
-        for (int64_t r0 = 0; r0 < p.red; r0 += TC_BK) {
+        for (int64_t r0 = 0; r0 < p.red; r0 += p.bk) {
           ptx::mbar_wait(full0 + 8 * s, ph);
           ptx::tc_fence_after();
-          const uint32_t sa_hi = base + s * p.stage_bytes, sa_lo = sa_hi + TC_A_PLANE;
-          const uint32_t sb_hi = sa_lo + TC_A_PLANE, sb_lo = sb_hi + p.b_plane_bytes;
-#pragma unroll
-          for (int k = 0; k < TC_BK / 16; ++k) {
-            const uint64_t da_hi = ptx::make_smem_desc(sa_hi + k * 32u, 0u, 1024);
-            const uint64_t da_lo = ptx::make_smem_desc(sa_lo + k * 32u, 0u, 1024);
-            const uint64_t db_hi = ptx::make_smem_desc(sb_hi + k * 32u, 0u, 1024);
-            const uint64_t db_lo = ptx::make_smem_desc(sb_lo + k * 32u, 0u, 1024);
+          const uint32_t sa_hi = base + s * p.stage_bytes, sa_lo = sa_hi + p.a_plane;
+          const uint32_t sb_hi = sa_lo + p.a_plane, sb_lo = sb_hi + p.b_plane_bytes;
+          for (int k = 0; k < p.bk / 16; ++k) {
+            const uint64_t da_hi = ptx::make_smem_desc(sa_hi + k * 32u, 0u, p.sbo, p.desc_layout);
+            const uint64_t da_lo = ptx::make_smem_desc(sa_lo + k * 32u, 0u, p.sbo, p.desc_layout);
+            const uint64_t db_hi = ptx::make_smem_desc(sb_hi + k * 32u, 0u, p.sbo, p.desc_layout);
+            const uint64_t db_lo = ptx::make_smem_desc(sb_lo + k * 32u, 0u, p.sbo, p.desc_layout);
             ptx::mma_bf16_ss_pair(d_tmem, da_hi, db_hi, idesc, first);
             first = 1;
             ptx::mma_bf16_ss_pair(d_tmem, da_hi, db_lo, idesc, 1);
@@ -750,8 +751,10 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-// 2D bf16 tensor [rows][cols] with row pitch `pitch` elements; box = {64 cols, box_rows}, SWIZZLE_128B.
-static int make_map(CUtensorMap* m, const void* ptr, int64_t rows, int64_t cols, int64_t pitch, int box_rows) {
+// 2D bf16 tensor [rows][cols] with row pitch `pitch` elements; box = {box_cols (64: SWIZZLE_128B, 32: SWIZZLE_64B),
+// box_rows}.
+static int make_map(CUtensorMap* m, const void* ptr, int64_t rows, int64_t cols, int64_t pitch, int box_rows,
+                    int box_cols = 64) {
   EncodeTiledFn enc = get_encode();
   if (!enc) {
     set_error("tc: cuTensorMapEncodeTiled entry point unavailable");
@@ -759,10 +762,11 @@ static int make_map(CUtensorMap* m, const void* ptr, int64_t rows, int64_t cols,
   }
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)pitch * 2};
-  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("tc: cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld pitch=%lld box_rows=%d", (int)r,
@@ -872,6 +876,19 @@ static void fill_epilogue(GemmParams& p, const EpiArgs& e) {
     dbg = v ? atoi(v) : 0;
   }
   p.dbg = (uint32_t)dbg;
+}
+
+// Reduction elements per smem stage.  Measured on cfg2 (profiles/r01_gemm_experiments.md): the K-major kernels
+// are ~4% faster with 64 (two or three 128-byte-swizzled stages), the MN-major weight-gradient kernel ~7% faster
+// with 32 (twice as many, half as large stages).  GANTTS_B200_BK=32|64 forces one value for both.
+static int stage_bk(bool mn) {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GANTTS_B200_BK");
+    v = e ? atoi(e) : 0;
+    if (v != 32 && v != 64) v = 0;
+  }
+  return v ? v : (mn ? 32 : 64);
 }
 
 static int use_pdl() {
@@ -991,14 +1008,20 @@ static int launch_gemm_kk(const Planes& A, const Planes& B, const EpiArgs& e, cu
     set_error("gemm_kk: reduction extents differ (%lld vs %lld)", (long long)A.cols, (long long)B.cols);
     return GANTTS_E_BADARG;
   }
-  p.red_chunk = (p.red + TC_BK - 1) / TC_BK * TC_BK;
+  p.bk = stage_bk(false);
+  const uint32_t rowb = (uint32_t)p.bk * 2;                 // bytes of one K-major smem row (128 or 64)
+  p.a_plane = TC_BM * rowb;
+  p.sbo = 8 * rowb;
+  p.kstep = 32;
+  p.desc_layout = p.bk == 64 ? 2u : 4u;
+  p.red_chunk = (p.red + p.bk - 1) / p.bk * p.bk;
   p.bn = pick_bn(p.cols_b);
   p.num_a = (int)((p.rows_a + TC_BM - 1) / TC_BM);
   p.num_b = (p.cols_b + p.bn - 1) / p.bn;
   p.num_z = 1;
-  p.b_plane_bytes = ((uint32_t)p.bn * 128 + 1023) / 1024 * 1024;
-  p.stage_bytes = 2 * TC_A_PLANE + 2 * p.b_plane_bytes;
-  p.tx_bytes = 2 * TC_A_PLANE + 2 * (uint32_t)p.bn * 128;
+  p.b_plane_bytes = ((uint32_t)p.bn * rowb + 1023) / 1024 * 1024;
+  p.stage_bytes = 2 * p.a_plane + 2 * p.b_plane_bytes;
+  p.tx_bytes = 2 * p.a_plane + 2 * (uint32_t)p.bn * rowb;
   p.num_stages = (int)((216 * 1024) / p.stage_bytes);
   if (p.num_stages > TC_MAX_STAGES) p.num_stages = TC_MAX_STAGES;
   p.tmem_cols = 512;
@@ -1009,19 +1032,19 @@ static int launch_gemm_kk(const Planes& A, const Planes& B, const EpiArgs& e, cu
                    ? (uint32_t)p.num_stages * p.stage_bytes + 256u : 0u;
   // GANTTS_B200_CLUSTER=3: CTA-pair MMA (cta_group::2), each CTA holds half of the B tile
   if ((use_cluster() == 3 || (use_cluster() == 0 && p.num_b >= 2)) && p.num_a >= 2) {
-    p.b_plane_bytes = ((uint32_t)(p.bn / 2) * 128 + 1023) / 1024 * 1024;
-    p.stage_bytes = 2 * TC_A_PLANE + 2 * p.b_plane_bytes;
-    p.tx_bytes = 2 * TC_A_PLANE + 2 * (uint32_t)(p.bn / 2) * 128;
+    p.b_plane_bytes = ((uint32_t)(p.bn / 2) * rowb + 1023) / 1024 * 1024;
+    p.stage_bytes = 2 * p.a_plane + 2 * p.b_plane_bytes;
+    p.tx_bytes = 2 * p.a_plane + 2 * (uint32_t)(p.bn / 2) * rowb;
     p.num_stages = (int)((216 * 1024) / p.stage_bytes);
     if (p.num_stages > TC_MAX_STAGES) p.num_stages = TC_MAX_STAGES;
     p.bias_off = (e.bias && (size_t)p.num_b * p.bn * sizeof(float) <= TC_BIAS_SMEM)
                      ? (uint32_t)p.num_stages * p.stage_bytes + 256u : 0u;
     CUtensorMap mAh, mAl, mBh, mBl;
     int rc;
-    if ((rc = make_map(&mAh, A.hi, A.rows, A.cols, A.pitch, TC_BM))) return rc;
-    if ((rc = make_map(&mAl, A.lo, A.rows, A.cols, A.pitch, TC_BM))) return rc;
-    if ((rc = make_map(&mBh, B.hi, B.rows, B.cols, B.pitch, p.bn / 2))) return rc;
-    if ((rc = make_map(&mBl, B.lo, B.rows, B.cols, B.pitch, p.bn / 2))) return rc;
+    if ((rc = make_map(&mAh, A.hi, A.rows, A.cols, A.pitch, TC_BM, p.bk))) return rc;
+    if ((rc = make_map(&mAl, A.lo, A.rows, A.cols, A.pitch, TC_BM, p.bk))) return rc;
+    if ((rc = make_map(&mBh, B.hi, B.rows, B.cols, B.pitch, p.bn / 2, p.bk))) return rc;
+    if ((rc = make_map(&mBl, B.lo, B.rows, B.cols, B.pitch, p.bn / 2, p.bk))) return rc;
     switch (e.epi) {
       case EPI_F32: return launch_pair_kernel<EPI_F32>(mAh, mAl, mBh, mBl, p, st);
       case EPI_PLANES_FWD: return launch_pair_kernel<EPI_PLANES_FWD>(mAh, mAl, mBh, mBl, p, st);
@@ -1032,10 +1055,10 @@ static int launch_gemm_kk(const Planes& A, const Planes& B, const EpiArgs& e, cu
   const bool cl2 = use_cluster() == 2 && p.num_a >= 2;
   CUtensorMap mAh, mAl, mBh, mBl;
   int rc;
-  if ((rc = make_map(&mAh, A.hi, A.rows, A.cols, A.pitch, TC_BM))) return rc;
-  if ((rc = make_map(&mAl, A.lo, A.rows, A.cols, A.pitch, TC_BM))) return rc;
-  if ((rc = make_map(&mBh, B.hi, B.rows, B.cols, B.pitch, cl2 ? p.bn / 2 : p.bn))) return rc;
-  if ((rc = make_map(&mBl, B.lo, B.rows, B.cols, B.pitch, cl2 ? p.bn / 2 : p.bn))) return rc;
+  if ((rc = make_map(&mAh, A.hi, A.rows, A.cols, A.pitch, TC_BM, p.bk))) return rc;
+  if ((rc = make_map(&mAl, A.lo, A.rows, A.cols, A.pitch, TC_BM, p.bk))) return rc;
+  if ((rc = make_map(&mBh, B.hi, B.rows, B.cols, B.pitch, cl2 ? p.bn / 2 : p.bn, p.bk))) return rc;
+  if ((rc = make_map(&mBl, B.lo, B.rows, B.cols, B.pitch, cl2 ? p.bn / 2 : p.bn, p.bk))) return rc;
   if (cl2) {
     switch (e.epi) {
       case EPI_F32: return launch_kernel<false, EPI_F32, 2>(mAh, mAl, mBh, mBl, p, st);
@@ -1057,11 +1080,12 @@ static int launch_gemm_kk(const Planes& A, const Planes& B, const EpiArgs& e, cu
 static size_t mn_partial_bytes(int64_t red, int rows_a, int cols_b, int* splits_out, int64_t* chunk_out) {
   int bn = pick_bn(cols_b);
   int tiles = ((rows_a + TC_BM - 1) / TC_BM) * ((cols_b + bn - 1) / bn);
-  int64_t blocks = (red + TC_BK - 1) / TC_BK;
+  const int bk = stage_bk(true);
+  int64_t blocks = (red + bk - 1) / bk;
   int64_t splits = num_sms() / tiles;
   if (splits < 1) splits = 1;
   if (splits > blocks) splits = blocks;
-  int64_t chunk = (blocks + splits - 1) / splits * TC_BK;
+  int64_t chunk = (blocks + splits - 1) / splits * bk;
   splits = (red + chunk - 1) / chunk;
   if (splits_out) *splits_out = (int)splits;
   if (chunk_out) *chunk_out = chunk;
@@ -1141,8 +1165,14 @@ static int launch_gemm_mn(const Planes& A, const Planes& B, float* C, float* gb,
   p.num_a = (int)((p.rows_a + TC_BM - 1) / TC_BM);
   p.num_b = (p.cols_b + p.bn - 1) / p.bn;
   const int nb_atoms = (p.bn + 63) / 64;
-  p.b_plane_bytes = (uint32_t)nb_atoms * 8192;
-  p.stage_bytes = 2 * TC_A_PLANE + 2 * p.b_plane_bytes;
+  p.bk = stage_bk(true);
+  p.atom_bytes = (uint32_t)p.bk * 128;                      // [bk reduction rows][128 B of 64 MN elements]
+  p.a_plane = (TC_BM / 64) * p.atom_bytes;
+  p.sbo = 1024;
+  p.kstep = 2048;
+  p.desc_layout = 2;
+  p.b_plane_bytes = (uint32_t)nb_atoms * p.atom_bytes;
+  p.stage_bytes = 2 * p.a_plane + 2 * p.b_plane_bytes;
   p.tx_bytes = p.stage_bytes;
   p.num_stages = (int)((212 * 1024) / p.stage_bytes);
   if (p.num_stages > TC_MAX_STAGES) p.num_stages = TC_MAX_STAGES;
@@ -1160,10 +1190,10 @@ static int launch_gemm_mn(const Planes& A, const Planes& B, float* C, float* gb,
   p.db = gb ? (direct ? gb : db_partial) : nullptr;
   CUtensorMap mAh, mAl, mBh, mBl;
   int rc;
-  if ((rc = make_map(&mAh, A.hi, A.rows, A.cols, A.pitch, TC_BK))) return rc;
-  if ((rc = make_map(&mAl, A.lo, A.rows, A.cols, A.pitch, TC_BK))) return rc;
-  if ((rc = make_map(&mBh, B.hi, B.rows, B.cols, B.pitch, TC_BK))) return rc;
-  if ((rc = make_map(&mBl, B.lo, B.rows, B.cols, B.pitch, TC_BK))) return rc;
+  if ((rc = make_map(&mAh, A.hi, A.rows, A.cols, A.pitch, p.bk))) return rc;
+  if ((rc = make_map(&mAl, A.lo, A.rows, A.cols, A.pitch, p.bk))) return rc;
+  if ((rc = make_map(&mBh, B.hi, B.rows, B.cols, B.pitch, p.bk))) return rc;
+  if ((rc = make_map(&mBl, B.lo, B.rows, B.cols, B.pitch, p.bk))) return rc;
   if ((rc = launch_kernel<true, EPI_F32, 1>(mAh, mAl, mBh, mBl, p, st))) return rc;
   if (!direct) {
     if (defer && defer->n + 2 <= REDUCE_MAX_JOBS) {

@@ -210,6 +210,203 @@ gemv_bwd_kernel(const float* __restrict__ gy, int64_t gy_rs, const float* __rest
   }
 }
 
+// ---- vectorised variants (K % 8 == 0): each lane owns 8 consecutive columns of every 256-column chunk
+// (one 16-byte load per plane), several rows per warp in flight, weights and gW accumulators in registers.
+__device__ __forceinline__ void unpack8(const uint4& h, const uint4& l, float (&a)[8]) {
+  const uint32_t hh[4] = {h.x, h.y, h.z, h.w}, ll[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    a[2 * i] = __uint_as_float(hh[i] << 16) + __uint_as_float(ll[i] << 16);
+    a[2 * i + 1] = __uint_as_float(hh[i] & 0xffff0000u) + __uint_as_float(ll[i] & 0xffff0000u);
+  }
+}
+
+__device__ __forceinline__ uint4 ldg_stream16(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p));
+  return v;
+}
+
+template <int NCH, int RU>
+__global__ void __launch_bounds__(GEMV_THREADS)
+gemv_fwd_vec_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, int64_t pitch,
+                    const float* __restrict__ w, const float* __restrict__ b, float* __restrict__ y, int64_t y_rs,
+                    int64_t M, int K, int sigmoid) {
+  const int lane = threadIdx.x & 31;
+  float wr[NCH][8];
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) {
+    const int c = ch * 256 + lane * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) wr[ch][j] = c < K ? w[c + j] : 0.f;
+  }
+  const int64_t warp = ((int64_t)blockIdx.x * GEMV_THREADS + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * GEMV_THREADS) >> 5;
+  const float bias = b[0];
+  for (int64_t r0 = warp * RU; r0 < M; r0 += nwarps * RU) {
+    uint4 h[RU][NCH], l[RU][NCH];
+#pragma unroll
+    for (int u = 0; u < RU; ++u) {
+      const int64_t r = r0 + u < M ? r0 + u : M - 1;
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        const int c = ch * 256 + lane * 8;
+        if (c < K) {
+          h[u][ch] = ldg_stream16(hi + r * pitch + c);
+          l[u][ch] = ldg_stream16(lo + r * pitch + c);
+        } else {
+          h[u][ch] = make_uint4(0, 0, 0, 0);
+          l[u][ch] = make_uint4(0, 0, 0, 0);
+        }
+      }
+    }
+    float acc[RU];
+#pragma unroll
+    for (int u = 0; u < RU; ++u) {
+      acc[u] = 0.f;
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        float a[8];
+        unpack8(h[u][ch], l[u][ch], a);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[u] = fmaf(a[j], wr[ch][j], acc[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < RU; ++u) acc[u] = warp_sum(acc[u]);
+    if (lane == 0) {
+#pragma unroll
+      for (int u = 0; u < RU; ++u)
+        if (r0 + u < M) {
+          const float z = acc[u] + bias;
+          y[(r0 + u) * y_rs] = sigmoid ? 1.f / (1.f + expf(-z)) : z;
+        }
+    }
+  }
+}
+
+template <int NCH, int RU>
+__global__ void __launch_bounds__(GEMV_THREADS)
+gemv_bwd_vec_kernel(const float* __restrict__ gy, int64_t gy_rs, const float* __restrict__ y, int64_t y_rs,
+                    const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, int64_t pitch,
+                    const uint32_t* __restrict__ code, int64_t code_pitch, const float* __restrict__ w,
+                    __nv_bfloat16* __restrict__ ghi, __nv_bfloat16* __restrict__ glo, int64_t gpitch,
+                    float* __restrict__ partial, int64_t M, int K, int sigmoid, float dpos, float dneg, float dzero,
+                    int want_gw) {
+  __shared__ float gws[GEMV_THREADS / 32][GEMV_MAX_K + 1];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  float wr[NCH][8], gw[NCH][8];
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) {
+    const int c = ch * 256 + lane * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      wr[ch][j] = c < K ? w[c + j] : 0.f;
+      gw[ch][j] = 0.f;
+    }
+  }
+  const int64_t warp = ((int64_t)blockIdx.x * GEMV_THREADS + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * GEMV_THREADS) >> 5;
+  float gsum = 0.f;
+  for (int64_t r0 = warp * RU; r0 < M; r0 += nwarps * RU) {
+    uint4 h[RU][NCH], l[RU][NCH];
+    uint32_t cw[RU][NCH];
+    float g[RU];
+#pragma unroll
+    for (int u = 0; u < RU; ++u) {
+      const bool ok = r0 + u < M;
+      const int64_t r = ok ? r0 + u : M - 1;
+      float gg = ok ? gy[r * gy_rs] : 0.f;
+      if (sigmoid) {
+        const float yy = y[r * y_rs];
+        gg *= yy * (1.f - yy);
+      }
+      g[u] = gg;
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        const int c = ch * 256 + lane * 8;
+        if (c < K) {
+          if (want_gw) {
+            h[u][ch] = ldg_stream16(hi + r * pitch + c);
+            l[u][ch] = ldg_stream16(lo + r * pitch + c);
+          }
+          cw[u][ch] = __ldg(code + r * code_pitch + (c >> 4)) >> (2 * (c & 15));
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < RU; ++u) {
+      gsum += g[u];
+      if (r0 + u >= M) continue;
+      const int64_t r = r0 + u;
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        const int c = ch * 256 + lane * 8;
+        if (c >= K) continue;
+        if (want_gw) {
+          float a[8];
+          unpack8(h[u][ch], l[u][ch], a);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) gw[ch][j] = fmaf(g[u], a[j], gw[ch][j]);
+        }
+        // gZ_prev = (g * w) * act'(H), derivative class from the 2-bit code plane
+        uint32_t oh[4], ol[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t c0 = (cw[u][ch] >> (4 * j)) & 3u, c1 = (cw[u][ch] >> (4 * j + 2)) & 3u;
+          const float v0 = g[u] * wr[ch][2 * j] * ((c0 & 1u) ? dzero : ((c0 & 2u) ? dneg : dpos));
+          const float v1 = g[u] * wr[ch][2 * j + 1] * ((c1 & 1u) ? dzero : ((c1 & 2u) ? dneg : dpos));
+          oh[j] = pack_bf16x2(v0, v1);
+          ol[j] = pack_bf16x2(v0 - __uint_as_float(oh[j] << 16), v1 - __uint_as_float(oh[j] & 0xffff0000u));
+        }
+        *reinterpret_cast<uint4*>(ghi + r * gpitch + c) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+        *reinterpret_cast<uint4*>(glo + r * gpitch + c) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+      }
+    }
+  }
+  if (want_gw) {
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      const int c = ch * 256 + lane * 8;
+      if (c < K) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) gws[wid][c + j] = gw[ch][j];
+      }
+    }
+    if (lane == 0) gws[wid][K] = gsum;
+    __syncthreads();
+    for (int i = threadIdx.x; i <= K; i += GEMV_THREADS) {
+      float s = 0.f;
+#pragma unroll
+      for (int q = 0; q < GEMV_THREADS / 32; ++q) s += gws[q][i];
+      partial[(int64_t)blockIdx.x * (K + 1) + i] = s;
+    }
+  }
+}
+
+// out_w[c] (+)= sum_b partial[b][c] (c < K), out_b[0] (+)= sum_b partial[b][K]; fixed summation order.
+__global__ void __launch_bounds__(256)
+gemv_partial_reduce_kernel(const float* __restrict__ partial, int blocks, int K, float* __restrict__ out_w,
+                           float* __restrict__ out_b, int accumulate) {
+  __shared__ float sm[8][33];
+  const int cl = threadIdx.x & 31, rg = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  float s = 0.f;
+  if (c <= K)
+    for (int b = rg; b < blocks; b += 8) s += partial[(int64_t)b * (K + 1) + c];
+  sm[rg][cl] = s;
+  __syncthreads();
+  if (rg == 0 && c <= K) {
+    float t = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t += sm[q][cl];
+    float* o = c < K ? (out_w ? out_w + c : nullptr) : out_b;
+    if (o) *o = accumulate ? *o + t : t;
+  }
+}
+
 constexpr int GEMV_BLOCKS = 148 * 2;
 
 constexpr int MLP_COLSUM_CHUNKS = 128;
@@ -345,8 +542,19 @@ extern "C" int gantts_mlp_fwd(const gantts_mlp_t* m, const float* x, int64_t x_r
     } else {
       if (m->dims[L] == 1 && L >= 2 && m->dims[l] <= GEMV_MAX_K && (m->dims[l] & 1) == 0) {
         // single-output last layer: GEMV + sigmoid, one warp per row
-        gemv_fwd_kernel<<<GEMV_BLOCKS, GEMV_THREADS, 0, st>>>(t.H[l].hi, t.H[l].lo, t.H[l].pitch, m->W[l], m->b[l], y,
-                                                              y_rs, M, m->dims[l], m->last_act == GANTTS_ACT_SIGMOID);
+        const int Kl = m->dims[l], sg = m->last_act == GANTTS_ACT_SIGMOID;
+        if (Kl % 8 == 0 && Kl <= 256)
+          gemv_fwd_vec_kernel<1, 4><<<2 * GEMV_BLOCKS, GEMV_THREADS, 0, st>>>(t.H[l].hi, t.H[l].lo, t.H[l].pitch, m->W[l],
+                                                                          m->b[l], y, y_rs, M, Kl, sg);
+        else if (Kl % 8 == 0 && Kl <= 512)
+          gemv_fwd_vec_kernel<2, 2><<<2 * GEMV_BLOCKS, GEMV_THREADS, 0, st>>>(t.H[l].hi, t.H[l].lo, t.H[l].pitch, m->W[l],
+                                                                          m->b[l], y, y_rs, M, Kl, sg);
+        else if (Kl % 8 == 0)
+          gemv_fwd_vec_kernel<4, 1><<<2 * GEMV_BLOCKS, GEMV_THREADS, 0, st>>>(t.H[l].hi, t.H[l].lo, t.H[l].pitch, m->W[l],
+                                                                          m->b[l], y, y_rs, M, Kl, sg);
+        else
+          gemv_fwd_kernel<<<GEMV_BLOCKS, GEMV_THREADS, 0, st>>>(t.H[l].hi, t.H[l].lo, t.H[l].pitch, m->W[l], m->b[l], y,
+                                                                y_rs, M, Kl, sg);
         GANTTS_LAUNCH_CHECK("gemv_fwd_kernel");
         continue;
       }
@@ -407,24 +615,26 @@ extern "C" int gantts_mlp_bwd(const gantts_mlp_t* m, const float* gy, int64_t gy
     G = carve_planes(cg, M, K1);
     const float ks = m->dropout_p > 0.f ? 1.f / (1.f - m->dropout_p) : 1.f;
     const int want = (gW && gW[L - 1]) || (gb && gb[L - 1]);
-    gemv_bwd_kernel<<<GEMV_BLOCKS, GEMV_THREADS, 0, st>>>(
-        gy, gy_rs, y, y_rs, t.H[L - 1].hi, t.H[L - 1].lo, t.H[L - 1].pitch, t.code[L - 1], t.code_pitch[L - 1],
-        m->W[L - 1], G.hi, G.lo, G.pitch, gemv_part, M, K1, m->last_act == GANTTS_ACT_SIGMOID ? 1 : 0, ks,
-        m->slope * ks, m->dropout_p > 0.f ? 0.f : m->slope, want);
+#define GANTTS_GEMV_BWD_ARGS                                                                                     \
+  gy, gy_rs, y, y_rs, t.H[L - 1].hi, t.H[L - 1].lo, t.H[L - 1].pitch, t.code[L - 1], t.code_pitch[L - 1],       \
+      m->W[L - 1], G.hi, G.lo, G.pitch, gemv_part, M, K1, m->last_act == GANTTS_ACT_SIGMOID ? 1 : 0, ks,        \
+      m->slope * ks, m->dropout_p > 0.f ? 0.f : m->slope, want
+    if (K1 % 8 == 0 && K1 <= 256)
+      gemv_bwd_vec_kernel<1, 4><<<GEMV_BLOCKS, GEMV_THREADS, 0, st>>>(GANTTS_GEMV_BWD_ARGS);
+    else if (K1 % 8 == 0 && K1 <= 512)
+      gemv_bwd_vec_kernel<2, 2><<<GEMV_BLOCKS, GEMV_THREADS, 0, st>>>(GANTTS_GEMV_BWD_ARGS);
+    else if (K1 % 8 == 0)
+      gemv_bwd_vec_kernel<4, 1><<<GEMV_BLOCKS, GEMV_THREADS, 0, st>>>(GANTTS_GEMV_BWD_ARGS);
+    else
+      gemv_bwd_kernel<<<GEMV_BLOCKS, GEMV_THREADS, 0, st>>>(GANTTS_GEMV_BWD_ARGS);
+#undef GANTTS_GEMV_BWD_ARGS
     GANTTS_LAUNCH_CHECK("gemv_bwd_kernel");
     if (want) {
-      // partial rows are [K1 weights | 1 bias]: reduce them with the deferred list (strided views are not
-      // supported there), so use two plain reductions
-      if (gW && gW[L - 1]) {
-        // gather the weight part: partial is [blocks][K1+1]; reduce column-wise
-        splitk_reduce_strided_kernel<<<(K1 + 255) / 256, 256, 0, st>>>(gemv_part, GEMV_BLOCKS, K1 + 1, 0, K1, gW[L - 1],
-                                                                     accumulate);
-        GANTTS_LAUNCH_CHECK("splitk_reduce_strided_kernel(gW)");
-      }
-      if (gb && gb[L - 1]) {
-        splitk_reduce_strided_kernel<<<1, 256, 0, st>>>(gemv_part, GEMV_BLOCKS, K1 + 1, K1, 1, gb[L - 1], accumulate);
-        GANTTS_LAUNCH_CHECK("splitk_reduce_strided_kernel(gb)");
-      }
+      // partial rows are [K1 weights | 1 bias]: one column-parallel reduction for both
+      gemv_partial_reduce_kernel<<<(K1 + 1 + 31) / 32, 256, 0, st>>>(gemv_part, GEMV_BLOCKS, K1,
+                                                                    gW ? gW[L - 1] : nullptr,
+                                                                    gb ? gb[L - 1] : nullptr, accumulate);
+      GANTTS_LAUNCH_CHECK("gemv_partial_reduce_kernel");
     }
     l_start = L - 2;
   } else

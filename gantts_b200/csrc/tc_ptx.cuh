@@ -209,13 +209,16 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // K-major tile  [rows][64 bf16] (128 B rows, 8-row groups of 1024 B): SBO = 1024, LBO unused.
 // MN-major tile [k rows][64 bf16 of MN] per 64-wide MN atom: SBO = 1024 (next 8 k rows),
 //   LBO = bytes between consecutive 64-wide MN atoms.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// layout: 2 = SWIZZLE_128B (128 B rows), 4 = SWIZZLE_64B (64 B rows: K-major tiles with 32 bf16 of K per stage,
+// 8-row groups of 512 B => SBO = 512).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout = 2) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3fffu);
   d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3fffu) << 16;
   d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3fffu) << 32;
   d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(2) << 61;
+  d |= static_cast<uint64_t>(layout & 7u) << 61;
   return d;
 }
 // Instruction descriptor for kind::f16 with bf16 A/B and fp32 D:
