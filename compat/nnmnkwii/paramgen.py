@@ -1,4 +1,5 @@
-"""nnmnkwii.paramgen shim: ``unit_variance_mlpg_matrix(windows, T)`` (reference train.py:511).
+"""nnmnkwii.paramgen shim: ``unit_variance_mlpg_matrix(windows, T)`` (reference train.py:511) and
+``mlpg(mean_frames, variance_frames, windows)`` (reference evaluation_tts.py:70-72,92-94).
 
 The reference rebuilds this dense (T, num_windows*T) float32 matrix on the CPU for every batch
 (O(T^2) banded inverse + O(T^3) dense product in the real package).  Here it is assembled once per
@@ -38,3 +39,18 @@ def unit_variance_mlpg_matrix(windows, T):
     R = np.ascontiguousarray(R.astype(np.float32))
     _cache[key] = R
     return R
+
+
+def mlpg(mean_frames, variance_frames, windows):
+    """Static trajectory (T, sd) from (T, nw*sd) means and (nw*sd,) or (T, nw*sd) variances: numpy in, numpy
+    out like the real package; the banded solve runs on the GPU (gantts_mlpg_var)."""
+    import torch
+    mean_frames = np.asarray(mean_frames)
+    dtype = mean_frames.dtype if mean_frames.dtype in (np.float32, np.float64) else np.float64
+    nw = len(windows)
+    if nw == 1 and tuple(windows[0][:2]) == (0, 0):
+        return mean_frames                                        # static-only features: nothing to solve
+    dev = torch.device("cuda")
+    mu = torch.as_tensor(np.ascontiguousarray(mean_frames, dtype=np.float32), device=dev)
+    var = torch.as_tensor(np.ascontiguousarray(variance_frames, dtype=np.float32), device=dev)
+    return ops.mlpg_var(mu, var, ops.windows_key(windows)).cpu().numpy().astype(dtype)

@@ -37,6 +37,14 @@ class WindowsT(ctypes.Structure):
                 ("coef", (ctypes.c_float * MAX_TAPS) * MAX_WINDOWS)]
 
 
+class DistortionColsT(ctypes.Structure):
+    _fields_ = [("mcd_start", ctypes.c_int), ("mcd_count", ctypes.c_int),
+                ("bap_start", ctypes.c_int), ("bap_count", ctypes.c_int),
+                ("lf0_col", ctypes.c_int), ("vuv_col", ctypes.c_int),
+                ("lf0_linear", ctypes.c_int),
+                ("mse_start", ctypes.c_int), ("mse_count", ctypes.c_int)]
+
+
 MAX_LAYERS = 8
 
 
@@ -95,6 +103,12 @@ SIGNATURES = {
     "gantts_masked_sse_workspace_bytes": (_sz, []),
     "gantts_masked_sse_fwd": (_i, [_vp, _i64, _vp, _i64, _vp, _i64, _i, _vp, _vp, _sz, _vp]),
     "gantts_masked_sse_bwd": (_i, [_vp, _i64, _vp, _i64, _vp, _i64, _i, _vp, _vp, _i64, _i, _vp]),
+    "gantts_mlpg_var_workspace_bytes": (_sz, [ctypes.POINTER(WindowsT), _i, _i, _i]),
+    "gantts_mlpg_var": (_i, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, ctypes.POINTER(WindowsT),
+                             _i, _i, _i, _vp, _sz, _vp]),
+    "gantts_distortions_workspace_bytes": (_sz, []),
+    "gantts_distortions": (_i, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i, _i, _i, _vp, _vp,
+                                ctypes.POINTER(DistortionColsT), _vp, _vp, _sz, _vp]),
     "gantts_masked_bce_fwd": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _sz, _vp]),
     "gantts_masked_bce_bwd": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _vp]),
     "gantts_linear_workspace_bytes": (_sz, [_i64, _i, _i, _i]),

@@ -696,6 +696,192 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant
   }
 }
 
+
+// ---------------------------------------------------------------------------- CTA-pair kernel, MN-major
+// Weight-gradient GEMM C[n][k] = sum_m A[m][n] B[m][k] on CTA pairs: the pair's MMA is 256 (n) x bn (k), each
+// CTA stages its own 128 columns of A and HALF of the B columns per reduction block, so the per-SM operand
+// ingest per unit of MMA work drops from (128 + bn) to (128 + bn/2) rows -- the single-CTA MN kernel is
+// ingest-bound (profiles/r01_gemm_experiments.md).  Requires bn % 128 == 0 (each half is whole 64-wide atoms).
+// One accumulator at TMEM columns [0, bn); the bias gradient (column sums of A) accumulates at [256, 272)
+// through an extra N = 16 MMA against an all-ones K-major tile present in both CTAs' shared memory.
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_pair_mn_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+                    const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
+                    const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = ptx::smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t ones_base = base + p.ones_off;
+  const uint32_t bar_base = base + p.num_stages * p.stage_bytes + 8192u;
+  const uint32_t full0 = bar_base, empty0 = bar_base + 8 * TC_MAX_STAGES;
+  const uint32_t tfull0 = bar_base + 16 * TC_MAX_STAGES, tempty0 = tfull0 + 16;
+  const uint32_t tmem_slot = tempty0 + 16;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = ptx::cluster_ctarank();
+  const bool leader = crank == 0;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.num_stages; ++s) {
+      ptx::mbar_init(full0 + 8 * s, 1);
+      ptx::mbar_init(empty0 + 8 * s, 1);
+    }
+    ptx::mbar_init(tfull0, 1);
+    ptx::mbar_init(tempty0, 2 * TC_EPI_WARPS);
+    ptx::fence_barrier_init();
+    ptx::prefetch_tensormap(&tmAh);
+    ptx::prefetch_tensormap(&tmAl);
+    ptx::prefetch_tensormap(&tmBh);
+    ptx::prefetch_tensormap(&tmBl);
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc_pair(tmem_slot, p.tmem_cols);
+    ptx::tmem_relinquish_pair();
+  }
+  {
+    uint32_t* ones = reinterpret_cast<uint32_t*>(smem_raw + (ones_base - raw));
+    for (int i = threadIdx.x; i < 8192 / 4; i += TC_THREADS) ones[i] = 0x3F803F80u;
+    ptx::fence_proxy_async();
+  }
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+
+  const int num_pairs = (p.num_a + 1) / 2;
+  const int tiles_ab = num_pairs * p.num_b;
+  const int total_tiles = tiles_ab * p.num_z;
+  const int first_tile = (int)blockIdx.x / 2, tile_step = (int)gridDim.x / 2;
+  const int half_bn = p.bn / 2;
+  const int half_atoms = half_bn / 64;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------------------------------------ TMA producer (both CTAs)
+      uint32_t s = 0, ph = 0;
+      for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
+        const int z = tile / tiles_ab, rem = tile - z * tiles_ab;
+        const int ta = (rem / p.num_b) * 2 + (int)crank, tb = rem % p.num_b;
+        const int64_t r_beg = (int64_t)z * p.red_chunk;
+        const int64_t r_end = r_beg + p.red_chunk < p.red ? r_beg + p.red_chunk : p.red;
+        const int a0 = ta * TC_BM, b0 = tb * p.bn + (int)crank * half_bn;
+        for (int64_t r0 = r_beg; r0 < r_end; r0 += p.bk) {
+          ptx::mbar_wait(empty0 + 8 * s, ph ^ 1);
+          const uint32_t fb_local = full0 + 8 * s;
+          if (leader) ptx::mbar_expect_tx(fb_local, 2 * p.tx_bytes);
+          const uint32_t fb = ptx::mapa(fb_local, 0);
+          const uint32_t sa_hi = base + s * p.stage_bytes, sa_lo = sa_hi + p.a_plane;
+          const uint32_t sb_hi = sa_lo + p.a_plane, sb_lo = sb_hi + p.b_plane_bytes;
+          for (int j = 0; j < TC_BM / 64; ++j) {
+            ptx::tma_load_2d_pair(sa_hi + j * p.atom_bytes, &tmAh, fb, a0 + 64 * j, (int32_t)r0);
+            ptx::tma_load_2d_pair(sa_lo + j * p.atom_bytes, &tmAl, fb, a0 + 64 * j, (int32_t)r0);
+          }
+          for (int j = 0; j < half_atoms; ++j) {
+            ptx::tma_load_2d_pair(sb_hi + j * p.atom_bytes, &tmBh, fb, b0 + 64 * j, (int32_t)r0);
+            ptx::tma_load_2d_pair(sb_lo + j * p.atom_bytes, &tmBl, fb, b0 + 64 * j, (int32_t)r0);
+          }
+          if (++s == (uint32_t)p.num_stages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      // ------------------------------------------------------------ MMA issuer (leader CTA, one thread)
+      const uint32_t idesc = ptx::make_idesc_bf16(2 * TC_BM, p.bn, 1, 1);
+      const uint32_t idesc_db = ptx::make_idesc_bf16(2 * TC_BM, 16, 1, 0);   // ones tile read K-major
+      const uint64_t d_ones = ptx::make_smem_desc(ones_base, 0u, 1024);
+      const uint32_t lbo = p.atom_bytes;
+      uint32_t s = 0, ph = 0;
+      int it = 0;
+      for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++it) {
+        const int z = tile / tiles_ab, rem = tile - z * tiles_ab;
+        const int64_t r_beg = (int64_t)z * p.red_chunk;
+        const int64_t r_end = r_beg + p.red_chunk < p.red ? r_beg + p.red_chunk : p.red;
+        const bool do_db = p.db != nullptr && (rem % p.num_b) == 0;
+        ptx::mbar_wait(tempty0, (uint32_t)(it & 1) ^ 1);
+        ptx::tc_fence_after();
+        uint32_t first = 0;
+        for (int64_t r0 = r_beg; r0 < r_end; r0 += p.bk) {
+          ptx::mbar_wait(full0 + 8 * s, ph);
+          ptx::tc_fence_after();
+          const uint32_t sa_hi = base + s * p.stage_bytes, sa_lo = sa_hi + p.a_plane;
+          const uint32_t sb_hi = sa_lo + p.a_plane, sb_lo = sb_hi + p.b_plane_bytes;
+          for (int k = 0; k < p.bk / 16; ++k) {
+            const uint64_t da_hi = ptx::make_smem_desc(sa_hi + k * 2048u, lbo, 1024);
+            const uint64_t da_lo = ptx::make_smem_desc(sa_lo + k * 2048u, lbo, 1024);
+            const uint64_t db_hi = ptx::make_smem_desc(sb_hi + k * 2048u, lbo, 1024);
+            const uint64_t db_lo = ptx::make_smem_desc(sb_lo + k * 2048u, lbo, 1024);
+            ptx::mma_bf16_ss_pair(tmem_base, da_hi, db_hi, idesc, first);
+            if (do_db) {
+              ptx::mma_bf16_ss_pair(tmem_base + 256, da_hi, d_ones, idesc_db, first);
+              ptx::mma_bf16_ss_pair(tmem_base + 256, da_lo, d_ones, idesc_db, 1);
+            }
+            first = 1;
+            ptx::mma_bf16_ss_pair(tmem_base, da_hi, db_lo, idesc, 1);
+            ptx::mma_bf16_ss_pair(tmem_base, da_lo, db_hi, idesc, 1);
+          }
+          ptx::mma_commit_pair(empty0 + 8 * s, (uint16_t)0x3);
+          if (++s == (uint32_t)p.num_stages) { s = 0; ph ^= 1; }
+        }
+        ptx::mma_commit_pair(tfull0, (uint16_t)0x3);
+      }
+    }
+  } else {
+    // -------------------------------------------------------------- epilogue warps (both CTAs, own 128 rows)
+    const int q = warp & 3;
+    const int chalf = (warp - 2) >> 2;
+    const int cw = p.bn >> 2;
+    const int cbeg = chalf * cw, cend = cbeg + cw;
+    int it = 0;
+    for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++it) {
+      const int z = tile / tiles_ab, rem = tile - z * tiles_ab;
+      const int ta = (rem / p.num_b) * 2 + (int)crank, tb = rem % p.num_b;
+      const int64_t row = (int64_t)ta * TC_BM + q * 32 + lane;
+      const int col0 = tb * p.bn;
+      const bool row_ok = row < p.rows_a;
+      ptx::mbar_wait(tfull0, (uint32_t)(it & 1));
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll
+      for (int ci = 0; ci < 2; ++ci) {
+        const int c = cbeg + 32 * ci;
+        if (c < cend) {
+          uint32_t r0[16], r1[16];
+          const bool two = c + 32 <= cend;
+          ptx::tmem_ld16(taddr + c, r0);
+          if (two) ptx::tmem_ld16(taddr + c + 16, r1);
+          ptx::tmem_ld_wait();
+          if (row_ok) {
+            if (col0 + c < p.cols_b) epilogue_chunk16<EPI_F32>(p, r0, row, col0 + c, z, nullptr, 0u);
+            if (two && col0 + c + 16 < p.cols_b) epilogue_chunk16<EPI_F32>(p, r1, row, col0 + c + 16, z, nullptr, 0u);
+          }
+        }
+      }
+      if (p.db != nullptr && tb == 0 && chalf == 0) {
+        uint32_t r0[16];
+        ptx::tmem_ld16(taddr + 256, r0);
+        ptx::tmem_ld_wait();
+        if (row_ok) p.db[(int64_t)z * p.rows_a + row] = __uint_as_float(r0[0]);
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) ptx::mbar_arrive(tempty0);
+        else ptx::mbar_arrive_cluster(ptx::mapa(tempty0, 0));
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc_pair(tmem_base, p.tmem_cols);
+  }
+}
+
 // ---------------------------------------------------------------------------- operand planes
 // fp32 [rows][cols] (row stride rs) -> bf16 hi/lo planes [rows][pitch]; transpose: out[c][r] = in[r][c].
 __global__ void split_planes_kernel(const float* __restrict__ src, int64_t rs, int64_t rows, int cols,
@@ -984,6 +1170,43 @@ static int launch_pair_kernel(const CUtensorMap& mAh, const CUtensorMap& mAl, co
   return GANTTS_OK;
 }
 
+static int launch_pair_mn_kernel(const CUtensorMap& mAh, const CUtensorMap& mAl, const CUtensorMap& mBh,
+                                 const CUtensorMap& mBl, const GemmParams& p, cudaStream_t st) {
+  const size_t smem = (size_t)p.num_stages * p.stage_bytes + 8192 + 1024 + 256;
+  static bool attr = false;
+  if (!attr) {
+    GANTTS_CUDA(cudaFuncSetAttribute(gemm_pair_mn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr = true;
+  }
+  const int units = ((p.num_a + 1) / 2) * p.num_b * p.num_z;
+  const int grid = units * 2 < num_sms() ? units * 2 : num_sms() / 2 * 2;
+  prof_begin(PROF_GEMM_MN, 2.0 * (double)p.rows_a * p.cols_b * (double)p.red, st);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  int na = 0;
+  at[na].id = cudaLaunchAttributeClusterDimension;
+  at[na].val.clusterDim.x = 2;
+  at[na].val.clusterDim.y = 1;
+  at[na].val.clusterDim.z = 1;
+  ++na;
+  if (use_pdl()) {
+    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = at;
+  cfg.numAttrs = na;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_pair_mn_kernel, mAh, mAl, mBh, mBl, p);
+  prof_end(st);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(gemm pair mn)");
+  GANTTS_LAUNCH_CHECK("gemm_pair_mn_kernel");
+  return GANTTS_OK;
+}
+
 static int use_cluster() {
   static int v = -1;
   if (v < 0) {
@@ -1077,9 +1300,16 @@ static int launch_gemm_kk(const Planes& A, const Planes& B, const EpiArgs& e, cu
 
 // C[n][k] (+)= sum_m A[m][n] * B[m][k]  (MN-major planes A [red][rows_a], B [red][cols_b]);
 // split over the reduction, partials in `partial`, reduced deterministically into C (ld = cols_b).
+// CTA pairs for the weight-gradient GEMM (gemm_pair_mn_kernel) need each half of the B tile to be whole
+// 64-wide atoms.  Measured on cfg2 (profiles/r01_gemm_experiments.md): correct but 4 % SLOWER than the
+// single-CTA kernel (200 vs 192 us for the four generator weight gradients) although it stages a third
+// fewer operand bytes per SM -- so it is opt-in (GANTTS_B200_CLUSTER=3), not the default.
+static bool mn_pair_ok(int cols_b) { return pick_bn(cols_b) % 128 == 0 && use_cluster() == 3; }
+
 static size_t mn_partial_bytes(int64_t red, int rows_a, int cols_b, int* splits_out, int64_t* chunk_out) {
   int bn = pick_bn(cols_b);
   int tiles = ((rows_a + TC_BM - 1) / TC_BM) * ((cols_b + bn - 1) / bn);
+  if (mn_pair_ok(cols_b)) tiles = 2 * ((((rows_a + TC_BM - 1) / TC_BM) + 1) / 2) * ((cols_b + bn - 1) / bn);
   const int bk = stage_bk(true);
   int64_t blocks = (red + bk - 1) / bk;
   int64_t splits = num_sms() / tiles;
@@ -1171,7 +1401,8 @@ static int launch_gemm_mn(const Planes& A, const Planes& B, float* C, float* gb,
   p.sbo = 1024;
   p.kstep = 2048;
   p.desc_layout = 2;
-  p.b_plane_bytes = (uint32_t)nb_atoms * p.atom_bytes;
+  const bool pair = mn_pair_ok(p.cols_b);
+  p.b_plane_bytes = (uint32_t)(pair ? nb_atoms / 2 : nb_atoms) * p.atom_bytes;
   p.stage_bytes = 2 * p.a_plane + 2 * p.b_plane_bytes;
   p.tx_bytes = p.stage_bytes;
   p.num_stages = (int)((212 * 1024) / p.stage_bytes);
@@ -1194,7 +1425,11 @@ static int launch_gemm_mn(const Planes& A, const Planes& B, float* C, float* gb,
   if ((rc = make_map(&mAl, A.lo, A.rows, A.cols, A.pitch, p.bk))) return rc;
   if ((rc = make_map(&mBh, B.hi, B.rows, B.cols, B.pitch, p.bk))) return rc;
   if ((rc = make_map(&mBl, B.lo, B.rows, B.cols, B.pitch, p.bk))) return rc;
-  if ((rc = launch_kernel<true, EPI_F32, 1>(mAh, mAl, mBh, mBl, p, st))) return rc;
+  if (pair) {
+    if ((rc = launch_pair_mn_kernel(mAh, mAl, mBh, mBl, p, st))) return rc;
+  } else if ((rc = launch_kernel<true, EPI_F32, 1>(mAh, mAl, mBh, mBl, p, st))) {
+    return rc;
+  }
   if (!direct) {
     if (defer && defer->n + 2 <= REDUCE_MAX_JOBS) {
       int j = defer->n++;

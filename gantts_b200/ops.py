@@ -175,6 +175,66 @@ def mlpg(x, windows, stream_entries, ncols_out):
     return out.squeeze(0) if squeeze else out
 
 
+def mlpg_var(mean, variance, windows):
+    """nnmnkwii.paramgen.mlpg on the device (reference evaluation_tts.py:70-72,92-94): mean (T, nw*sd) or
+    (B, T, nw*sd) CUDA float32, variance (nw*sd,) [time-invariant], (T, nw*sd) or (B, T, nw*sd);
+    returns the static trajectory (…, T, sd)."""
+    require_cuda(mean, variance)
+    lib = _lib.load()
+    squeeze = mean.dim() == 2
+    if squeeze:
+        mean = mean.unsqueeze(0)
+    B, T, D = mean.shape
+    nw = len(windows)
+    if D % nw:
+        raise RuntimeError("gantts_b200: feature width %d is not a multiple of the window count %d" % (D, nw))
+    sd = D // nw
+    if mean.stride(2) != 1:
+        mean = mean.contiguous()
+    variance = variance.contiguous()
+    if variance.shape[-1] != D:
+        raise RuntimeError("gantts_b200: variance width %d != mean width %d" % (variance.shape[-1], D))
+    if variance.dim() == 1:
+        v_bs, v_ts = 0, 0
+    elif variance.dim() == 2:
+        v_bs, v_ts = 0, variance.stride(0)
+    else:
+        v_bs, v_ts = variance.stride(0), variance.stride(1)
+    if variance.dim() >= 2 and variance.shape[-2] != T:
+        raise RuntimeError("gantts_b200: variance has %d frames, mean has %d" % (variance.shape[-2], T))
+    w = _lib.make_windows(windows)
+    out = torch.empty(B, T, sd, dtype=torch.float32, device=mean.device)
+    nbytes = lib.gantts_mlpg_var_workspace_bytes(ctypes.byref(w), B, T, sd)
+    ws = workspace(nbytes, mean.device, "mlpg_var")
+    _lib.check(lib.gantts_mlpg_var(mean.data_ptr(), mean.stride(0), mean.stride(1), variance.data_ptr(), v_bs, v_ts,
+                                   out.data_ptr(), out.stride(0), out.stride(1), ctypes.byref(w), B, T, sd,
+                                   ws.data_ptr(), ws.numel(), _stream()))
+    return out.squeeze(0) if squeeze else out
+
+
+def distortion_sums(y, y_hat, lengths, mean, std, mcd=(0, 0), bap=(0, 0), lf0_col=-1, vuv_col=-1,
+                    lf0_linear=True, mse=(0, 0)):
+    """Eight sums behind the objective metrics of reference train.py:399-432 (see include/gantts_b200.h,
+    gantts_distortions).  y, y_hat: (B, T, D) CUDA float32; lengths: int64 CUDA (B,); mean/std: (D,) CUDA.
+    Returns a CUDA float32 tensor of 8 values (no host synchronisation here)."""
+    require_cuda(y, y_hat, mean, std)
+    lib = _lib.load()
+    B, T, D = y.shape
+    if y.stride(2) != 1:
+        y = y.contiguous()
+    if y_hat.stride(2) != 1:
+        y_hat = y_hat.contiguous()
+    cols = _lib.DistortionColsT(int(mcd[0]), int(mcd[1]), int(bap[0]), int(bap[1]), int(lf0_col), int(vuv_col),
+                                1 if lf0_linear else 0, int(mse[0]), int(mse[1]))
+    out = torch.empty(8, dtype=torch.float32, device=y.device)
+    ws = workspace(lib.gantts_distortions_workspace_bytes(), y.device, "distortions")
+    _lib.check(lib.gantts_distortions(y.data_ptr(), y.stride(0), y.stride(1), y_hat.data_ptr(), y_hat.stride(0),
+                                      y_hat.stride(1), lengths.data_ptr(), B, T, D, mean.contiguous().data_ptr(),
+                                      std.contiguous().data_ptr(), ctypes.byref(cols), out.data_ptr(),
+                                      ws.data_ptr(), ws.numel(), _stream()))
+    return out
+
+
 def unit_variance_mlpg(R, means):
     """Drop-in for nnmnkwii.autograd.unit_variance_mlpg(R, means) (reference
     gantts/multistream.py:120, gantts/models.py:66,115): means (B, T, nw*sd) or (T, nw*sd)."""

@@ -322,6 +322,49 @@ int gantts_gan_step(const gantts_gan_step_t* cfg, int phases, const float* x, co
                     float* y_hat_static, float* losses_dev, void* workspace, size_t workspace_bytes,
                     void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Inference-time MLPG with real variances (replaces nnmnkwii.paramgen.mlpg as called by reference
+ * evaluation_tts.py:70-72,92-94):  solves, per static dimension d and batch row b,
+ *   (sum_w W_w^T diag(1/var_w) W_w) y = sum_w W_w^T diag(1/var_w) mean_w
+ * by banded Cholesky in float64.  mean/var: float32 [B][T][nw*sd], window-major feature blocks
+ * ([static sd, delta sd, delta-delta sd]), element strides (bstride, tstride); a time-invariant variance
+ * vector (the reference's use) is passed with v_tstride = 0 (and v_bstride = 0).  out: float32 [B][T][sd].
+ */
+size_t gantts_mlpg_var_workspace_bytes(const gantts_windows_t* windows, int B, int T, int sd);
+int gantts_mlpg_var(const float* mean, int64_t m_bstride, int64_t m_tstride, const float* var,
+                    int64_t v_bstride, int64_t v_tstride, float* out, int64_t o_bstride, int64_t o_tstride,
+                    const gantts_windows_t* windows, int B, int T, int sd, void* workspace,
+                    size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Objective distortions of the training loop (reference train.py:399-432 compute_distortions, :383-396
+ * split_streams, :358-380 inv_scale; nnmnkwii.metrics.{melcd, lf0_mean_squared_error, vuv_error,
+ * mean_squared_error}).  y, y_hat: float32 [B][T][D] static-domain features (normalised); mean_dev /
+ * std_dev: float32[D] de-normalisation per static column (the caller maps the reference's
+ * static+dynamic-domain indices).  Column groups (count 0 / col -1 disables a term):
+ *   mcd  : [mcd_start, +mcd_count)   sum over valid frames of ||delta||_2   (reference passes mgc[:, :, 1:])
+ *   bap  : [bap_start, +bap_count)   the same for band aperiodicity
+ *   lf0_col, vuv_col: F0 squared error (after exp when lf0_linear) over frames voiced in both; V/UV is
+ *          binarised at 0.5 after de-normalisation (train.py:374-377)
+ *   mse  : [mse_start, +mse_count)   plain squared error sum (duration model / VC)
+ * out8_dev: { sum ||d mcd||, sum ||d bap||, sum f0 err^2, #frames voiced in both, #V/UV mismatches,
+ *             #valid frames, sum sq err of the mse group, 0 }.  One device-to-host read of 32 bytes
+ * gives every metric: mcd = 10/ln10*sqrt(2) * out[0]/out[5], f0_rmse = sqrt(out[2]/out[3]), ...
+ */
+typedef struct {
+  int mcd_start, mcd_count;
+  int bap_start, bap_count;
+  int lf0_col, vuv_col;
+  int lf0_linear;
+  int mse_start, mse_count;
+} gantts_distortion_cols_t;
+
+size_t gantts_distortions_workspace_bytes(void);
+int gantts_distortions(const float* y, int64_t y_bstride, int64_t y_tstride, const float* y_hat,
+                       int64_t yh_bstride, int64_t yh_tstride, const int64_t* lengths_dev, int B, int T, int D,
+                       const float* mean_dev, const float* std_dev, const gantts_distortion_cols_t* cols,
+                       float* out8_dev, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -146,3 +146,31 @@ def mlpg_solve_f64(windows, means):
             rhs += W.T @ means[b, :, w * sd:(w + 1) * sd]
         out[b] = cho_solve_banded((c, True), rhs)
     return out
+
+
+def mlpg(mean_frames, variance_frames, windows):
+    """``nnmnkwii.paramgen.mlpg(mean_frames, variance_frames, windows)`` restated (reference call sites
+    evaluation_tts.py:70-72,92-94; the package is not vendored -> parity unpinned, but the unit-variance
+    case must equal ``unit_variance_mlpg_matrix(windows, T) @ means``, which IS pinned by the goldens).
+
+    mean_frames ``(T, nw*sd)``; variance_frames ``(nw*sd,)`` or ``(T, nw*sd)``.  Dense float64 solve of
+    ``(sum_w W_w^T diag(1/var_w) W_w) y = sum_w W_w^T diag(1/var_w) mu_w`` per static dimension.
+    """
+    mu = np.asarray(mean_frames, dtype=np.float64)
+    T, D = mu.shape
+    nw = len(windows)
+    sd = D // nw
+    var = np.asarray(variance_frames, dtype=np.float64)
+    if var.ndim == 1:
+        var = np.tile(var, (T, 1))
+    mats = window_matrices(windows, T)
+    out = np.empty((T, sd))
+    for d in range(sd):
+        P = np.zeros((T, T))
+        b = np.zeros(T)
+        for w, W in enumerate(mats):
+            tau = 1.0 / var[:, w * sd + d]
+            P += W.T @ (tau[:, None] * W)
+            b += W.T @ (tau * mu[:, w * sd + d])
+        out[:, d] = np.linalg.solve(P, b)
+    return out

@@ -154,3 +154,17 @@ def test_gan_step_two_iterations(golden_step, tag, cond):
         for (W, b), n in zip(state.d, names):
             assert rel_err(W.detach().numpy(), g[p + "d_" + n + ".weight"]) < 1e-5
             assert rel_err(b.detach().numpy(), g[p + "d_" + n + ".bias"]) < 1e-5
+
+
+def test_variance_mlpg_restatement_reduces_to_R():
+    """oracle mlpg (evaluation-time, real variances) with unit variance == the pinned R-matrix product."""
+    rng = np.random.RandomState(2)
+    T, sd = 37, 3
+    mu = rng.randn(T, 3 * sd)
+    R = nnp.unit_variance_mlpg_matrix(WINDOWS, T).astype(np.float64)
+    wm = np.concatenate([mu[:, w * sd:(w + 1) * sd] for w in range(3)], axis=0)
+    np.testing.assert_allclose(nnp.mlpg(mu, np.ones(3 * sd), WINDOWS), R @ wm, rtol=0, atol=1e-6)
+    # a per-dimension rescaling of all windows of one dimension leaves its trajectory unchanged
+    v = np.ones(3 * sd)
+    v[[0, sd, 2 * sd]] = 7.0
+    np.testing.assert_allclose(nnp.mlpg(mu, v, WINDOWS), nnp.mlpg(mu, np.ones(3 * sd), WINDOWS), atol=1e-9)
