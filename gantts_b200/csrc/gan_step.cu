@@ -200,11 +200,12 @@ static int check_step(const gantts_gan_step_t* c) {
   GANTTS_CHECK_ARG(c->n_static_cols == c->n_static, "gan_step: static column list must have n_static entries");
   if (c->w_d > 0.f) {
     GANTTS_CHECK_ARG(c->d.num_layers >= 1 && c->d.num_layers <= GANTTS_MAX_LAYERS, "gan_step: bad discriminator");
-    GANTTS_CHECK_ARG(c->n_adv >= 1 && c->n_adv <= GANTTS_MAX_COLS && c->d.dims[0] == c->n_adv,
-                     "gan_step: discriminator input width %d != adversarial columns %d", c->d.dims[0], c->n_adv);
+    const int cond_w = c->d_conditioned ? c->g.dims[0] : 0;
+    GANTTS_CHECK_ARG(c->n_adv >= 1 && c->n_adv <= GANTTS_MAX_COLS && c->d.dims[0] == cond_w + c->n_adv,
+                     "gan_step: discriminator input width %d != %d conditioning + %d adversarial columns",
+                     c->d.dims[0], cond_w, c->n_adv);
     GANTTS_CHECK_ARG(c->d.dims[c->d.num_layers] == 1 && c->d.last_act == GANTTS_ACT_SIGMOID,
                      "gan_step: discriminator must end in a single sigmoid output");
-    GANTTS_CHECK_ARG(!c->d_conditioned, "gan_step: linguistic conditioning of D is not supported by the fused step");
   }
   GANTTS_CHECK_ARG(c->g.last_act == GANTTS_ACT_NONE, "gan_step: generator must have a linear output");
   GANTTS_CHECK_ARG(c->mlpg_table, "gan_step: null MLPG table");
@@ -254,6 +255,10 @@ extern "C" int gantts_gan_step(const gantts_gan_step_t* c, int phases, const flo
   const int dD = c->d.dims[0], nS = c->n_static;
   const bool has_d = c->w_d > 0.f;
   const bool has_adv = has_d && c->adv_w > 0.f;
+  // discriminator_linguistic_condition (train.py:254-256,302-303): D sees cat((x, y_adv), -1); the first
+  // cond_w columns of both halves of d_in are copies of x, the gradient w.r.t. them is discarded.
+  const int cond_w = (has_d && c->d_conditioned) ? d_in : 0;
+  const int nA = dD - cond_w;
   ParamList pg, pd;
   param_list(c->g, c->g_sumW, c->g_sumb, L.g_grads, &pg);
   if (has_d) param_list(c->d, c->d_sumW, c->d_sumb, L.d_grads, &pd);
@@ -280,11 +285,18 @@ extern "C" int gantts_gan_step(const gantts_gan_step_t* c, int phases, const flo
       return rc;
     if (has_d) {
       // ---- update_discriminator (train.py:245-279): stacked real | fake batch of 2M rows
-      gather_cols_list_kernel<<<blocks_1d(M * dD, 1024), 256, 0, st>>>(L.y_static, nS, L.d_in, dD, adv_cols, M);
+      gather_cols_list_kernel<<<blocks_1d(M * nA, 1024), 256, 0, st>>>(L.y_static, nS, L.d_in + cond_w, dD, adv_cols,
+                                                                       M);
       GANTTS_LAUNCH_CHECK("gather_cols_list_kernel(real)");
-      gather_cols_list_kernel<<<blocks_1d(M * dD, 1024), 256, 0, st>>>(y_hat_static, nS, L.d_in + M * dD, dD,
+      gather_cols_list_kernel<<<blocks_1d(M * nA, 1024), 256, 0, st>>>(y_hat_static, nS, L.d_in + M * dD + cond_w, dD,
                                                                        adv_cols, M);
       GANTTS_LAUNCH_CHECK("gather_cols_list_kernel(fake)");
+      if (cond_w) {
+        GANTTS_CUDA(cudaMemcpy2DAsync(L.d_in, (size_t)dD * sizeof(float), x, (size_t)d_in * sizeof(float),
+                                      (size_t)cond_w * sizeof(float), (size_t)M, cudaMemcpyDeviceToDevice, st));
+        GANTTS_CUDA(cudaMemcpy2DAsync(L.d_in + M * dD, (size_t)dD * sizeof(float), x, (size_t)d_in * sizeof(float),
+                                      (size_t)cond_w * sizeof(float), (size_t)M, cudaMemcpyDeviceToDevice, st));
+      }
       d.seed = seed * 4 + 1;
       if ((rc = gantts_mlp_fwd(&d, L.d_in, dD, 2 * M, L.d_out, 1, L.d_tape, L.d_tape_bytes, stream))) return rc;
       if ((rc = gantts_masked_bce_fwd(L.d_out, L.mask, M, 0, L.scal + S_REAL, L.red_ws, L.red_ws_bytes, stream))) return rc;
@@ -295,8 +307,8 @@ extern "C" int gantts_gan_step(const gantts_gan_step_t* c, int phases, const flo
       if ((rc = gantts_mlp_bwd(&d, L.g_dout, 1, L.d_out, 1, 2 * M, L.d_tape, L.d_tape_bytes, L.g_din, dD, pd.gW,
                                pd.gb, 0, L.mlp_ws, L.mlp_ws_bytes, stream)))
         return rc;
-      scatter_cols_list_add_kernel<<<blocks_1d(M * dD, 1024), 256, 0, st>>>(L.g_din + M * dD, dD, L.g_static, nS,
-                                                                            adv_cols, M);
+      scatter_cols_list_add_kernel<<<blocks_1d(M * nA, 1024), 256, 0, st>>>(L.g_din + M * dD + cond_w, dD, L.g_static,
+                                                                            nS, adv_cols, M);
       GANTTS_LAUNCH_CHECK("scatter_cols_list_add_kernel(fake)");
     }
   }
@@ -324,7 +336,8 @@ extern "C" int gantts_gan_step(const gantts_gan_step_t* c, int phases, const flo
       if ((rc = gantts_mlp_bwd(&d, L.g_dout, 1, L.d_out, 1, M, L.d_tape, L.d_tape_bytes, L.g_din, dD, nullptr,
                                nullptr, 0, L.mlp_ws, L.mlp_ws_bytes, stream)))
         return rc;
-      scatter_cols_list_add_kernel<<<blocks_1d(M * dD, 1024), 256, 0, st>>>(L.g_din, dD, L.g_static, nS, adv_cols, M);
+      scatter_cols_list_add_kernel<<<blocks_1d(M * nA, 1024), 256, 0, st>>>(L.g_din + cond_w, dD, L.g_static, nS,
+                                                                            adv_cols, M);
       GANTTS_LAUNCH_CHECK("scatter_cols_list_add_kernel(adv)");
     }
     if (c->mge_w != 0.f) {

@@ -240,6 +240,236 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_bwd_kernel(const LstmPar
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Register-resident variants (HS = 8, H <= 512).  The shared-memory kernels above re-read the CTA's W_hh
+// slice from shared memory once per thread group and step (8 x 64 KB per step: ~2 us of shared-memory
+// bandwidth).  Here every thread keeps its 64 weights in REGISTERS for the whole sequence:
+//   forward : thread (r = tid % 32, kq = tid / 32) owns W_hh[row r][kq*KR .. +KR); per step it forms the
+//             partial dot products of all 16 batch rows of the chunk (h_{t-1} from shared memory, one
+//             broadcast LDS.128 per 4 FMAs), the 8 k-ranges are summed in the gate stage;
+//   backward: thread owns rows {tid + 256 i} of W_hh[:, u0 .. u0+8); per step it accumulates
+//             dh_prev[b][k] partials for 8 batch rows x 8 units in registers (scalar conflict-free LDS of
+//             the staged gate gradients, 8 FMAs per load), a butterfly reduction over the warp (62
+//             shuffles for 64 values) and an 8-way shared-memory sum finish it.
+// Both are FMA-bound at ~1 us per step and chunk instead of shared-memory-bound at 2-4 us.
+template <int KR>
+__global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_fwd_reg_kernel(const LstmParams p) {
+  constexpr int HS = 8, R = 32, NKQ = LSTM_THREADS / R;     // 8 k-ranges
+  extern __shared__ __align__(16) float sm[];
+  const int H = p.H;
+  const int HPAD = NKQ * KR;                                // >= H, zero padded
+  float* hs = sm;                                           // [LSTM_BC][HPAD]
+  float* part = hs + LSTM_BC * HPAD;                        // [NKQ][LSTM_BC][R]
+  float* cst = part + NKQ * LSTM_BC * R;                    // [LSTM_MAX_B][HS]
+  const int dir = blockIdx.x / p.slices, sl = blockIdx.x % p.slices, u0 = sl * HS;
+  const int tid = threadIdx.x;
+  const int ldx = p.ndir * 4 * H, ldh = p.ndir * H;
+  const float* Wd = p.W_hh + (int64_t)dir * 4 * H * H;
+  const int r = tid % R, kq = tid / R;
+  float w[KR];
+  {
+    const int g = r / HS, u = r - g * HS;
+    const bool row_ok = u0 + u < H;
+    const float* wr = Wd + (int64_t)(g * H + u0 + u) * H;
+#pragma unroll
+    for (int j = 0; j < KR; ++j) {
+      const int k = kq * KR + j;
+      w[j] = (row_ok && k < H) ? wr[k] : 0.f;
+    }
+  }
+  for (int i = tid; i < LSTM_MAX_B * HS; i += LSTM_THREADS) cst[i] = 0.f;
+  for (int i = tid; i < LSTM_BC * HPAD; i += LSTM_THREADS) hs[i] = 0.f;
+  __syncthreads();
+  unsigned int gen = 0;
+  unsigned int* bar = p.bar + 2 * dir;
+  float* gates_d = p.gates + (int64_t)dir * p.B * p.T * 4 * H;
+  float* cells_d = p.cells + (int64_t)dir * p.B * p.T * H;
+
+  for (int step = 0; step < p.T; ++step) {
+    const int t = dir == 0 ? step : p.T - 1 - step;
+    const int tprev = dir == 0 ? t - 1 : t + 1;
+    for (int cb = 0; cb < p.B; cb += LSTM_BC) {
+      for (int i = tid; i < LSTM_BC * (H / 4); i += LSTM_THREADS) {
+        const int bb = i / (H / 4), k4 = i - bb * (H / 4), b = cb + bb;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (step > 0 && b < p.B)
+          v = __ldcg(reinterpret_cast<const float4*>(p.h_out + ((int64_t)b * p.T + tprev) * ldh + dir * H + 4 * k4));
+        *reinterpret_cast<float4*>(hs + bb * HPAD + 4 * k4) = v;
+      }
+      __syncthreads();
+      float xq[4] = {0.f, 0.f, 0.f, 0.f};
+      if (tid < LSTM_BC * HS) {
+        const int bb = tid / HS, u = tid - bb * HS, b = cb + bb;
+        if (b < p.B && u0 + u < H && (int64_t)t < p.lengths[b]) {
+          const float* xp = p.xproj + ((int64_t)b * p.T + t) * ldx + dir * 4 * H + u0 + u;
+          xq[0] = xp[0]; xq[1] = xp[H]; xq[2] = xp[2 * H]; xq[3] = xp[3 * H];
+        }
+      }
+      float acc[LSTM_BC];
+#pragma unroll
+      for (int b = 0; b < LSTM_BC; ++b) acc[b] = 0.f;
+      const float* hk = hs + kq * KR;
+#pragma unroll
+      for (int j4 = 0; j4 < KR / 4; ++j4) {
+#pragma unroll
+        for (int b = 0; b < LSTM_BC; ++b) {
+          const float4 h = *reinterpret_cast<const float4*>(hk + b * HPAD + 4 * j4);
+          acc[b] = fmaf(w[4 * j4], h.x, fmaf(w[4 * j4 + 1], h.y, fmaf(w[4 * j4 + 2], h.z, fmaf(w[4 * j4 + 3], h.w, acc[b]))));
+        }
+      }
+#pragma unroll
+      for (int b = 0; b < LSTM_BC; ++b) part[(kq * LSTM_BC + b) * R + r] = acc[b];
+      __syncthreads();
+      if (tid < LSTM_BC * HS) {
+        const int bb = tid / HS, u = tid - bb * HS, b = cb + bb;
+        if (b < p.B && u0 + u < H) {
+          const bool valid = (int64_t)t < p.lengths[b];
+          const int64_t row = (int64_t)b * p.T + t;
+          float hval = 0.f;
+          if (valid) {
+            float pre[4] = {xq[0], xq[1], xq[2], xq[3]};
+#pragma unroll
+            for (int q = 0; q < NKQ; ++q) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) pre[g] += part[(q * LSTM_BC + bb) * R + g * HS + u];
+            }
+            const float gi = sigmoidf_(pre[0]);
+            const float gf = sigmoidf_(pre[1]);
+            const float gg = tanhf(pre[2]);
+            const float go = sigmoidf_(pre[3]);
+            const float c = gf * cst[b * HS + u] + gi * gg;
+            cst[b * HS + u] = c;
+            hval = go * tanhf(c);
+            float* gp = gates_d + row * 4 * H + u0 + u;
+            gp[0] = gi; gp[H] = gf; gp[2 * H] = gg; gp[3 * H] = go;
+            cells_d[row * H + u0 + u] = c;
+          }
+          p.h_out[row * ldh + dir * H + u0 + u] = hval;
+        }
+      }
+      __syncthreads();
+    }
+    if (step + 1 < p.T) dir_barrier(bar, p.slices, gen);
+  }
+}
+
+// Sum v[0..63] over the 32 lanes of a warp; afterwards lane L holds the totals of indices
+// idx(L) + {0, 1} with idx(L) = 32*b4 + 16*b3 + 8*b2 + 4*b1 + 2*b0 (bN = bit N of L) in v[0], v[1].
+__device__ __forceinline__ void warp_reduce64(float (&v)[64], int lane) {
+#pragma unroll
+  for (int half = 32, bit = 16; half >= 2; half >>= 1, bit >>= 1) {
+    const bool upper = (lane & bit) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float send = upper ? v[i] : v[i + half];
+      const float keep = upper ? v[i + half] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+    }
+  }
+}
+
+template <int RPT>
+__global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_bwd_reg_kernel(const LstmParams p) {
+  constexpr int HS = 8, HB = 8;                       // hidden units per CTA, batch rows per register pass
+  extern __shared__ __align__(16) float sm[];
+  const int H = p.H, G4 = 4 * H;
+  const int GPAD = RPT * LSTM_THREADS;                // >= 4H, zero padded
+  float* dgs = sm;                                    // [LSTM_BC][GPAD]
+  float* red = dgs + LSTM_BC * GPAD;                  // [8 warps][64]
+  float* dhr = red + 8 * 64;                          // [LSTM_MAX_B][HS]
+  float* dcs = dhr + LSTM_MAX_B * HS;                 // [LSTM_MAX_B][HS]
+  const int dir = blockIdx.x / p.slices, sl = blockIdx.x % p.slices, u0 = sl * HS;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ldx = p.ndir * 4 * H, ldh = p.ndir * H;
+  const float* Wd = p.W_hh + (int64_t)dir * 4 * H * H;
+  float w[RPT][HS];
+#pragma unroll
+  for (int i = 0; i < RPT; ++i) {
+    const int row = i * LSTM_THREADS + tid;
+#pragma unroll
+    for (int k = 0; k < HS; ++k) w[i][k] = (row < G4 && u0 + k < H) ? Wd[(int64_t)row * H + u0 + k] : 0.f;
+  }
+  for (int i = tid; i < LSTM_MAX_B * HS; i += LSTM_THREADS) { dhr[i] = 0.f; dcs[i] = 0.f; }
+  for (int i = tid; i < LSTM_BC * GPAD; i += LSTM_THREADS) dgs[i] = 0.f;
+  __syncthreads();
+  unsigned int gen = 0;
+  unsigned int* bar = p.bar + 2 * dir;
+  const float* gates_d = p.gates + (int64_t)dir * p.B * p.T * 4 * H;
+  const float* cells_d = p.cells + (int64_t)dir * p.B * p.T * H;
+
+  for (int step = 0; step < p.T; ++step) {
+    const int t = dir == 0 ? p.T - 1 - step : step;
+    const int tprev = dir == 0 ? t - 1 : t + 1;
+    // phase A: gate gradients of the own hidden units (as in lstm_bwd_kernel)
+    for (int i = tid; i < p.B * HS; i += LSTM_THREADS) {
+      const int b = i / HS, u = i - b * HS;
+      if (u0 + u >= H) continue;
+      const int64_t len = p.lengths[b];
+      const int64_t row = (int64_t)b * p.T + t;
+      float* dxp = p.dxproj + row * ldx + dir * 4 * H + u0 + u;
+      float di = 0.f, df = 0.f, dg = 0.f, d_og = 0.f;
+      if ((int64_t)t < len) {
+        const float* gp = gates_d + row * 4 * H + u0 + u;
+        const float gi = gp[0], gf = gp[H], gg = gp[2 * H], go = gp[3 * H];
+        const float c = cells_d[row * H + u0 + u];
+        const bool first = dir == 0 ? (t == 0) : ((int64_t)t == len - 1);
+        const float cprev = first ? 0.f : cells_d[((int64_t)b * p.T + tprev) * H + u0 + u];
+        const float dh = p.dh_out[row * ldh + dir * H + u0 + u] + dhr[i];
+        const float tc = tanhf(c);
+        const float dct = dcs[i] + dh * go * (1.f - tc * tc);
+        d_og = dh * tc * go * (1.f - go);
+        di = dct * gg * gi * (1.f - gi);
+        dg = dct * gi * (1.f - gg * gg);
+        df = dct * cprev * gf * (1.f - gf);
+        dcs[i] = dct * gf;
+      }
+      dxp[0] = di; dxp[H] = df; dxp[2 * H] = dg; dxp[3 * H] = d_og;
+    }
+    if (step + 1 == p.T) break;
+    dir_barrier(bar, p.slices, gen);
+    // phase B: dh_prev[b][own units] = sum_row dgates_t[b][row] * W_hh[row][unit]
+    for (int cb = 0; cb < p.B; cb += LSTM_BC) {
+      for (int i = tid; i < LSTM_BC * (G4 / 4); i += LSTM_THREADS) {
+        const int bb = i / (G4 / 4), r4 = i - bb * (G4 / 4), b = cb + bb;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (b < p.B)
+          v = __ldcg(reinterpret_cast<const float4*>(p.dxproj + ((int64_t)b * p.T + t) * ldx + dir * 4 * H + 4 * r4));
+        *reinterpret_cast<float4*>(dgs + bb * GPAD + 4 * r4) = v;
+      }
+      __syncthreads();
+#pragma unroll 1
+      for (int hb = 0; hb < LSTM_BC; hb += HB) {
+        float acc[64];
+#pragma unroll
+        for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+#pragma unroll
+          for (int b = 0; b < HB; ++b) {
+            const float d = dgs[(hb + b) * GPAD + i * LSTM_THREADS + tid];
+#pragma unroll
+            for (int k = 0; k < HS; ++k) acc[b * HS + k] = fmaf(d, w[i][k], acc[b * HS + k]);
+          }
+        }
+        warp_reduce64(acc, lane);
+        const int idx = ((lane & 16) ? 32 : 0) + ((lane & 8) ? 16 : 0) + ((lane & 4) ? 8 : 0) + ((lane & 2) ? 4 : 0) +
+                        ((lane & 1) ? 2 : 0);
+        red[warp * 64 + idx] = acc[0];
+        red[warp * 64 + idx + 1] = acc[1];
+        __syncthreads();
+        if (tid < 64) {
+          float s = 0.f;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) s += red[q * 64 + tid];
+          const int b = cb + hb + tid / HS;
+          if (b < p.B) dhr[b * HS + (tid % HS)] = s;
+        }
+        __syncthreads();
+      }
+    }
+  }
+}
+
 // hprev[b][t][:] = h[b][t -/+ 1][dir*H : (dir+1)*H] (forward-order predecessor), 0 at the first step and
 // beyond the length: the operand of dW_hh = dgates^T h_prev.
 __global__ void lstm_hprev_kernel(const float* __restrict__ h, const int64_t* __restrict__ lengths,
@@ -317,6 +547,39 @@ static int lstm_launch(bool bwd, LstmParams& p, cudaStream_t st) {
   return GANTTS_OK;
 }
 
+static int lstm_use_reg() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GANTTS_B200_LSTM_REG");
+    v = e ? atoi(e) : 1;
+  }
+  return v;
+}
+
+// Register-resident kernels: HS = 8 and H <= 512 (64 weights per thread).
+static int lstm_launch_reg(bool bwd, LstmParams& p, cudaStream_t st) {
+  const int H = p.H;
+  void* fn;
+  size_t smem;
+  if (!bwd) {
+    const int KR = H <= 256 ? 32 : 64;
+    fn = KR == 32 ? (void*)lstm_fwd_reg_kernel<32> : (void*)lstm_fwd_reg_kernel<64>;
+    smem = ((size_t)LSTM_BC * 8 * KR + 8 * LSTM_BC * 32 + LSTM_MAX_B * 8) * sizeof(float);
+  } else {
+    const int RPT = 4 * H <= 4 * LSTM_THREADS ? 4 : 8;
+    fn = RPT == 4 ? (void*)lstm_bwd_reg_kernel<4> : (void*)lstm_bwd_reg_kernel<8>;
+    smem = ((size_t)LSTM_BC * RPT * LSTM_THREADS + 8 * 64 + 2 * LSTM_MAX_B * 8) * sizeof(float);
+  }
+  GANTTS_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  GANTTS_CUDA(cudaMemsetAsync(p.bar, 0, 4 * sizeof(unsigned int), st));
+  void* args[] = {&p};
+  dim3 grid(p.slices * p.ndir), block(LSTM_THREADS);
+  cudaError_t e = cudaLaunchCooperativeKernel(fn, grid, block, args, smem, st);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchCooperativeKernel(lstm reg)");
+  count_launch();
+  return GANTTS_OK;
+}
+
 }  // namespace gantts
 
 using namespace gantts;
@@ -335,6 +598,7 @@ extern "C" int gantts_lstm_layer_fwd(const float* xproj, const float* W_hh, cons
   p.bar = static_cast<unsigned int*>(workspace);
   p.B = B; p.T = T; p.H = H; p.ndir = ndir;
   const int hs = lstm_pick_hs(H, ndir, &p.slices);
+  if (hs == 8 && H <= 512 && lstm_use_reg()) return lstm_launch_reg(false, p, as_stream(stream));
   if (hs == 8) return lstm_launch<8>(false, p, as_stream(stream));
   if (hs == 16) return lstm_launch<16>(false, p, as_stream(stream));
   set_error("lstm: hidden size %d x %d directions does not fit one wave of CTAs", H, ndir);
@@ -354,6 +618,7 @@ extern "C" int gantts_lstm_layer_bwd(const float* dh_out, const float* W_hh, con
   p.bar = static_cast<unsigned int*>(workspace);
   p.B = B; p.T = T; p.H = H; p.ndir = ndir;
   const int hs = lstm_pick_hs(H, ndir, &p.slices);
+  if (hs == 8 && H <= 512 && lstm_use_reg()) return lstm_launch_reg(true, p, as_stream(stream));
   if (hs == 8) return lstm_launch<8>(true, p, as_stream(stream));
   if (hs == 16) return lstm_launch<16>(true, p, as_stream(stream));
   set_error("lstm: hidden size %d x %d directions does not fit one wave of CTAs", H, ndir);

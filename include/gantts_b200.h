@@ -308,7 +308,8 @@ typedef struct {
   int static_cols[GANTTS_MAX_COLS];        /* columns of y forming y_static (get_static_features) */
   int n_adv;
   int adv_cols[GANTTS_MAX_COLS];           /* columns of y_(hat_)static fed to D (select + mask_nth) */
-  int d_conditioned;                       /* must be 0 (linguistic conditioning: use the modular path) */
+  int d_conditioned;                       /* hp.discriminator_linguistic_condition (train.py:254-256): D input =
+                                              cat((x, y_adv), -1), d.dims[0] = g.dims[0] + n_adv */
   float lr_g, lr_d, wd_g, wd_d, eps, max_norm;
   float w_d, mse_w, mge_w, adv_w;
 } gantts_gan_step_t;

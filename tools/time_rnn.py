@@ -23,7 +23,11 @@ def run(name, model, B, T, I, n=3):
         y.backward(g)
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / n
-    print("%-46s B=%d T=%d: fwd+bwd %.1f ms -> %.3g frames/s" % (name, B, T, dt * 1e3, B * T / dt), flush=True)
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    e[0].record(); y = model(x, lens); e[1].record(); y.backward(g); e[2].record()
+    torch.cuda.synchronize()
+    print("%-46s B=%d T=%d: fwd+bwd %.1f ms (fwd %.1f, bwd %.1f) -> %.3g frames/s" % (
+        name, B, T, dt * 1e3, e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2]), B * T / dt), flush=True)
 
 
 run("LSTMRNN 177-(3x512 bi)-177 [cfg3 width]", gantts_b200.models.LSTMRNN(177, 177, 3, 512, bidirectional=True), 16, 2000, 177)
