@@ -215,7 +215,7 @@ def run_reference_arm(args):
             "config": workload_config(w, "cpu"), "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit_json_line(line)
 
 
 def workload_config(w, engine):
@@ -227,12 +227,35 @@ def workload_config(w, engine):
             "parallelism": "utterance-sharded data parallel, one NCCL SUM all-reduce per model per step"}
 
 
+_REAL_STDOUT_FD = None
+
+
+def redirect_stdout_to_stderr():
+    global _REAL_STDOUT_FD
+    if _REAL_STDOUT_FD is None:
+        sys.stdout.flush()
+        _REAL_STDOUT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_json_line(line):
+    text = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT_FD is None:
+        os.write(1, text)
+    else:
+        os.write(_REAL_STDOUT_FD, text)
+
+
 # ------------------------------------------------------------------------------------ B200 arm
 def run_b200_arm(args):
     import __graft_entry__
     from gantts_b200 import parallel
-    # stdout carries exactly ONE JSON line: NCCL's banner / debug output goes to stderr
+    # stdout carries exactly ONE JSON line.  NCCL prints its version banner with a bare printf on fd 1 during
+    # the first communicator init (NCCL_DEBUG_FILE does not catch it), so fd 1 points at stderr for the whole
+    # run and the JSON line is written to the saved descriptor (emit_json_line).
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    redirect_stdout_to_stderr()
     rank, world, local = parallel.init_from_env()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the B200 arm has no CPU fallback")
@@ -411,7 +434,7 @@ def run_b200_arm(args):
             "path": "gantts_gan_step (one C call per mini-batch)" if args.path == "fused" else "GanTrainer (python-orchestrated native ops)"}
     if cb is not None:
         line["cpu_baseline"] = cb
-    print(json.dumps(line), flush=True)
+    emit_json_line(line)
 
 
 def main():

@@ -11,6 +11,6 @@ timeout 600 python bench.py --steps 50 --warmup 10 > gpurun_out/bench_${TAG}.jso
 kill $SMI
 tail -c 400 gpurun_out/bench_${TAG}.err
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_${TAG}_reference.json 2>> gpurun_out/bench_${TAG}.err
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 700 -c 100 --csv --log-file gpurun_out/launches_${TAG}.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench_${TAG}.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 690 -c 140 --csv --log-file gpurun_out/launches_${TAG}.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench_${TAG}.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16x3 -s 46 -c 31 -o gpurun_out/prof_gemm_${TAG} python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_${TAG}.log 2>&1
 ls -la gpurun_out | tail -8
