@@ -255,9 +255,10 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_bwd_kernel(const LstmPar
 template <int KR>
 __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_fwd_reg_kernel(const LstmParams p) {
   constexpr int HS = 8, R = 32, NKQ = LSTM_THREADS / R;     // 8 k-ranges
+  constexpr int HPAD = NKQ * KR;                            // >= H, zero padded
+  constexpr int NQ = LSTM_BC * (HPAD / 4) / LSTM_THREADS;   // float4 loads of h_{t-1} per thread and chunk
   extern __shared__ __align__(16) float sm[];
   const int H = p.H;
-  const int HPAD = NKQ * KR;                                // >= H, zero padded
   float* hs = sm;                                           // [LSTM_BC][HPAD]
   float* part = hs + LSTM_BC * HPAD;                        // [NKQ][LSTM_BC][R]
   float* cst = part + NKQ * LSTM_BC * R;                    // [LSTM_MAX_B][HS]
@@ -279,6 +280,13 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_fwd_reg_kernel(const Lst
   }
   for (int i = tid; i < LSTM_MAX_B * HS; i += LSTM_THREADS) cst[i] = 0.f;
   for (int i = tid; i < LSTM_BC * HPAD; i += LSTM_THREADS) hs[i] = 0.f;
+  int sofs[NQ];                                             // smem offset bb * HPAD + 4 * k4, -1 if unused
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    const int i = tid + q * LSTM_THREADS;
+    const int bb = i / (H / 4), k4 = i - bb * (H / 4);
+    sofs[q] = bb < LSTM_BC ? bb * HPAD + 4 * k4 : -1;
+  }
   __syncthreads();
   unsigned int gen = 0;
   unsigned int* bar = p.bar + 2 * dir;
@@ -289,13 +297,23 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_fwd_reg_kernel(const Lst
     const int t = dir == 0 ? step : p.T - 1 - step;
     const int tprev = dir == 0 ? t - 1 : t + 1;
     for (int cb = 0; cb < p.B; cb += LSTM_BC) {
-      for (int i = tid; i < LSTM_BC * (H / 4); i += LSTM_THREADS) {
-        const int bb = i / (H / 4), k4 = i - bb * (H / 4), b = cb + bb;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (step > 0 && b < p.B)
-          v = __ldcg(reinterpret_cast<const float4*>(p.h_out + ((int64_t)b * p.T + tprev) * ldh + dir * H + 4 * k4));
-        *reinterpret_cast<float4*>(hs + bb * HPAD + 4 * k4) = v;
+      // all of this thread's h_{t-1} loads are issued before the first store (a load->store loop compiles
+      // to one L2 round trip per iteration: 8 serial round trips per step in the ncu source view)
+      float4 hv[NQ];
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        hv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int so = sofs[q];
+        if (so >= 0) {
+          const int bb = so / HPAD, b = cb + bb;
+          if (step > 0 && b < p.B)
+            hv[q] = __ldcg(reinterpret_cast<const float4*>(p.h_out + ((int64_t)b * p.T + tprev) * ldh + dir * H +
+                                                           (so - bb * HPAD)));
+        }
       }
+#pragma unroll
+      for (int q = 0; q < NQ; ++q)
+        if (sofs[q] >= 0) *reinterpret_cast<float4*>(hs + sofs[q]) = hv[q];
       __syncthreads();
       float xq[4] = {0.f, 0.f, 0.f, 0.f};
       if (tid < LSTM_BC * HS) {
@@ -373,7 +391,7 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_bwd_reg_kernel(const Lst
   constexpr int HS = 8, HB = 8;                       // hidden units per CTA, batch rows per register pass
   extern __shared__ __align__(16) float sm[];
   const int H = p.H, G4 = 4 * H;
-  const int GPAD = RPT * LSTM_THREADS;                // >= 4H, zero padded
+  constexpr int GPAD = RPT * LSTM_THREADS;            // >= 4H, zero padded
   float* dgs = sm;                                    // [LSTM_BC][GPAD]
   float* red = dgs + LSTM_BC * GPAD;                  // [8 warps][64]
   float* dhr = red + 8 * 64;                          // [LSTM_MAX_B][HS]
@@ -429,12 +447,29 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_bwd_reg_kernel(const Lst
     dir_barrier(bar, p.slices, gen);
     // phase B: dh_prev[b][own units] = sum_row dgates_t[b][row] * W_hh[row][unit]
     for (int cb = 0; cb < p.B; cb += LSTM_BC) {
-      for (int i = tid; i < LSTM_BC * (G4 / 4); i += LSTM_THREADS) {
-        const int bb = i / (G4 / 4), r4 = i - bb * (G4 / 4), b = cb + bb;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (b < p.B)
-          v = __ldcg(reinterpret_cast<const float4*>(p.dxproj + ((int64_t)b * p.T + t) * ldx + dir * 4 * H + 4 * r4));
-        *reinterpret_cast<float4*>(dgs + bb * GPAD + 4 * r4) = v;
+      // gate gradients of ALL units for the chunk: four batch rows (RPT/4 float4 each per thread) are in
+      // flight before the first store -- no integer division, no load->store serialisation
+      constexpr int RQ = RPT / 4;
+#pragma unroll 1
+      for (int bb0 = 0; bb0 < LSTM_BC; bb0 += 4) {
+        float4 v[4][RQ];
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+#pragma unroll
+          for (int q = 0; q < RQ; ++q) {
+            const int r4 = tid + q * LSTM_THREADS, b = cb + bb0 + rr;
+            v[rr][q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r4 < G4 / 4 && b < p.B)
+              v[rr][q] = __ldcg(reinterpret_cast<const float4*>(p.dxproj + ((int64_t)b * p.T + t) * ldx +
+                                                                dir * 4 * H + 4 * r4));
+          }
+        }
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+#pragma unroll
+          for (int q = 0; q < RQ; ++q)
+            *reinterpret_cast<float4*>(dgs + (bb0 + rr) * GPAD + 4 * (tid + q * LSTM_THREADS)) = v[rr][q];
+        }
       }
       __syncthreads();
 #pragma unroll 1
