@@ -29,7 +29,15 @@ __device__ __forceinline__ float sru_dact(float c, float val, int act) {
   return act == 1 ? (1.f - val * val) : (act == 2 ? (c > 0.f ? 1.f : 0.f) : 1.f);
 }
 
-__global__ void sru_fwd_kernel(const SruParams p) {
+// The scan is sequential in t only through c; everything it READS (U, x, saved c, dh) is known up front.  A
+// plain loop issues one dependent HBM round trip per step (the stores to c / h keep the compiler from hoisting
+// the next step's loads): measured 1.3 ms per layer at B=32, T=1000, 1024 columns, 15x the HBM time.  So the
+// steps are processed in chunks of SRU_UNR: all loads of a chunk are issued first (independent, SRU_UNR deep
+// per thread), then the recurrence runs on registers.
+constexpr int SRU_UNR = 8;
+
+template <int K>
+__global__ void __launch_bounds__(128) sru_fwd_kernel(const SruParams p) {
   const int ncols = p.d * (p.bidir ? 2 : 1);
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= p.B * ncols) return;
@@ -37,23 +45,44 @@ __global__ void sru_fwd_kernel(const SruParams p) {
   const bool rev = p.bidir && col >= p.d;
   const float bf = p.bias[col], br = p.bias[col + ncols];
   const float m = p.mask_h ? p.mask_h[idx] : 1.f;
+  const int64_t base = (int64_t)b * p.T * ncols + col;       // element (b, t = 0, col)
+  const int64_t tstep = rev ? -(int64_t)ncols : (int64_t)ncols;
+  const int64_t first = rev ? base + (int64_t)(p.T - 1) * ncols : base;
   float c = 0.f;
-  for (int s = 0; s < p.T; ++s) {
-    const int t = rev ? p.T - 1 - s : s;
-    const int64_t row = (int64_t)b * p.T + t;
-    const float* up = p.u + (row * ncols + col) * p.k;
-    const float u0 = up[0];
-    const float g1 = 1.f / (1.f + expf(-(up[1] + bf)));
-    const float g2 = 1.f / (1.f + expf(-(up[2] + br)));
-    const float xp = p.k == 3 ? p.x[row * ncols + col] : up[3];
-    c = (c - u0) * g1 + u0;
-    p.c[row * ncols + col] = c;
-    const float val = sru_act(c, p.act);
-    p.h[row * ncols + col] = (val * m - xp) * g2 + xp;
+  for (int s0 = 0; s0 < p.T; s0 += SRU_UNR) {
+    float u0[SRU_UNR], u1[SRU_UNR], u2[SRU_UNR], xp[SRU_UNR];
+#pragma unroll
+    for (int j = 0; j < SRU_UNR; ++j) {
+      u0[j] = u1[j] = u2[j] = xp[j] = 0.f;
+      if (s0 + j < p.T) {
+        const int64_t e = first + (int64_t)(s0 + j) * tstep;
+        if (K == 4) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(p.u + e * 4));
+          u0[j] = v.x; u1[j] = v.y; u2[j] = v.z; xp[j] = v.w;
+        } else {
+          const float* up = p.u + e * 3;
+          u0[j] = __ldg(up); u1[j] = __ldg(up + 1); u2[j] = __ldg(up + 2);
+          xp[j] = __ldg(p.x + e);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < SRU_UNR; ++j) {
+      if (s0 + j < p.T) {
+        const int64_t e = first + (int64_t)(s0 + j) * tstep;
+        const float g1 = 1.f / (1.f + expf(-(u1[j] + bf)));
+        const float g2 = 1.f / (1.f + expf(-(u2[j] + br)));
+        c = (c - u0[j]) * g1 + u0[j];
+        p.c[e] = c;
+        const float val = sru_act(c, p.act);
+        p.h[e] = (val * m - xp[j]) * g2 + xp[j];
+      }
+    }
   }
 }
 
-__global__ void sru_bwd_kernel(const SruParams p) {
+template <int K>
+__global__ void __launch_bounds__(128) sru_bwd_kernel(const SruParams p) {
   const int ncols = p.d * (p.bidir ? 2 : 1);
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= p.B * ncols) return;
@@ -61,31 +90,63 @@ __global__ void sru_bwd_kernel(const SruParams p) {
   const bool rev = p.bidir && col >= p.d;
   const float bf = p.bias[col], br = p.bias[col + ncols];
   const float m = p.mask_h ? p.mask_h[idx] : 1.f;
+  const int64_t base = (int64_t)b * p.T * ncols + col;
+  const int64_t tstep = rev ? -(int64_t)ncols : (int64_t)ncols;      // forward-scan direction
+  const int64_t first = rev ? base + (int64_t)(p.T - 1) * ncols : base;
   float dc = 0.f, gbf = 0.f, gbr = 0.f;
-  for (int s = p.T - 1; s >= 0; --s) {              // reverse of the forward scan order
-    const int t = rev ? p.T - 1 - s : s;
-    const int tprev = rev ? t + 1 : t - 1;
-    const int64_t row = (int64_t)b * p.T + t;
-    const float* up = p.u + (row * ncols + col) * p.k;
-    float* dup = p.du + (row * ncols + col) * p.k;
-    const float u0 = up[0];
-    const float g1 = 1.f / (1.f + expf(-(up[1] + bf)));
-    const float g2 = 1.f / (1.f + expf(-(up[2] + br)));
-    const float xp = p.k == 3 ? p.x[row * ncols + col] : up[3];
-    const float c = p.c[row * ncols + col];
-    const float cprev = s > 0 ? p.c[((int64_t)b * p.T + tprev) * ncols + col] : 0.f;
-    const float val = sru_act(c, p.act);
-    const float dhv = p.dh[row * ncols + col];
-    const float dg2 = dhv * (val * m - xp);
-    const float dxp = dhv * (1.f - g2);
-    const float dct = dc + dhv * g2 * m * sru_dact(c, val, p.act);
-    const float du0 = dct * (1.f - g1);
-    const float dg1 = dct * (cprev - u0);
-    dc = dct * g1;
-    const float du1 = dg1 * g1 * (1.f - g1), du2 = dg2 * g2 * (1.f - g2);
-    dup[0] = du0; dup[1] = du1; dup[2] = du2;
-    if (p.k == 3) p.dx[row * ncols + col] += dxp; else dup[3] = dxp;
-    gbf += du1; gbr += du2;
+  // scan steps s = T-1 .. 0 (reverse of the forward order); element of step s is first + s * tstep
+  for (int s0 = p.T - 1; s0 >= 0; s0 -= SRU_UNR) {
+    float u0[SRU_UNR], u1[SRU_UNR], u2[SRU_UNR], xp[SRU_UNR], cs[SRU_UNR + 1], dhv[SRU_UNR], dxo[SRU_UNR];
+#pragma unroll
+    for (int j = 0; j < SRU_UNR; ++j) {
+      u0[j] = u1[j] = u2[j] = xp[j] = cs[j] = dhv[j] = dxo[j] = 0.f;
+      const int sidx = s0 - j;
+      if (sidx >= 0) {
+        const int64_t e = first + (int64_t)sidx * tstep;
+        if (K == 4) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(p.u + e * 4));
+          u0[j] = v.x; u1[j] = v.y; u2[j] = v.z; xp[j] = v.w;
+        } else {
+          const float* up = p.u + e * 3;
+          u0[j] = __ldg(up); u1[j] = __ldg(up + 1); u2[j] = __ldg(up + 2);
+          xp[j] = __ldg(p.x + e);
+          dxo[j] = p.dx[e];
+        }
+        cs[j] = p.c[e];
+        dhv[j] = __ldg(p.dh + e);
+      }
+    }
+    {
+      const int sidx = s0 - SRU_UNR;                       // c of the step before the chunk's last one
+      cs[SRU_UNR] = sidx >= 0 ? p.c[first + (int64_t)sidx * tstep] : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < SRU_UNR; ++j) {
+      const int sidx = s0 - j;
+      if (sidx >= 0) {
+        const int64_t e = first + (int64_t)sidx * tstep;
+        const float g1 = 1.f / (1.f + expf(-(u1[j] + bf)));
+        const float g2 = 1.f / (1.f + expf(-(u2[j] + br)));
+        const float c = cs[j];
+        const float cprev = sidx > 0 ? cs[j + 1] : 0.f;
+        const float val = sru_act(c, p.act);
+        const float dg2 = dhv[j] * (val * m - xp[j]);
+        const float dxp = dhv[j] * (1.f - g2);
+        const float dct = dc + dhv[j] * g2 * m * sru_dact(c, val, p.act);
+        const float du0 = dct * (1.f - g1);
+        const float dg1 = dct * (cprev - u0[j]);
+        dc = dct * g1;
+        const float du1 = dg1 * g1 * (1.f - g1), du2 = dg2 * g2 * (1.f - g2);
+        if (K == 4) {
+          *reinterpret_cast<float4*>(p.du + e * 4) = make_float4(du0, du1, du2, dxp);
+        } else {
+          float* dup = p.du + e * 3;
+          dup[0] = du0; dup[1] = du1; dup[2] = du2;
+          p.dx[e] = dxo[j] + dxp;
+        }
+        gbf += du1; gbr += du2;
+      }
+    }
   }
   p.dbias_part[(int64_t)b * 2 * ncols + col] = gbf;
   p.dbias_part[(int64_t)b * 2 * ncols + ncols + col] = gbr;
@@ -112,7 +173,8 @@ extern "C" int gantts_sru_fwd(const float* u, const float* x, const float* bias,
   if (rc) return rc;
   GANTTS_CHECK_ARG(h && c, "sru_fwd: null output");
   const int n = B * d * (bidir ? 2 : 1);
-  sru_fwd_kernel<<<(n + 127) / 128, 128, 0, as_stream(stream)>>>(p);
+  if (k == 4) sru_fwd_kernel<4><<<(n + 127) / 128, 128, 0, as_stream(stream)>>>(p);
+  else sru_fwd_kernel<3><<<(n + 127) / 128, 128, 0, as_stream(stream)>>>(p);
   GANTTS_LAUNCH_CHECK("sru_fwd_kernel");
   return GANTTS_OK;
 }
@@ -128,7 +190,8 @@ extern "C" int gantts_sru_bwd(const float* u, const float* x, const float* bias,
   if (rc) return rc;
   GANTTS_CHECK_ARG(c && dh && du && dbias_part && (k == 4 || dx), "sru_bwd: null pointer");
   const int n = B * d * (bidir ? 2 : 1);
-  sru_bwd_kernel<<<(n + 127) / 128, 128, 0, as_stream(stream)>>>(p);
+  if (k == 4) sru_bwd_kernel<4><<<(n + 127) / 128, 128, 0, as_stream(stream)>>>(p);
+  else sru_bwd_kernel<3><<<(n + 127) / 128, 128, 0, as_stream(stream)>>>(p);
   GANTTS_LAUNCH_CHECK("sru_bwd_kernel");
   return GANTTS_OK;
 }
