@@ -145,3 +145,30 @@ def test_state_dict_keys_match_reference_layout():
     assert list(h.state_dict()) == ["T.weight", "T.bias", "H.0.weight", "H.0.bias", "H.1.weight", "H.1.bias",
                                     "last_linear.weight", "last_linear.bias"]
     assert h.include_parameter_generation() and not m.include_parameter_generation()
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    """Without the built .so every op raises (no silent eager/CPU route)."""
+    from gantts_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "libgantts_b200.so"))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _lib.load()
+    # an existing file that lacks a declared symbol is rejected too
+    import ctypes.util
+    libm = ctypes.util.find_library("m")
+    if libm:
+        monkeypatch.setattr(_lib, "LIB_PATH", ctypes.CDLL(libm)._name if os.path.isabs(ctypes.CDLL(libm)._name)
+                            else "/usr/lib/x86_64-linux-gnu/" + libm)
+        if os.path.exists(_lib.LIB_PATH):
+            with pytest.raises(AttributeError):
+                _lib.load()
+
+
+def test_distortion_struct_matches_header():
+    """ctypes mirror of gantts_distortion_cols_t: same field order as include/gantts_b200.h."""
+    from gantts_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "gantts_b200.h")).read()
+    body = hdr[hdr.index("typedef struct {\n  int mcd_start"):hdr.index("} gantts_distortion_cols_t;")]
+    names = [tok.strip(" ;") for line in body.splitlines()[1:] for tok in line.replace("int ", "").split(",") if tok.strip(" ;")]
+    assert names == [f for f, _ in _lib.DistortionColsT._fields_]
