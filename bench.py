@@ -249,6 +249,9 @@ def emit_json_line(line):
 
 # ------------------------------------------------------------------------------------ B200 arm
 def run_b200_arm(args):
+    if os.environ.get("GANTTS_B200_DBG", "0") not in ("", "0"):
+        raise SystemExit("bench.py: GANTTS_B200_DBG is a phase-timing switch that skips work inside the kernels; "
+                         "refusing to produce a benchmark line with it set")
     import __graft_entry__
     from gantts_b200 import parallel
     # stdout carries exactly ONE JSON line.  NCCL prints its version banner with a bare printf on fd 1 during

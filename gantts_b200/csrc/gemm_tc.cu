@@ -1060,6 +1060,9 @@ static void fill_epilogue(GemmParams& p, const EpiArgs& e) {
   if (dbg < 0) {
     const char* v = getenv("GANTTS_B200_DBG");
     dbg = v ? atoi(v) : 0;
+    if (dbg)
+      fprintf(stderr, "gantts_b200: GANTTS_B200_DBG=%d removes parts of the GEMM kernels (phase timing only): "
+                      "RESULTS ARE WRONG, do not use for training or benchmarks\n", dbg);
   }
   p.dbg = (uint32_t)dbg;
 }
