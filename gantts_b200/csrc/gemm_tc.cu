@@ -28,6 +28,7 @@ constexpr int TC_BM = 128;          // MMA M (TMEM lanes)
 constexpr int TC_BK = 64;           // default reduction elements per stage (p.bk: 64, or 32 for deeper pipelines)
 constexpr int TC_MAX_STAGES = 8;
 constexpr uint32_t TC_BIAS_SMEM = 4096;              // staged bias vector (<= 1024 columns)
+constexpr uint32_t TC_F32_STAGE_SMEM = 16 * 2048;    // opt-in transpose scratch of the fp32 epilogue (2 KB per warp)
 
 // Epilogue flavours (template parameter of the kernel).
 constexpr int EPI_F32 = 0;          // bias + {none | leaky+dropout | sigmoid} -> fp32 C (optionally +=)
@@ -60,6 +61,8 @@ struct GemmParams {
   uint32_t* code;
   int64_t code_pitch;   // words per row
   uint32_t bias_off;    // byte offset (from the aligned smem base) of the staged bias vector, 0 = none
+  uint32_t f32_stage_off;   // EPI_F32 with an unaligned row stride: byte offset of the per-warp transpose scratch
+                            // (TC_EPI_WARPS x 2 KB), 0 = store straight from registers
   uint32_t dbg;         // experiment switches (env GANTTS_B200_DBG): 1 no plane stores, 2 no dropout, 4 no code
   // MN-major only: column sums of A (= bias gradient) via an extra N=16 MMA against a tile of ones
   float* db;            // [num_z][rows_a] partial sums, or null
@@ -110,6 +113,67 @@ __device__ __forceinline__ void store_planes16(const float* v, __nv_bfloat16* hi
     *reinterpret_cast<uint4*>(hi) = make_uint4(h[0], h[1], h[2], h[3]);
     *reinterpret_cast<uint4*>(lo) = make_uint4(l[0], l[1], l[2], l[3]);
   }
+}
+
+// EPI_F32 for outputs whose row stride is not a multiple of 4 floats (y_hat: ld 187, the discriminator input
+// gradient: ld 58, weight-gradient partials of 425- and 58-wide layers).  Straight from registers a thread can
+// only issue 16 scalar stores per chunk and a warp store touches 32 rows = 32 sectors (the 512->187 layer takes
+// 58 us against a 14 us floor, profiles/r01_gemm_per_launch.md).  Here the warp's 32 x 16 tile goes through a
+// private 2 KB shared-memory scratch (float4 writes, XOR-swizzled: conflict-free) and is written back with lanes
+// 0-15 / 16-31 covering two whole 64-byte row segments per store instruction.  Same arithmetic, same order.
+// OPT-IN (GANTTS_B200_F32_STAGE=1): written after the round's GPU budget was spent, not yet run on hardware.
+__device__ __forceinline__ void epilogue_f32_staged(const GemmParams& p, const uint32_t (&r)[16], int64_t row0,
+                                                    int lane, int col, int z, const float* __restrict__ bias_s,
+                                                    float* scr) {
+  const int64_t row = row0 + lane;
+  float v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+  if (p.bias) {
+    if (bias_s) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] += bias_s[col + j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (col + j < p.cols_b) v[j] += __ldg(p.bias + col + j);
+    }
+  }
+  if (p.act == GANTTS_ACT_LEAKY_DROPOUT) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], v[j] * p.slope);
+    if (p.thresh) {
+      const uint32_t half_n = (uint32_t)(p.cols_b + 1) >> 1;
+#pragma unroll
+      for (int j = 0; j < 16; j += 2) {
+        const uint32_t bits = dropout_pair_bits(p.seed, (uint32_t)row, half_n, (uint32_t)(col + j) >> 1);
+        v[j] = (bits & 0xffffu) >= p.thresh ? v[j] * p.keep_scale : 0.f;
+        v[j + 1] = (bits >> 16) >= p.thresh ? v[j + 1] * p.keep_scale : 0.f;
+      }
+    }
+  } else if (p.act == GANTTS_ACT_SIGMOID) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = 1.f / (1.f + expf(-v[j]));
+  }
+  const int sw = (lane >> 1) & 3;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    *reinterpret_cast<float4*>(scr + lane * 16 + 4 * (k ^ sw)) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+  __syncwarp();
+  float* cbase = p.C + (int64_t)z * p.c_zstride;
+  const int j = lane & 15, hr = lane >> 4;
+  const bool col_ok = col + j < p.cols_b;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int rr = 2 * i + hr;
+    const float val = scr[rr * 16 + 4 * ((j >> 2) ^ ((rr >> 1) & 3)) + (j & 3)];
+    const int64_t grow = row0 + rr;
+    if (col_ok && grow < p.rows_a) {
+      float* q = cbase + grow * p.ldc + col + j;
+      *q = p.accumulate ? *q + val : val;
+    }
+  }
+  __syncwarp();
 }
 
 // One 16-column chunk of one output row: registers (fp32 accumulators) -> global.
@@ -399,6 +463,9 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
     const int chalf = (warp - 2) >> 2;                  // column quarter 0..3
     const int cw = p.bn >> 2;                           // columns per warp (multiple of 16)
     const int cbeg = chalf * cw, cend = cbeg + cw;
+    float* stage_scr = (EPI == EPI_F32 && p.f32_stage_off)
+                           ? reinterpret_cast<float*>(smem_raw + (base + p.f32_stage_off - raw)) + (warp - 2) * 512
+                           : nullptr;
     uint32_t code_next[4] = {0u, 0u, 0u, 0u};
     if (EPI == EPI_PLANES_BWD && first_tile < total_tiles) {
       const int nrem = first_tile % tiles_ab;
@@ -450,7 +517,12 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
           ptx::tmem_ld16(taddr + c, r0);
           if (two) ptx::tmem_ld16(taddr + c + 16, r1);
           ptx::tmem_ld_wait();
-          if (row_ok) {
+          if (EPI == EPI_F32 && stage_scr != nullptr) {
+            // whole warp takes part (rows beyond rows_a are masked at the store)
+            if (col0 + c < p.cols_b) epilogue_f32_staged(p, r0, row - lane, lane, col0 + c, z, bias_s, stage_scr);
+            if (two && col0 + c + 16 < p.cols_b)
+              epilogue_f32_staged(p, r1, row - lane, lane, col0 + c + 16, z, bias_s, stage_scr);
+          } else if (row_ok) {
             if (col0 + c < p.cols_b)
               code_out[2 * ci] = epilogue_chunk16<EPI>(p, r0, row, col0 + c, z, bias_s, codes[2 * ci]);
             if (two && col0 + c + 16 < p.cols_b)
@@ -1080,6 +1152,16 @@ static int stage_bk(bool mn) {
   return v ? v : (mn ? 32 : 64);
 }
 
+// Opt-in (GANTTS_B200_F32_STAGE=1): stage fp32 output tiles with unaligned row strides through shared memory.
+static int use_f32_stage() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GANTTS_B200_F32_STAGE");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+
 static int use_pdl() {
   static int v = -1;
   if (v < 0) {
@@ -1092,7 +1174,8 @@ static int use_pdl() {
 template <bool MN, int EPI, int CL>
 static int launch_kernel(const CUtensorMap& mAh, const CUtensorMap& mAl, const CUtensorMap& mBh,
                          const CUtensorMap& mBl, const GemmParams& p, cudaStream_t st) {
-  const size_t smem = (size_t)p.num_stages * p.stage_bytes + (MN ? 8192 : 0) + 1024 + 256 + TC_BIAS_SMEM;
+  const size_t smem = (size_t)p.num_stages * p.stage_bytes + (MN ? 8192 : 0) + 1024 + 256 + TC_BIAS_SMEM +
+                      (p.f32_stage_off ? TC_F32_STAGE_SMEM : 0);
   static bool attr = false;
   if (!attr) {
     GANTTS_CUDA(cudaFuncSetAttribute(gemm_bf16x3_kernel<MN, EPI, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1224,6 +1307,19 @@ static int use_cluster() {
   return v;
 }
 
+// Opt-in staged fp32 epilogue (single-CTA kernels): reserve the 32 KB transpose scratch behind the bias block and
+// give the stages what is left.  No-op unless GANTTS_B200_F32_STAGE=1 and the output row stride is unaligned.
+static void maybe_stage_f32(GemmParams& p, const EpiArgs& e, bool mn, uint32_t budget_bytes) {
+  p.f32_stage_off = 0;
+  if (!use_f32_stage() || e.epi != EPI_F32 || p.vec_ok || !p.C) return;
+  const int stages = (int)((budget_bytes - TC_F32_STAGE_SMEM) / p.stage_bytes);
+  if (stages < 2) return;
+  p.num_stages = stages < p.num_stages ? stages : p.num_stages;
+  if (p.bias_off) p.bias_off = (uint32_t)p.num_stages * p.stage_bytes + 256u;
+  if (mn) p.ones_off = (uint32_t)p.num_stages * p.stage_bytes;
+  p.f32_stage_off = (uint32_t)p.num_stages * p.stage_bytes + (mn ? 8192u : 0u) + 256u + TC_BIAS_SMEM;
+}
+
 // out[rows_a][cols_b] = epi(A * B^T)   (K-major planes A [rows_a][red], B [cols_b][red]).
 static int launch_gemm_kk(const Planes& A, const Planes& B, const EpiArgs& e, cudaStream_t st) {
   GemmParams p{};
@@ -1279,6 +1375,7 @@ static int launch_gemm_kk(const Planes& A, const Planes& B, const EpiArgs& e, cu
   }
   // 2-CTA clusters (B tile multicast) when there are at least two row tiles
   const bool cl2 = use_cluster() == 2 && p.num_a >= 2;
+  if (!cl2) maybe_stage_f32(p, e, false, 216 * 1024);
   CUtensorMap mAh, mAl, mBh, mBl;
   int rc;
   if ((rc = make_map(&mAh, A.hi, A.rows, A.cols, A.pitch, TC_BM, p.bk))) return rc;
@@ -1422,6 +1519,7 @@ static int launch_gemm_mn(const Planes& A, const Planes& B, float* C, float* gb,
   fill_epilogue(p, e);
   p.c_zstride = n;
   p.db = gb ? (direct ? gb : db_partial) : nullptr;
+  if (!pair) maybe_stage_f32(p, e, true, 212 * 1024);
   CUtensorMap mAh, mAl, mBh, mBl;
   int rc;
   if ((rc = make_map(&mAh, A.hi, A.rows, A.cols, A.pitch, p.bk))) return rc;
