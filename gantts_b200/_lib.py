@@ -135,7 +135,12 @@ SIGNATURES = {
     "gantts_optim_workspace_bytes": (_sz, []),
     "gantts_grad_sumsq": (_i, [_vp, _vp, _i, _vp, _vp, _sz, _vp]),
     "gantts_clip_adagrad_step": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _f, _f, _f, _f, _vp]),
+    "gantts_clip_adam_step": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _f, _f, _f, _f, _f, _f, _i64, _vp]),
+    "gantts_gan_step_seed": (_u64, [_u64, _i]),
+    "gantts_mlp_layer_seed": (_u64, [_u64, _i]),
 }
+
+STEP_D, STEP_G, STEP_FINISH, STEP_EVAL = 1, 2, 4, 8
 
 
 def load():

@@ -60,8 +60,10 @@ __global__ void scatter_cols_list_add_kernel(const float* __restrict__ go, int64
     for (int j = lane; j < cols.n; j += 32) gi[r * gi_rs + sc[j]] += go[r * go_rs + j];
 }
 
-__global__ void set_scales_kernel(float* scal, float inv_frames, float adv_w, float mge_w, float mse_w) {
+__global__ void set_scales_kernel(float* scal, float inv_frames, float adv_w, float mge_w, float mse_w,
+                                  int zero_norms) {
   if (threadIdx.x == 0) {
+    if (zero_norms) scal[S_DSUMSQ] = scal[S_GSUMSQ] = 0.f;
     scal[S_INV_T] = inv_frames;
     scal[S_ADV_SCALE] = adv_w * inv_frames;
     scal[S_MGE_SCALE] = mge_w * inv_frames;
@@ -216,6 +218,8 @@ static int check_step(const gantts_gan_step_t* c) {
 
 using namespace gantts;
 
+extern "C" uint64_t gantts_gan_step_seed(uint64_t seed, int which) { return seed * 4 + (uint64_t)which; }
+
 extern "C" size_t gantts_gan_step_workspace_bytes(const gantts_gan_step_t* c) {
   if (check_step(c)) return 0;
   StepLayout L;
@@ -268,12 +272,58 @@ extern "C" int gantts_gan_step(const gantts_gan_step_t* c, int phases, const flo
   adv_cols.n = has_d ? c->n_adv : 0;
   for (int i = 0; i < adv_cols.n; ++i) adv_cols.c[i] = c->adv_cols[i];
   gantts_mlp_t g = c->g, d = c->d;
-  g.seed = seed * 4 + 0;
+  g.seed = gantts_gan_step_seed(seed, 0);
+
+  if (phases & GANTTS_STEP_EVAL) {
+    // ---- "test" phase of train.py:481-486 (model.eval(), phase != "train" at :273,:315): forwards and losses only
+    GANTTS_CHECK_ARG(phases == GANTTS_STEP_EVAL, "gan_step: GANTTS_STEP_EVAL cannot be combined with training phases");
+    g.dropout_p = 0.f;
+    d.dropout_p = 0.f;
+    if ((rc = gantts_sequence_mask(lengths_dev, L.mask, c->B, c->T, stream))) return rc;
+    set_scales_kernel<<<1, 32, 0, st>>>(L.scal, inv_frames, has_adv ? c->adv_w : 0.f, c->mge_w, c->mse_w, 1);
+    GANTTS_LAUNCH_CHECK("set_scales_kernel");
+    gather_cols_list_kernel<<<blocks_1d(M * nS, 1024), 256, 0, st>>>(y, d_out, L.y_static, nS, static_cols, M);
+    GANTTS_LAUNCH_CHECK("gather_cols_list_kernel(y_static)");
+    if ((rc = gantts_mlp_fwd(&g, x, d_in, M, y_hat, d_out, L.g_tape, L.g_tape_bytes, stream))) return rc;
+    if ((rc = gantts_mlpg_fwd(y_hat, (int64_t)c->T * d_out, d_out, y_hat_static, (int64_t)c->T * nS, nS,
+                              c->mlpg_table, &c->streams, &c->windows, c->B, c->T, stream)))
+      return rc;
+    if (has_d) {
+      gather_cols_list_kernel<<<blocks_1d(M * nA, 1024), 256, 0, st>>>(L.y_static, nS, L.d_in + cond_w, dD, adv_cols,
+                                                                       M);
+      GANTTS_LAUNCH_CHECK("gather_cols_list_kernel(real)");
+      gather_cols_list_kernel<<<blocks_1d(M * nA, 1024), 256, 0, st>>>(y_hat_static, nS, L.d_in + M * dD + cond_w, dD,
+                                                                       adv_cols, M);
+      GANTTS_LAUNCH_CHECK("gather_cols_list_kernel(fake)");
+      if (cond_w) {
+        GANTTS_CUDA(cudaMemcpy2DAsync(L.d_in, (size_t)dD * sizeof(float), x, (size_t)d_in * sizeof(float),
+                                      (size_t)cond_w * sizeof(float), (size_t)M, cudaMemcpyDeviceToDevice, st));
+        GANTTS_CUDA(cudaMemcpy2DAsync(L.d_in + M * dD, (size_t)dD * sizeof(float), x, (size_t)d_in * sizeof(float),
+                                      (size_t)cond_w * sizeof(float), (size_t)M, cudaMemcpyDeviceToDevice, st));
+      }
+      if ((rc = gantts_mlp_fwd(&d, L.d_in, dD, 2 * M, L.d_out, 1, L.d_tape, L.d_tape_bytes, stream))) return rc;
+      if ((rc = gantts_masked_bce_fwd(L.d_out, L.mask, M, 0, L.scal + S_REAL, L.red_ws, L.red_ws_bytes, stream))) return rc;
+      if ((rc = gantts_masked_bce_fwd(L.d_out + M, L.mask, M, 1, L.scal + S_FAKE, L.red_ws, L.red_ws_bytes, stream))) return rc;
+      if (has_adv &&
+          (rc = gantts_masked_bce_fwd(L.d_out + M, L.mask, M, 0, L.scal + S_ADV, L.red_ws, L.red_ws_bytes, stream)))
+        return rc;
+    }
+    if ((rc = gantts_masked_sse_fwd(y_hat_static, nS, L.y_static, nS, L.mask, M, nS, L.scal + S_MGE, L.red_ws,
+                                    L.red_ws_bytes, stream)))
+      return rc;
+    if ((rc = gantts_masked_sse_fwd(y_hat, d_out, y, d_out, L.mask, M, d_out, L.scal + S_MSE, L.red_ws,
+                                    L.red_ws_bytes, stream)))
+      return rc;
+    finalize_losses_kernel<<<1, 32, 0, st>>>(L.scal, losses_dev, has_adv ? c->adv_w : 0.f, c->mge_w, c->mse_w,
+                                             has_d ? 1 : 0);
+    GANTTS_LAUNCH_CHECK("finalize_losses_kernel");
+    return GANTTS_OK;
+  }
 
   if (phases & 1) {
     // ---- prologue: mask, scales, y_static (train.py:528-535)
     if ((rc = gantts_sequence_mask(lengths_dev, L.mask, c->B, c->T, stream))) return rc;
-    set_scales_kernel<<<1, 32, 0, st>>>(L.scal, inv_frames, has_adv ? c->adv_w : 0.f, c->mge_w, c->mse_w);
+    set_scales_kernel<<<1, 32, 0, st>>>(L.scal, inv_frames, has_adv ? c->adv_w : 0.f, c->mge_w, c->mse_w, 0);
     GANTTS_LAUNCH_CHECK("set_scales_kernel");
     gather_cols_list_kernel<<<blocks_1d(M * nS, 1024), 256, 0, st>>>(y, d_out, L.y_static, nS, static_cols, M);
     GANTTS_LAUNCH_CHECK("gather_cols_list_kernel(y_static)");
@@ -297,15 +347,16 @@ extern "C" int gantts_gan_step(const gantts_gan_step_t* c, int phases, const flo
         GANTTS_CUDA(cudaMemcpy2DAsync(L.d_in + M * dD, (size_t)dD * sizeof(float), x, (size_t)d_in * sizeof(float),
                                       (size_t)cond_w * sizeof(float), (size_t)M, cudaMemcpyDeviceToDevice, st));
       }
-      d.seed = seed * 4 + 1;
+      d.seed = gantts_gan_step_seed(seed, 1);
       if ((rc = gantts_mlp_fwd(&d, L.d_in, dD, 2 * M, L.d_out, 1, L.d_tape, L.d_tape_bytes, stream))) return rc;
       if ((rc = gantts_masked_bce_fwd(L.d_out, L.mask, M, 0, L.scal + S_REAL, L.red_ws, L.red_ws_bytes, stream))) return rc;
       if ((rc = gantts_masked_bce_fwd(L.d_out + M, L.mask, M, 1, L.scal + S_FAKE, L.red_ws, L.red_ws_bytes, stream))) return rc;
       if ((rc = gantts_masked_bce_bwd(L.d_out, L.mask, M, 0, L.scal + S_INV_T, L.g_dout, stream))) return rc;
       if ((rc = gantts_masked_bce_bwd(L.d_out + M, L.mask, M, 1, L.scal + S_INV_T, L.g_dout + M, stream))) return rc;
       // loss_d.backward(): D parameter gradients + gradient w.r.t. the (fake) D input
-      if ((rc = gantts_mlp_bwd(&d, L.g_dout, 1, L.d_out, 1, 2 * M, L.d_tape, L.d_tape_bytes, L.g_din, dD, pd.gW,
-                               pd.gb, 0, L.mlp_ws, L.mlp_ws_bytes, stream)))
+      // (input gradient for the fake half only: rows M..2M-1)
+      if ((rc = mlp_bwd_impl(&d, L.g_dout, 1, L.d_out, 1, 2 * M, L.d_tape, L.d_tape_bytes, L.g_din, dD, M, pd.gW,
+                             pd.gb, 0, L.mlp_ws, L.mlp_ws_bytes, stream)))
         return rc;
       scatter_cols_list_add_kernel<<<blocks_1d(M * nA, 1024), 256, 0, st>>>(L.g_din + M * dD + cond_w, dD, L.g_static,
                                                                             nS, adv_cols, M);
@@ -329,7 +380,7 @@ extern "C" int gantts_gan_step(const gantts_gan_step_t* c, int phases, const flo
       return rc;
     if (has_adv) {
       // third D forward: updated weights, fresh dropout mask (train.py:307)
-      d.seed = seed * 4 + 2;
+      d.seed = gantts_gan_step_seed(seed, 2);
       if ((rc = gantts_mlp_fwd(&d, L.d_in + M * dD, dD, M, L.d_out, 1, L.d_tape, L.d_tape_bytes, stream))) return rc;
       if ((rc = gantts_masked_bce_fwd(L.d_out, L.mask, M, 0, L.scal + S_ADV, L.red_ws, L.red_ws_bytes, stream))) return rc;
       if ((rc = gantts_masked_bce_bwd(L.d_out, L.mask, M, 0, L.scal + S_ADV_SCALE, L.g_dout, stream))) return rc;

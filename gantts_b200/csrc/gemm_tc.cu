@@ -1034,15 +1034,21 @@ static int make_map(CUtensorMap* m, const void* ptr, int64_t rows, int64_t cols,
   return GANTTS_OK;
 }
 
+static int current_device() {
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  return dev;
+}
+
 static int num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+  static int n[64] = {};
+  const int dev = current_device();
+  if (dev < 0 || dev >= 64) return 148;
+  if (!n[dev]) {
+    cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (n[dev] <= 0) n[dev] = 148;
   }
-  return n;
+  return n[dev];
 }
 
 static inline int64_t pitch_for(int64_t cols) { return (cols + 15) / 16 * 16; }   // 32-byte rows
@@ -1176,11 +1182,13 @@ static int launch_kernel(const CUtensorMap& mAh, const CUtensorMap& mAl, const C
                          const CUtensorMap& mBl, const GemmParams& p, cudaStream_t st) {
   const size_t smem = (size_t)p.num_stages * p.stage_bytes + (MN ? 8192 : 0) + 1024 + 256 + TC_BIAS_SMEM +
                       (p.f32_stage_off ? TC_F32_STAGE_SMEM : 0);
-  static bool attr = false;
-  if (!attr) {
+  // the opt-in is per device (and context): remember it per device ordinal, not per process
+  static bool attr[64] = {};
+  const int dev = current_device();
+  if (dev < 0 || dev >= 64 || !attr[dev]) {
     GANTTS_CUDA(cudaFuncSetAttribute(gemm_bf16x3_kernel<MN, EPI, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      227 * 1024));
-    attr = true;
+    if (dev >= 0 && dev < 64) attr[dev] = true;
   }
   const int units = ((p.num_a + CL - 1) / CL) * p.num_b * p.num_z;     // tiles (CL=1) or pair tiles (CL=2)
   int grid = units * CL < num_sms() ? units * CL : num_sms() / CL * CL;
@@ -1222,10 +1230,11 @@ template <int EPI>
 static int launch_pair_kernel(const CUtensorMap& mAh, const CUtensorMap& mAl, const CUtensorMap& mBh,
                               const CUtensorMap& mBl, const GemmParams& p, cudaStream_t st) {
   const size_t smem = (size_t)p.num_stages * p.stage_bytes + 1024 + 256 + TC_BIAS_SMEM;
-  static bool attr = false;
-  if (!attr) {
+  static bool attr[64] = {};
+  const int dev = current_device();
+  if (dev < 0 || dev >= 64 || !attr[dev]) {
     GANTTS_CUDA(cudaFuncSetAttribute(gemm_pair_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr = true;
+    if (dev >= 0 && dev < 64) attr[dev] = true;
   }
   const int units = ((p.num_a + 1) / 2) * p.num_b;
   const int grid = units * 2 < num_sms() ? units * 2 : num_sms() / 2 * 2;
@@ -1259,10 +1268,11 @@ static int launch_pair_kernel(const CUtensorMap& mAh, const CUtensorMap& mAl, co
 static int launch_pair_mn_kernel(const CUtensorMap& mAh, const CUtensorMap& mAl, const CUtensorMap& mBh,
                                  const CUtensorMap& mBl, const GemmParams& p, cudaStream_t st) {
   const size_t smem = (size_t)p.num_stages * p.stage_bytes + 8192 + 1024 + 256;
-  static bool attr = false;
-  if (!attr) {
+  static bool attr[64] = {};
+  const int dev = current_device();
+  if (dev < 0 || dev >= 64 || !attr[dev]) {
     GANTTS_CUDA(cudaFuncSetAttribute(gemm_pair_mn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr = true;
+    if (dev >= 0 && dev < 64) attr[dev] = true;
   }
   const int units = ((p.num_a + 1) / 2) * p.num_b * p.num_z;
   const int grid = units * 2 < num_sms() ? units * 2 : num_sms() / 2 * 2;

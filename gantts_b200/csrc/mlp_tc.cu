@@ -494,6 +494,8 @@ static inline uint64_t layer_seed(uint64_t seed, int l) { return seed + 0x9E3779
 
 using namespace gantts;
 
+extern "C" uint64_t gantts_mlp_layer_seed(uint64_t seed, int layer) { return layer_seed(seed, layer); }
+
 extern "C" size_t gantts_mlp_tape_bytes(const gantts_mlp_t* m, int64_t M) {
   if (!m || m->num_layers < 1 || m->num_layers > GANTTS_MAX_LAYERS || M < 1) return 0;
   return carve_tape(m, M, nullptr, nullptr) + 512;
@@ -590,11 +592,29 @@ extern "C" int gantts_mlp_fwd(const gantts_mlp_t* m, const float* x, int64_t x_r
   return GANTTS_OK;
 }
 
+// gx_row0: the input gradient is only produced for rows [gx_row0, M) (the fused step stacks real | fake rows and
+// needs the gradient w.r.t. the fake half only: the real half's input is data).
+namespace gantts {
+static int mlp_bwd_impl(const gantts_mlp_t* m, const float* gy, int64_t gy_rs, const float* y, int64_t y_rs, int64_t M,
+                        const void* tape, size_t tape_bytes, float* gx, int64_t gx_rs, int64_t gx_row0,
+                        float* const* gW, float* const* gb, int accumulate, void* workspace, size_t workspace_bytes,
+                        void* stream);
+}
+
 extern "C" int gantts_mlp_bwd(const gantts_mlp_t* m, const float* gy, int64_t gy_rs, const float* y,
                               int64_t y_rs, int64_t M, const void* tape, size_t tape_bytes, float* gx,
                               int64_t gx_rs, float* const* gW, float* const* gb, int accumulate,
                               void* workspace, size_t workspace_bytes, void* stream) {
+  return mlp_bwd_impl(m, gy, gy_rs, y, y_rs, M, tape, tape_bytes, gx, gx_rs, 0, gW, gb, accumulate, workspace,
+                      workspace_bytes, stream);
+}
+
+static int gantts::mlp_bwd_impl(const gantts_mlp_t* m, const float* gy, int64_t gy_rs, const float* y, int64_t y_rs,
+                                int64_t M, const void* tape, size_t tape_bytes, float* gx, int64_t gx_rs,
+                                int64_t gx_row0, float* const* gW, float* const* gb, int accumulate, void* workspace,
+                                size_t workspace_bytes, void* stream) {
   int rc = check_mlp(m, M);
+  GANTTS_CHECK_ARG(gx_row0 >= 0 && gx_row0 < M, "mlp_bwd: bad gx_row0");
   if (rc) return rc;
   const int L = m->num_layers;
   GANTTS_CHECK_ARG(gy && gy_rs >= m->dims[L], "mlp_bwd: bad gy");
@@ -698,10 +718,14 @@ extern "C" int gantts_mlp_bwd(const gantts_mlp_t* m, const float* gy, int64_t gy
     } else if (gx) {
       EpiArgs e;
       e.epi = EPI_F32;
-      e.C = gx;
+      e.C = gx + gx_row0 * gx_rs;
       e.ldc = gx_rs;
       e.accumulate = accumulate;
-      if ((rc = launch_gemm_kk(G, t.Wt[0], e, st))) return rc;
+      Planes Gs = G;
+      Gs.hi += gx_row0 * G.pitch;
+      Gs.lo += gx_row0 * G.pitch;
+      Gs.rows = G.rows - gx_row0;
+      if ((rc = launch_gemm_kk(Gs, t.Wt[0], e, st))) return rc;
     }
   }
   return flush_reduce(rl, accumulate, st);

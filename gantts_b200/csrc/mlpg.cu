@@ -357,13 +357,16 @@ extern "C" int gantts_mlpg_fwd(const float* in, int64_t in_bs, int64_t in_ts, fl
   if (rc) return rc;
   GANTTS_CHECK_ARG(in && out && table_dev && B >= 1 && T >= 1, "mlpg_fwd: bad arguments");
   const size_t smem = ((TT + 2 * K_HALF) * TC + TT * GROW) * sizeof(float);
-  static bool attr_done = false;
+  static bool attr_done_dev[64] = {};
+  int dev_id = -1;
+  cudaGetDevice(&dev_id);
+  const bool attr_done = dev_id >= 0 && dev_id < 64 && attr_done_dev[dev_id];
   if (!attr_done) {
+    if (dev_id >= 0 && dev_id < 64) attr_done_dev[dev_id] = true;
     GANTTS_CUDA(cudaFuncSetAttribute(mlpg_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     // 42 KB per block: with the full shared-memory carve-out 5 blocks fit per SM and the 512 blocks of a
     // cfg2 launch are resident in one wave (the default carve-out admitted 3)
     GANTTS_CUDA(cudaFuncSetAttribute(mlpg_fwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    attr_done = true;
   }
   dim3 grid((ncols + TC - 1) / TC, (T + TT - 1) / TT, B);
   {
@@ -387,11 +390,14 @@ extern "C" int gantts_mlpg_bwd(const float* go, int64_t go_bs, int64_t go_ts, fl
   if (rc) return rc;
   GANTTS_CHECK_ARG(go && gi && table_dev && B >= 1 && T >= 1, "mlpg_bwd: bad arguments");
   const size_t smem = (GIN_ROWS * TC + 72 * GROW + 72 * TC) * sizeof(float);
-  static bool attr_done = false;
+  static bool attr_done_dev[64] = {};
+  int dev_id = -1;
+  cudaGetDevice(&dev_id);
+  const bool attr_done = dev_id >= 0 && dev_id < 64 && attr_done_dev[dev_id];
   if (!attr_done) {
+    if (dev_id >= 0 && dev_id < 64) attr_done_dev[dev_id] = true;
     GANTTS_CUDA(cudaFuncSetAttribute(mlpg_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     GANTTS_CUDA(cudaFuncSetAttribute(mlpg_bwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    attr_done = true;
   }
   dim3 grid((ncols + TC - 1) / TC, (T + TT - 1) / TT, B);
   {

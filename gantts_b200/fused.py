@@ -114,9 +114,14 @@ class FusedGanStep(object):
                                        self.y_hat_static.data_ptr(), self.losses.data_ptr(), self._ws.data_ptr(),
                                        self._ws.numel(), ops._stream()))
 
-    def step(self, x, y, lengths, frames, adv_w=1.0):
+    def step(self, x, y, lengths, frames, adv_w=1.0, train=None):
         """x (B,T,d_in), y (B,T,d_out) contiguous CUDA float32; lengths CUDA int64 (B,); frames = GLOBAL
-        number of valid frames (host number).  Returns the device tensor of 12 loss scalars."""
+        number of valid frames (host number; checked against the device-side count when the losses are read,
+        see loss_dict).  Returns the device tensor of 12 loss scalars.
+
+        ``train=None`` follows the models like the reference's train_loop does (train.py:481-486): both models
+        in ``.train()`` -> training step; both in ``.eval()`` -> the "test" phase (forwards and losses only,
+        dropout off, parameters and Adagrad state untouched)."""
         ops.require_cuda(x, y)
         if not (x.is_contiguous() and y.is_contiguous()):
             raise RuntimeError("FusedGanStep: x and y must be contiguous")
@@ -128,9 +133,18 @@ class FusedGanStep(object):
         for desc, layers in ((self.cfg.g, self._g_layers), (self.cfg.d, self._d_layers)):
             for i, l in enumerate(layers):      # parameters may have been re-allocated (load_state_dict keeps them)
                 desc.W[i], desc.b[i] = l.weight.data_ptr(), l.bias.data_ptr()
-        seed = (self._seed + self._step) & ((1 << 61) - 1)
-        self._step += 1
+        if train is None:
+            if self.g.training != self.d.training:
+                raise RuntimeError("FusedGanStep: generator and discriminator disagree on train()/eval()")
+            train = self.g.training
+        self._frames_claim = float(frames)
         inv = 1.0 / float(frames)
+        if not train:
+            self._call(_lib.STEP_EVAL, x, y, lengths, inv, 0)
+            return self.losses
+        seed = (self._seed + self._step) & ((1 << 61) - 1)
+        self.last_seed = seed
+        self._step += 1
         world = torch.distributed.get_world_size(self.pg) if (torch.distributed.is_available()
                                                               and torch.distributed.is_initialized()) else 1
         if world == 1:
@@ -144,5 +158,50 @@ class FusedGanStep(object):
         return self.losses
 
     def loss_dict(self):
-        v = self.losses.tolist()
-        return dict(zip(LOSS_NAMES, v))
+        """Host copy of the 12 loss scalars (one synchronising read).  Single process: also verifies the `frames`
+        the caller passed to step() against the device-side sum of the mask -- a wrong value would silently
+        rescale every loss and gradient."""
+        v = dict(zip(LOSS_NAMES, self.losses.tolist()))
+        world = torch.distributed.get_world_size(self.pg) if (torch.distributed.is_available()
+                                                              and torch.distributed.is_initialized()) else 1
+        claim = getattr(self, "_frames_claim", None)
+        if world == 1 and claim is not None and v["frames"] != claim:
+            raise RuntimeError("FusedGanStep: step() was told frames=%g but the lengths sum to %g valid frames"
+                               % (claim, v["frames"]))
+        return v
+
+    # ---- checkpoint / resume (reference train.py:162-171 save_checkpoint, :174-199 load_checkpoint round-trip
+    # optimizer.state_dict(); the layout below is torch.optim.Adagrad's, one entry per parameter in
+    # model.parameters() order, so the files are interchangeable with the reference's)
+    def _opt_state(self, model, sums, lr, wd):
+        n = len(sums)
+        return {"state": {i: {"step": torch.tensor(float(self._step)), "sum": s.detach().clone()}
+                          for i, s in enumerate(sums)},
+                "param_groups": [{"lr": lr, "lr_decay": 0, "eps": float(self.cfg.eps), "weight_decay": wd,
+                                  "initial_accumulator_value": 0, "foreach": None, "maximize": False,
+                                  "differentiable": False, "fused": None, "params": list(range(n))}]}
+
+    def state_dict(self):
+        ng = 2 * len(self._g_layers)
+        return {"optimizer_g": self._opt_state(self.g, self._sums[:ng], float(self.cfg.lr_g), float(self.cfg.wd_g)),
+                "optimizer_d": self._opt_state(self.d, self._sums[ng:], float(self.cfg.lr_d), float(self.cfg.wd_d)),
+                "step": self._step, "seed": self._seed}
+
+    def load_state_dict(self, sd):
+        ng = 2 * len(self._g_layers)
+        for key, sums in (("optimizer_g", self._sums[:ng]), ("optimizer_d", self._sums[ng:])):
+            st = sd[key]["state"]
+            for i, s in enumerate(sums):
+                e = st.get(i, st.get(str(i)))
+                if e is None:
+                    raise RuntimeError("FusedGanStep.load_state_dict: %s has no state for parameter %d" % (key, i))
+                s.copy_(e["sum"])
+            grp = (sd[key].get("param_groups") or [{}])[0]
+            if key == "optimizer_g":
+                self.cfg.lr_g = float(grp.get("lr", self.cfg.lr_g))
+                self.cfg.wd_g = float(grp.get("weight_decay", self.cfg.wd_g))
+            else:
+                self.cfg.lr_d = float(grp.get("lr", self.cfg.lr_d))
+                self.cfg.wd_d = float(grp.get("weight_decay", self.cfg.wd_d))
+        self._step = int(sd.get("step", self._step))
+        self._seed = int(sd.get("seed", self._seed))

@@ -431,9 +431,49 @@ class _LinearAct(torch.autograd.Function):
         return (gx.view(xshape) if gx is not None else None), gW, gb, None, None, None, None, None
 
 
+_seed_state = [None, 0]      # [torch.initial_seed() the counter belongs to, draws since then]
+
+
 def draw_seed():
-    """64-bit dropout seed from torch's CPU generator (reproducible under torch.manual_seed)."""
-    return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+    """62-bit dropout seed, reproducible under torch.manual_seed: splitmix64 of (torch.initial_seed(), number
+    of draws since the last manual_seed).  Pure host arithmetic -- no tensor op, no synchronisation (the old
+    form went through torch.randint(...).item() once per dropout layer)."""
+    base = torch.initial_seed()
+    if _seed_state[0] != base:
+        _seed_state[0], _seed_state[1] = base, 0
+    _seed_state[1] += 1
+    z = (base + 0x9E3779B97F4A7C15 * _seed_state[1]) & 0xFFFFFFFFFFFFFFFF
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+    return (z ^ (z >> 31)) & ((1 << 62) - 1)
+
+
+def peek_seeds(n):
+    """The next `n` values draw_seed() will return (test hook: regenerate the masks of a step about to run)."""
+    saved = list(_seed_state)
+    out = [draw_seed() for _ in range(n)]
+    _seed_state[0], _seed_state[1] = saved
+    if _seed_state[0] is None:
+        _seed_state[0], _seed_state[1] = torch.initial_seed(), 0
+    return out
+
+
+def dropout_mask(rows, cols, p, seed, device):
+    """The dropout multiplier {0, 1/(1-p)} every engine applies for (seed, rows, cols): float32 (rows, cols).
+    Test hook for injected-mask parity against the oracle (gantts_dropout on a tensor of ones)."""
+    lib = _lib.load()
+    ones = torch.ones(int(rows), int(cols), dtype=torch.float32, device=device)
+    out = torch.empty_like(ones)
+    _lib.check(lib.gantts_dropout(ones.data_ptr(), out.data_ptr(), int(rows), int(cols), float(p), int(seed),
+                                  _stream()))
+    return out
+
+
+def mlp_dropout_masks(rows, hidden_dims, p, seed, device):
+    """Masks of the hidden layers of an MLP run (mlp_stack / gantts_mlp_fwd) with dropout seed `seed`."""
+    lib = _lib.load()
+    return [dropout_mask(rows, n, p, lib.gantts_mlp_layer_seed(int(seed), l), device)
+            for l, n in enumerate(hidden_dims)]
 
 
 def linear_act(x, W, b, act=_lib.ACT_NONE, p=0.0, training=False, slope=LEAKY_SLOPE, engine=None, seed=None):

@@ -131,8 +131,11 @@ def lstm_forward(lstm, x, lengths, training, engine=None):
         h = _LSTMLayer.apply(h, lens, W_ih, W_hh, bias, eng)
         if training and lstm.dropout > 0 and k + 1 < lstm.num_layers:
             h = _Dropout.apply(h, float(lstm.dropout), ops.draw_seed())
-    if lengths is not None:
-        t_out = int(max(int(v) for v in lengths)) if not torch.is_tensor(lengths) else int(lengths.max().item())
+    # pad_packed_sequence returns max(lengths) frames.  The reference always passes HOST lengths
+    # (cpu_sorted_lengths, train.py:503): those are honoured.  A CUDA lengths tensor keeps the padded length
+    # (reading its maximum would be a host synchronisation per forward; in train.py's batches it equals T).
+    if lengths is not None and not (torch.is_tensor(lengths) and lengths.is_cuda):
+        t_out = int(max(int(v) for v in lengths))
         if t_out < T:
             h = h[:, :t_out]
     return h
@@ -199,14 +202,17 @@ class SRUCell(torch.nn.Module):
         """x: (B, T, n_in) -> (B, T, dirs*n_out)."""
         B, T, _ = x.shape
         ncols = self.n_out * (2 if self.bidirectional else 1)
+        # upstream cuda_functional.SRUCell.forward: only the GEMM input is masked (u = (input * mask_x) @ W); the
+        # highway term (1 - r) * x of SRU_Compute receives the UNMASKED input.
+        x_in = x
         if self.training and self.rnn_dropout > 0:        # variational: one mask per sequence, shared over time
             ones = torch.ones(B, 1, self.n_in, device=x.device)
-            x = x * _Dropout.apply(ones, float(self.rnn_dropout), ops.draw_seed())
+            x = x_in * _Dropout.apply(ones, float(self.rnn_dropout), ops.draw_seed())
         u = ops.linear_act(x, self.weight.t().contiguous(), None, _lib.ACT_NONE, engine=engine)
         mask_h = None
         if self.training and self.dropout > 0:
             mask_h = _Dropout.apply(torch.ones(B, ncols, device=x.device), float(self.dropout), ops.draw_seed())
-        x_hw = x if self.k == 3 else None
+        x_hw = x_in if self.k == 3 else None
         return _SRUScan.apply(u, x_hw, self.bias, mask_h, self.n_out, self.k, self.bidirectional,
                               self.activation_type)
 

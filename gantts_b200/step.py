@@ -13,7 +13,7 @@ import torch
 from . import multistream
 from . import ops
 from . import parallel
-from .optim import ClipAdagrad
+from .optim import ClipAdagrad, make_optimizer
 from .seqloss import sequence_mask
 
 
@@ -39,10 +39,13 @@ def get_selected_static_stream(y_hat_static, hp):
 
 
 def apply_generator(model_g, x, R, lengths, hp):
-    """reference train.py:336-355."""
+    """reference train.py:336-355 (including the front-padding of a shortened pad_packed_sequence output,
+    :346-349 -- a no-op whenever the longest utterance spans the padded length, as in train.py's batches)."""
     if model_g.include_parameter_generation():
         return model_g(x, R, lengths=lengths)
     y_hat = model_g(x, lengths=lengths)
+    if y_hat.size(1) != x.size(1):
+        y_hat = torch.nn.functional.pad(y_hat.unsqueeze(0), (0, 0, x.size(1) - y_hat.size(-2), 0)).squeeze(0)
     y_hat_static = multistream.multi_stream_mlpg(y_hat, R, hp.stream_sizes, hp.has_dynamic_features)
     return y_hat, y_hat_static
 
@@ -51,11 +54,12 @@ class GanTrainer(object):
     """One-call GAN step over native ops.  ``step`` returns device scalars (no host sync)."""
 
     def __init__(self, model_g, model_d, hp, w_d=1.0, mse_w=0.0, mge_w=1.0, lr=0.01, weight_decay=1e-7,
-                 process_group=None):
+                 process_group=None, optimizer="Adagrad", optimizer_params=None):
         self.g, self.d, self.hp = model_g, model_d, hp
         self.w_d, self.mse_w, self.mge_w = float(w_d), float(mse_w), float(mge_w)
-        self.opt_g = ClipAdagrad(model_g.parameters(), lr=lr, weight_decay=weight_decay)
-        self.opt_d = ClipAdagrad(model_d.parameters(), lr=lr, weight_decay=weight_decay) if model_d is not None else None
+        okw = dict(optimizer_params) if optimizer_params is not None else dict(lr=lr, weight_decay=weight_decay)
+        self.opt_g = make_optimizer(optimizer, model_g.parameters(), **okw)
+        self.opt_d = make_optimizer(optimizer, model_d.parameters(), **okw) if model_d is not None else None
         self.pg = process_group
         parallel.broadcast_parameters(model_g, group=process_group)
         if model_d is not None:
@@ -65,14 +69,23 @@ class GanTrainer(object):
         return parallel.allreduce_sum_(t, self.pg)
 
     def step(self, x, y, lengths, R, adv_w=1.0, train=True):
+        """lengths: CUDA int64 tensor, or what train.py passes (a list of ints / 0-d tensors, sorted descending:
+        ``cpu_sorted_lengths``, train.py:503).  The lengths go to the generator and to all three discriminator
+        forwards like train.py:542-575 does (recurrent models honour them: packed-sequence semantics).
+        ``train=False`` is the "test" phase (train.py:481-486,273,315): no backward, no optimiser step; call
+        ``model.eval()`` on the models to switch dropout off as the reference does."""
         hp = self.hp
         nw = len(hp.windows)
+        if torch.is_tensor(lengths):
+            cpu_lengths = lengths
+        else:
+            cpu_lengths = [int(v) for v in lengths]
+            lengths = torch.tensor(cpu_lengths, dtype=torch.int64).to(x.device, non_blocking=True)
         y_static = multistream.get_static_features(y, nw, hp.stream_sizes, hp.has_dynamic_features)   # :528
         mask = sequence_mask(lengths, x.size(1)).unsqueeze(-1)                                        # :535
         self.opt_g.zero_grad()                                                                        # :538
         if self.opt_d is not None:
             self.opt_d.zero_grad()                                                                    # :539
-        cpu_lengths = None
         y_hat, y_hat_static = apply_generator(self.g, x, R, cpu_lengths, hp)                          # :542
         out = {}
         # Global number of valid frames (data parallel: normalise by the GLOBAL count, sum grads)

@@ -220,7 +220,8 @@ int gantts_mlp_bwd(const gantts_mlp_t* mlp, const float* gy, int64_t gy_rstride,
  * reference train.py:275-276,317-318 with hparams.py:223-227,240-244).  Operates on a list of
  * parameter tensors given as device pointer arrays.
  */
-/* Tensor lists are HOST arrays of device pointers (at most 32 tensors); sizes are element counts.
+/* Tensor lists are HOST arrays of device pointers (any count: lists longer than 32 tensors are processed in
+ * chunks of 32 that share the same sum of squares); sizes are element counts.
  * sumsq_dev[0] = sum over all tensors of g^2 (deterministic two-stage reduction). */
 size_t gantts_optim_workspace_bytes(void);
 int gantts_grad_sumsq(float* const* grads, const int64_t* sizes_host, int ntensors, float* sumsq_dev,
@@ -230,6 +231,14 @@ int gantts_grad_sumsq(float* const* grads, const int64_t* sizes_host, int ntenso
 int gantts_clip_adagrad_step(float* const* params, float* const* grads, float* const* state_sums,
                              const int64_t* sizes_host, int ntensors, const float* sumsq_dev,
                              float max_norm, float lr, float weight_decay, float eps, void* stream);
+/* clip_grad_norm_ + torch.optim.Adam.step() (reference hparams.py:125-130: the duration model's optimiser,
+ * lr 1e-3, betas (0.5, 0.9), weight_decay 0, eps 1e-8, amsgrad off):  g *= coef; g' = g + wd * p;
+ * m = b1 m + (1-b1) g'; v = b2 v + (1-b2) g'^2; p -= lr / (1 - b1^t) * m / (sqrt(v) / sqrt(1 - b2^t) + eps),
+ * t = step (1 for the first call). */
+int gantts_clip_adam_step(float* const* params, float* const* grads, float* const* exp_avg,
+                          float* const* exp_avg_sq, const int64_t* sizes_host, int ntensors,
+                          const float* sumsq_dev, float max_norm, float lr, float beta1, float beta2,
+                          float weight_decay, float eps, int64_t step, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * LSTM layer with packed-sequence semantics (reference gantts/models.py:84-85 In2OutRNNHighwayNet,
@@ -313,6 +322,23 @@ typedef struct {
   float lr_g, lr_d, wd_g, wd_d, eps, max_norm;
   float w_d, mse_w, mge_w, adv_w;
 } gantts_gan_step_t;
+
+/* Phase bits of gantts_gan_step.  GANTTS_STEP_EVAL = the "test" phase of reference train.py:481-486,
+ * :273,:315 (model.eval(), phase != "train"): forwards and losses only -- dropout off, no backward, no
+ * optimiser step, parameters and Adagrad state untouched; the adversarial loss re-uses the fake half of the
+ * discriminator forward (with dropout off and no discriminator step in between, the reference's third forward
+ * returns exactly those values). */
+#define GANTTS_STEP_D 1
+#define GANTTS_STEP_G 2
+#define GANTTS_STEP_FINISH 4
+#define GANTTS_STEP_EVAL 8
+
+/* Dropout seeds of the fused step, so a test can regenerate every keep mask with gantts_dropout():
+ * forward `which` (0 generator, 1 stacked real|fake discriminator batch, 2 adversarial discriminator forward)
+ * of a step called with `seed` runs its MLP with gantts_gan_step_seed(seed, which); hidden layer l of an MLP
+ * run with seed s draws its mask as gantts_dropout(ones[rows][dims[l+1]], p, gantts_mlp_layer_seed(s, l)). */
+uint64_t gantts_gan_step_seed(uint64_t seed, int which);
+uint64_t gantts_mlp_layer_seed(uint64_t seed, int layer);
 
 size_t gantts_gan_step_workspace_bytes(const gantts_gan_step_t* cfg);
 /* Flat gradient buffer inside `workspace` (which: 0 = generator, 1 = discriminator). */

@@ -100,25 +100,49 @@ def multi_stream_mlpg(inputs, R, stream_sizes=(180, 3, 1, 3),
 
 
 # ------------------------------------------------------------------------------ models.py
-def mlp_forward(x, layers, dropout_p=0.0, training=False, last_sigmoid=False):
+def mlp_forward(x, layers, dropout_p=0.0, training=False, last_sigmoid=False, masks=None):
     """reference gantts/models.py:137-141 -- x = Dropout(LeakyReLU(Linear(x))) per hidden
     layer, then last_linear (+ sigmoid).  ``layers`` = [(W, b), ...]; the last pair is
-    ``last_linear``."""
-    for W, b in layers[:-1]:
-        x = F.dropout(F.leaky_relu(F.linear(x, W, b), LEAKY_SLOPE), dropout_p, training)
+    ``last_linear``.
+
+    ``masks`` (test hook, SURVEY.md 7 hard part 4): one tensor per hidden layer holding the dropout
+    multiplier {0, 1/(1-p)} of every element; when given it REPLACES ``F.dropout`` (same place in
+    the chain: Linear -> LeakyReLU -> Dropout), so a train-mode run of the product can be compared
+    against this port with the product's own keep decisions injected (torch's Philox stream cannot
+    be reproduced on the device)."""
+    for l, (W, b) in enumerate(layers[:-1]):
+        h = F.leaky_relu(F.linear(x, W, b), LEAKY_SLOPE)
+        x = h * masks[l].view_as(h) if masks is not None else F.dropout(h, dropout_p, training)
     W, b = layers[-1]
     x = F.linear(x, W, b)
     return torch.sigmoid(x) if last_sigmoid else x
 
 
-def in2out_highway_forward(x, R, gate, layers, static_dim, dropout_p=0.0, training=False):
+def in2out_highway_forward(x, R, gate, layers, static_dim, dropout_p=0.0, training=False, masks=None):
     """reference gantts/models.py:54-69 -- returns (y_hat, x_static + sigmoid(T x_static) * MLPG(y_hat))."""
     x = x.unsqueeze(0) if x.dim() == 2 else x
     x_static = x[:, :, :static_dim]
     Tx = torch.sigmoid(F.linear(x_static, gate[0], gate[1]))
-    h = mlp_forward(x, layers, dropout_p, training, last_sigmoid=False)
+    h = mlp_forward(x, layers, dropout_p, training, last_sigmoid=False, masks=masks)
     Gx = nn_port.unit_variance_mlpg(R, h)
     return h, x_static + Tx * Gx
+
+
+def in2out_rnn_highway_forward(x, R, lengths, gate, lstm, hidden2out, static_dim):
+    """reference gantts/models.py:92-118 -- pack -> nn.LSTM -> pad -> hidden2out -> MLPG; returns
+    ``(x, x_static + sigmoid(T x_static) * Gx)``: the FIRST output is the input itself (``:118``)."""
+    x = x.unsqueeze(0) if x.dim() == 2 else x
+    x_static = x[:, :, :static_dim]
+    Tx = torch.sigmoid(F.linear(x_static, gate[0], gate[1]))
+    if lengths is not None:
+        packed = torch.nn.utils.rnn.pack_padded_sequence(x, [int(l) for l in lengths], batch_first=True)
+        out, _ = lstm(packed)
+        out, _ = torch.nn.utils.rnn.pad_packed_sequence(out, batch_first=True)
+    else:
+        out, _ = lstm(x)
+    out = F.linear(out, hidden2out[0], hidden2out[1])
+    Gx = nn_port.unit_variance_mlpg(R, out)
+    return x, x_static + Tx * Gx
 
 
 def lstm_forward(x, lengths, lstm, hidden2out, last_sigmoid=False):
@@ -189,57 +213,75 @@ class GanStepState(object):
         return [t for pair in self.d for t in pair]
 
 
-def gan_step_mlp(state, x, y, lengths, R, hp, w_d=1.0, mse_w=0.0, mge_w=1.0, adv_w=1.0,
-                 dropout_g=0.0, dropout_d=0.0, training=True, lr=0.01, weight_decay=1e-7,
-                 update=True):
-    """One mini-batch of the reference train_loop body (train.py:528-580) for an MLP generator
-    and MLP discriminator, restated with explicit tensors.
+def apply_generator(model_out, x, R, hp, include_parameter_generation=False):
+    """reference train.py:336-355 given the generator's raw output: models that include parameter
+    generation return ``(y_hat, y_hat_static)`` themselves; generic models return ``y_hat`` which is
+    (front-)padded to the input length if pad_packed_sequence shortened it (``:347-349``, a no-op
+    whenever the longest utterance spans the padded length, as in train.py's own batches) and goes
+    through ``multi_stream_mlpg``."""
+    if include_parameter_generation:
+        return model_out
+    y_hat = model_out
+    if y_hat.size(1) != x.size(1):
+        y_hat = F.pad(y_hat.unsqueeze(0), (0, 0, x.size(1) - y_hat.size(-2), 0)).squeeze(0)
+    return y_hat, multi_stream_mlpg(y_hat, R, hp["stream_sizes"], hp["has_dynamic_features"])
+
+
+def gan_step(g_forward, g_params, g_sum, d_layers, d_sum, x, y, lengths, R, hp, w_d=1.0, mse_w=0.0,
+             mge_w=1.0, adv_w=1.0, dropout_d=0.0, training=True, lr=0.01, weight_decay=1e-7, update=True,
+             d_masks=None):
+    """One mini-batch of the reference train_loop body (train.py:528-580) for ANY generator:
+    ``g_forward()`` -> ``(y_hat, y_hat_static)`` is the result of ``apply_generator`` (train.py:336-355)
+    with autograd history on ``g_params``; ``d_layers`` is the MLP discriminator ``[(W, b), ...]`` or
+    None.  ``d_masks`` = {"real": [...], "fake": [...], "adv": [...]} injects dropout multipliers into
+    the three discriminator forwards (see ``mlp_forward``).
 
     Order of operations and quirks preserved: single zero_grad at the
     top; y_hat_static is NOT detached in the discriminator update, so ``loss_d.backward`` also
     deposits the fake-term gradient on the generator; the discriminator steps before the third
     D forward used by the adversarial loss; gradients of both backwards accumulate on G before
-    its clip + Adagrad step.  Returns a dict of python floats and the generator outputs.
-    """
+    its clip + Adagrad step.  ``training=False`` with ``update=False`` is the "test" phase of
+    train.py:481-486 (forwards and losses only).  Returns a dict of python floats and the
+    generator outputs."""
     nw = hp["num_windows"]
     y_static = get_static_features(y, nw, hp["stream_sizes"], hp["has_dynamic_features"])   # :528-529
     mask = sequence_mask(lengths, x.size(1)).unsqueeze(-1)                                   # :535
-    for p in state.g_params() + state.d_params():                                            # :538-539
+    d_params = [t for pair in d_layers for t in pair] if d_layers is not None else []
+    for p in list(g_params) + d_params:                                                      # :538-539
         p.grad = None
-    # apply_generator, train.py:336-355
-    y_hat = mlp_forward(x, state.g, dropout_g, training, last_sigmoid=False)
-    y_hat_static = multi_stream_mlpg(y_hat, R, hp["stream_sizes"], hp["has_dynamic_features"])
+    y_hat, y_hat_static = g_forward()                                                        # :542
     out = {}
     T = mask.sum().item()
     cond = hp.get("discriminator_linguistic_condition", False)
-    if w_d > 0:
+    dm = d_masks or {}
+    if w_d > 0 and d_layers is not None:
         # update_discriminator, train.py:245-279
         real_in = get_selected_static_stream(y_static, hp)
         fake_in = get_selected_static_stream(y_hat_static, hp)
         if cond:
             real_in = torch.cat((x, real_in), -1)
             fake_in = torch.cat((x, fake_in), -1)
-        D_real = mlp_forward(real_in, state.d, dropout_d, training, last_sigmoid=True)
+        D_real = mlp_forward(real_in, d_layers, dropout_d, training, last_sigmoid=True, masks=dm.get("real"))
         out["real_correct"] = ((D_real > 0.5).float() * mask).sum().item()
-        D_fake = mlp_forward(fake_in, state.d, dropout_d, training, last_sigmoid=True)
+        D_fake = mlp_forward(fake_in, d_layers, dropout_d, training, last_sigmoid=True, masks=dm.get("fake"))
         out["fake_correct"] = ((D_fake < 0.5).float() * mask).sum().item()
         loss_real = bce_real(D_real, mask, T)
         loss_fake = bce_fake(D_fake, mask, T)
         loss_d = loss_real + loss_fake
         if update:
             loss_d.backward(retain_graph=True)
-            dg = [p.grad for p in state.d_params()]
+            dg = [p.grad for p in d_params]
             out["d_grad_norm"] = float(clip_grad_norm(dg, 1.0))
-            adagrad_step(state.d_params(), dg, state.d_sum, lr, weight_decay)
+            adagrad_step(d_params, dg, d_sum, lr, weight_decay)
         out.update(loss_d=loss_d.item(), loss_fake_d=loss_fake.item(), loss_real_d=loss_real.item())
     # update_generator, train.py:282-320
     loss_mge = masked_mse(y_hat_static, y_static, mask=mask)
     loss_mse = masked_mse(y_hat, y, mask=mask)
-    if adv_w > 0 and w_d > 0:
+    if adv_w > 0 and w_d > 0 and d_layers is not None:
         fake_in = get_selected_static_stream(y_hat_static, hp)
         if cond:
             fake_in = torch.cat((x, fake_in), -1)
-        D_adv = mlp_forward(fake_in, state.d, dropout_d, training, last_sigmoid=True)
+        D_adv = mlp_forward(fake_in, d_layers, dropout_d, training, last_sigmoid=True, masks=dm.get("adv"))
         loss_adv = bce_real(D_adv, mask, T)
     else:
         loss_adv = y.new_zeros(1)
@@ -247,16 +289,96 @@ def gan_step_mlp(state, x, y, lengths, R, hp, w_d=1.0, mse_w=0.0, mge_w=1.0, adv
     loss_g = (mse_w * loss_mse + mge_w * loss_mge) + adv_w * loss_adv
     if update:
         loss_g.backward()
-        gg = [p.grad for p in state.g_params()]
+        g_params = list(g_params)
+        gg = [p.grad if p.grad is not None else torch.zeros_like(p) for p in g_params]
         out["g_grad_norm"] = float(clip_grad_norm(gg, 1.0))
-        adagrad_step(state.g_params(), gg, state.g_sum, lr, weight_decay)
+        adagrad_step(g_params, gg, g_sum, lr, weight_decay)
     out.update(loss_mse=loss_mse.item(), loss_mge=loss_mge.item(), loss_adv=float(loss_adv.detach()),
                loss_g=float(loss_g.detach()))
     return out, y_hat.detach(), y_hat_static.detach()
 
 
+def gan_step_mlp(state, x, y, lengths, R, hp, w_d=1.0, mse_w=0.0, mge_w=1.0, adv_w=1.0,
+                 dropout_g=0.0, dropout_d=0.0, training=True, lr=0.01, weight_decay=1e-7,
+                 update=True, masks=None):
+    """``gan_step`` for an MLP generator (reference ``MLP`` class, models.py:121-141) held in a
+    ``GanStepState``.  ``masks`` = {"g": [...], "real": [...], "fake": [...], "adv": [...]} injects the
+    dropout multipliers of the generator forward and of the three discriminator forwards."""
+    masks = masks or {}
+
+    def g_forward():
+        y_hat = mlp_forward(x, state.g, dropout_g, training, last_sigmoid=False, masks=masks.get("g"))
+        return apply_generator(y_hat, x, R, hp)
+
+    return gan_step(g_forward, state.g_params(), state.g_sum, state.d if w_d > 0 else None, state.d_sum,
+                    x, y, lengths, R, hp, w_d=w_d, mse_w=mse_w, mge_w=mge_w, adv_w=adv_w, dropout_d=dropout_d,
+                    training=training, lr=lr, weight_decay=weight_decay, update=update, d_masks=masks)
+
+
+class GeneratorOracle(object):
+    """CPU generator + Adagrad state for ``gan_step`` built from a reference ``state_dict`` (same key
+    names as the reference classes, models.py:40-48,84-86,128-131,198-200).  ``kind``:
+    "mlp" (MLP), "highway" (In2OutHighwayNet), "rnn_highway" (In2OutRNNHighwayNet), "lstm" (LSTMRNN;
+    GRURNN with ``rnn_attr="gru"``).  Recurrent kinds run torch's own CPU ``nn.LSTM`` on packed
+    sequences exactly like the reference."""
+
+    def __init__(self, kind, sd, static_dim=None, num_hidden=None, hidden_dim=None, bidirectional=False,
+                 rnn_attr="lstm"):
+        self.kind, self.static_dim = kind, static_dim
+        t = lambda k: torch.as_tensor(np.asarray(sd[k])).clone().float().requires_grad_(True)
+        self.named = {}
+        if kind in ("mlp", "highway"):
+            pre = "layers" if kind == "mlp" else "H"
+            n = len([k for k in sd if k.startswith(pre + ".") and k.endswith(".weight")])
+            self.layers = [(t("%s.%d.weight" % (pre, i)), t("%s.%d.bias" % (pre, i))) for i in range(n)]
+            self.layers.append((t("last_linear.weight"), t("last_linear.bias")))
+            for i in range(n):
+                self.named["%s.%d.weight" % (pre, i)], self.named["%s.%d.bias" % (pre, i)] = self.layers[i]
+            self.named["last_linear.weight"], self.named["last_linear.bias"] = self.layers[-1]
+        else:
+            in_dim = np.asarray(sd[rnn_attr + ".weight_ih_l0"]).shape[1]
+            self.lstm = torch.nn.LSTM(in_dim, hidden_dim, num_hidden, batch_first=True, bidirectional=bidirectional)
+            self.lstm.load_state_dict({k[len(rnn_attr) + 1:]: torch.as_tensor(np.asarray(v)).float()
+                                       for k, v in sd.items() if k.startswith(rnn_attr + ".")})
+            self.lstm.train()
+            for k, p in self.lstm.named_parameters():
+                self.named[rnn_attr + "." + k] = p
+            self.h2o = (t("hidden2out.weight"), t("hidden2out.bias"))
+            self.named["hidden2out.weight"], self.named["hidden2out.bias"] = self.h2o
+        if kind in ("highway", "rnn_highway"):
+            self.gate = (t("T.weight"), t("T.bias"))
+            self.named["T.weight"], self.named["T.bias"] = self.gate
+        self.sums = [torch.zeros_like(p) for p in self.params()]
+
+    def params(self):
+        return list(self.named.values())
+
+    def include_parameter_generation(self):
+        return self.kind in ("highway", "rnn_highway")
+
+    def forward(self, x, R, lengths, hp, dropout_p=0.0, training=False, masks=None):
+        """(y_hat, y_hat_static) as reference apply_generator (train.py:336-355) returns them."""
+        if self.kind == "mlp":
+            out = mlp_forward(x, self.layers, dropout_p, training, last_sigmoid=False, masks=masks)
+        elif self.kind == "highway":
+            out = in2out_highway_forward(x, R, self.gate, self.layers, self.static_dim, dropout_p, training, masks)
+        elif self.kind == "rnn_highway":
+            out = in2out_rnn_highway_forward(x, R, lengths, self.gate, self.lstm, self.h2o, self.static_dim)
+        else:
+            out = lstm_forward(x, lengths, self.lstm, self.h2o)
+        return apply_generator(out, x, R, hp, self.include_parameter_generation())
+
+
+def discriminator_layers(sd):
+    """[(W, b), ...] (requires_grad) of a reference ``MLP`` state_dict (``layers.i``, ``last_linear``)."""
+    t = lambda k: torch.as_tensor(np.asarray(sd[k])).clone().float().requires_grad_(True)
+    n = len([k for k in sd if k.startswith("layers.") and k.endswith(".weight")])
+    return [(t("layers.%d.weight" % i), t("layers.%d.bias" % i)) for i in range(n)] + \
+           [(t("last_linear.weight"), t("last_linear.bias"))]
+
+
 # ------------------------------------------------------------------------------ SRU (unpinned)
-def sru_layer_forward(x, W, b, bidirectional=False, use_tanh=False, use_relu=True):
+def sru_layer_forward(x, W, b, bidirectional=False, use_tanh=False, use_relu=True, mask_x=None, mask_h=None):
     """SRU v1 layer (Lei et al. 2017, github.com/taolei87/sru ``cuda_functional.py``; NOT vendored
     in the reference tree -- restated from the published recurrence, **parity unpinned**):
 
@@ -266,12 +388,18 @@ def sru_layer_forward(x, W, b, bidirectional=False, use_tanh=False, use_relu=Tru
         h_t = r_t * g(c_t) + (1 - r_t) * x'_t     (x' = x if k == 3 else U_x')
 
     ``x``: (T, B, n_in); ``W``: (n_in, dirs*k*d) laid out ``[..., dir, d, k]`` (k fastest) as in
-    the upstream kernel; ``b``: (dirs*2*d,) = [f-bias | r-bias] per direction."""
+    the upstream kernel; ``b``: (dirs*2*d,) = [f-bias | r-bias] per direction.
+
+    Train mode of upstream ``SRUCell.forward``: ``mask_x`` (B, n_in) is the variational ``rnn_dropout``
+    multiplier applied to the GEMM input ONLY (``u = (x * mask_x) @ W``; the highway term keeps the unmasked
+    ``x``); ``mask_h`` (B, dirs*d) is the ``dropout`` multiplier on ``g(c_t)`` inside the recurrence
+    (``h_t = r_t * g(c_t) * mask_h + (1 - r_t) * x'_t``)."""
     T, B, n_in = x.shape
     dirs = 2 if bidirectional else 1
     d = b.numel() // (2 * dirs)
     k = W.shape[1] // (d * dirs)
-    U = (x.reshape(-1, n_in) @ W).view(T, B, dirs, d, k)
+    xin = x * mask_x.unsqueeze(0) if mask_x is not None else x
+    U = (xin.reshape(-1, n_in) @ W).view(T, B, dirs, d, k)
     bias = b.view(dirs, 2, d)
     act = torch.tanh if use_tanh else (torch.relu if use_relu else (lambda v: v))
     outs = []
@@ -285,6 +413,7 @@ def sru_layer_forward(x, W, b, bidirectional=False, use_tanh=False, use_relu=Tru
             r = torch.sigmoid(u[..., 2] + bias[di, 1])
             c = f * c + (1 - f) * u[..., 0]
             xp = x[t][:, di * d:(di + 1) * d] if k == 3 else u[..., 3]
-            hs[t] = r * act(c) + (1 - r) * xp
+            gc = act(c) * mask_h[:, di * d:(di + 1) * d] if mask_h is not None else act(c)
+            hs[t] = r * gc + (1 - r) * xp
         outs.append(torch.stack(hs, 0))
     return torch.cat(outs, -1)

@@ -50,6 +50,11 @@ def golden_step():
     return np.load(os.path.join(GOLDEN, "step.npz"))
 
 
+@pytest.fixture(scope="session")
+def golden_step_models():
+    return np.load(os.path.join(GOLDEN, "step_models.npz"))
+
+
 def rel_err(a, b):
     """max |a-b| / max(|b|) -- the 'relative to output scale' error used for float parity."""
     a = np.asarray(a, dtype=np.float64)

@@ -185,10 +185,99 @@ def gen_step(ref, out, cond, tag):
     hp.discriminator_linguistic_condition = True
 
 
+def _run_ref_step(ref, tr, hp, g, d, og, od, x, y, lens, R, w_d, mse_w, mge_w, adv_w=1.0):
+    """One mini-batch through the reference's own apply_generator / update_discriminator /
+    update_generator (train.py:336-355, 245-279, 282-320) exactly as train_loop calls them."""
+    lengths = torch.LongTensor(lens)
+    y_static = ref.multistream.get_static_features(y, len(hp.windows), hp.stream_sizes, hp.has_dynamic_features)
+    mask = ref.seqloss.sequence_mask(lengths).unsqueeze(-1)
+    og.zero_grad()
+    if od is not None:
+        od.zero_grad()
+    y_hat, y_hat_static = tr.apply_generator(g, x, R, lens)
+    res = {}
+    if w_d > 0:
+        ld, lf, lr_, rc, fc = tr.update_discriminator(d, od, x, y_static, y_hat_static, lens, mask, "train")
+        res.update(loss_d=ld, loss_fake_d=lf, loss_real_d=lr_, real_correct=rc, fake_correct=fc)
+    lmse, lmge, ladv, lg = tr.update_generator(g, d, og, x, y, y_hat, y_static, y_hat_static,
+                                                adv_w if w_d > 0 else 0.0, lens, mask, "train", mse_w=mse_w,
+                                                mge_w=mge_w)
+    res.update(loss_mse=lmse, loss_mge=lmge, loss_adv=ladv, loss_g=lg)
+    return res, y_hat, y_hat_static
+
+
+LOSS_KEYS = ("loss_d", "loss_fake_d", "loss_real_d", "loss_mse", "loss_mge", "loss_adv", "loss_g",
+             "real_correct", "fake_correct")
+
+
+def gen_step_models(ref, out):
+    """GAN steps of the reference with its non-MLP generators (BASELINE cfg1 / cfg3 / cfg5 at toy sizes,
+    dropout 0 so train mode is deterministic): In2OutHighwayNet without a discriminator (w_d = 0),
+    In2OutRNNHighwayNet (bidirectional LSTM) + MLP D on hparams.vc, LSTMRNN (bidirectional) + MLP D on
+    hparams.tts_acoustic; two consecutive mini-batches each, ragged lengths."""
+    tr, hparams, M = ref.train, ref.hparams, ref.models
+    from oracle.nnmnkwii_port import unit_variance_mlpg_matrix
+    rng = np.random.default_rng(9)
+    cases = [
+        ("hw_", hparams.vc, lambda: M.In2OutHighwayNet(in_dim=27, out_dim=27, static_dim=9, num_hidden=2,
+                                                         hidden_dim=24, dropout=0.0), None, 27, 27, 0.0, 1.0, 1.0),
+        ("rhw_", hparams.vc, lambda: M.In2OutRNNHighwayNet(in_dim=27, out_dim=27, static_dim=9, num_hidden=2,
+                                                            hidden_dim=12, bidirectional=True, dropout=0.0),
+         lambda: M.MLP(in_dim=9, out_dim=1, num_hidden=2, hidden_dim=16, dropout=0.0, last_sigmoid=True),
+         27, 27, 1.0, 0.0, 1.0),
+        ("lstm_", hparams.tts_acoustic, lambda: M.LSTMRNN(in_dim=20, out_dim=187, num_hidden=2, hidden_dim=16,
+                                                          bidirectional=True, dropout=0.0, last_sigmoid=False),
+         lambda: M.MLP(in_dim=58, out_dim=1, num_hidden=3, hidden_dim=16, dropout=0.0, last_sigmoid=True),
+         20, 187, 1.0, 0.5, 1.0),
+    ]
+    B, T = 3, 24
+    for tag, hp, mk_g, mk_d, d_in, d_out, w_d, mse_w, mge_w in cases:
+        saved = (hp.stream_sizes, hp.discriminator_linguistic_condition)
+        if hp is hparams.vc:
+            hp.stream_sizes = [27]                    # 9 static dims x 3 windows (hparams.py:27 with order 9)
+        hp.discriminator_linguistic_condition = False
+        tr.hp = hp
+        torch.manual_seed(31)
+        g = mk_g()
+        d = mk_d() if mk_d is not None else None
+        g.train()
+        state_arrays(g, tag + "g0_", out)
+        og = optim.Adagrad(g.parameters(), lr=0.01, weight_decay=1e-7)
+        od = None
+        if d is not None:
+            d.train()
+            state_arrays(d, tag + "d0_", out)
+            od = optim.Adagrad(d.parameters(), lr=0.01, weight_decay=1e-7)
+        R = torch.from_numpy(unit_variance_mlpg_matrix(hp.windows, T))
+        for it in range(2):
+            lens = lengths_desc(rng, B, T)
+            x = torch.randn(B, T, d_in) if hp is hparams.vc else torch.rand(B, T, d_in) * 0.98 + 0.01
+            y = torch.randn(B, T, d_out)
+            for b, n in enumerate(lens):
+                x[b, n:] = 0
+                y[b, n:] = 0
+            res, y_hat, y_hat_static = _run_ref_step(ref, tr, hp, g, d, og, od, x, y, lens, R, w_d, mse_w, mge_w)
+            p = "%sit%d_" % (tag, it)
+            out[p + "x"], out[p + "y"], out[p + "lengths"] = npy(x), npy(y), np.array(lens)
+            out[p + "y_hat"], out[p + "y_hat_static"] = npy(y_hat), npy(y_hat_static)
+            out[p + "losses"] = np.array([res.get(k, np.nan) for k in LOSS_KEYS], dtype=np.float64)
+            state_arrays(g, p + "g_", out)
+            if d is not None:
+                state_arrays(d, p + "d_", out)
+        out[tag + "cfg"] = np.array([w_d, mse_w, mge_w], dtype=np.float64)
+        hp.stream_sizes, hp.discriminator_linguistic_condition = saved
+
+
 def main():
     ref = reference_loader.load()
     torch.manual_seed(1234)
     torch.set_num_threads(1)
+    if "--only-step-models" in sys.argv:
+        d = {}
+        gen_step_models(ref, d)
+        np.savez_compressed(os.path.join(HERE, "step_models.npz"), **d)
+        print("step_models", os.path.getsize(os.path.join(HERE, "step_models.npz")))
+        return
     a, b, c = {}, {}, {}
     gen_seqloss(ref, a)
     gen_multistream(ref, a)
@@ -198,7 +287,10 @@ def main():
     np.savez_compressed(os.path.join(HERE, "ops.npz"), **a)
     np.savez_compressed(os.path.join(HERE, "models.npz"), **b)
     np.savez_compressed(os.path.join(HERE, "step.npz"), **c)
-    for n in ("ops", "models", "step"):
+    d = {}
+    gen_step_models(ref, d)
+    np.savez_compressed(os.path.join(HERE, "step_models.npz"), **d)
+    for n in ("ops", "models", "step", "step_models"):
         print(n, os.path.getsize(os.path.join(HERE, n + ".npz")))
 
 

@@ -156,6 +156,56 @@ def test_gan_step_two_iterations(golden_step, tag, cond):
             assert rel_err(b.detach().numpy(), g[p + "d_" + n + ".bias"]) < 1e-5
 
 
+VC_TOY_HP = dict(stream_sizes=[27], has_dynamic_features=[True], adversarial_streams=[True],
+                 mask_nth_mgc_for_adv_loss=0, num_windows=3, discriminator_linguistic_condition=False)
+STEP_MODEL_CASES = {
+    "hw_": ("highway", dict(static_dim=9), VC_TOY_HP),
+    "rhw_": ("rnn_highway", dict(static_dim=9, num_hidden=2, hidden_dim=12, bidirectional=True), VC_TOY_HP),
+    "lstm_": ("lstm", dict(num_hidden=2, hidden_dim=16, bidirectional=True), TTS_HP),
+}
+LOSS_KEYS = ("loss_d", "loss_fake_d", "loss_real_d", "loss_mse", "loss_mge", "loss_adv", "loss_g",
+             "real_correct", "fake_correct")
+
+
+@pytest.mark.parametrize("tag", sorted(STEP_MODEL_CASES))
+def test_gan_step_non_mlp_generators(golden_step_models, tag):
+    """The generic step of the port (gp.gan_step + GeneratorOracle) against the reference's own step functions
+    run with In2OutHighwayNet (no discriminator, BASELINE cfg1), In2OutRNNHighwayNet + MLP D (cfg3) and
+    LSTMRNN + MLP D (cfg5) at toy sizes: losses, counts, outputs and post-step weights of two mini-batches."""
+    g = golden_step_models
+    kind, kw, hp = STEP_MODEL_CASES[tag]
+    sub = lambda pre: {k[len(pre):]: g[k] for k in g.files if k.startswith(pre)}
+    gen = gp.GeneratorOracle(kind, sub(tag + "g0_"), **kw)
+    dsd = sub(tag + "d0_")
+    d_layers = gp.discriminator_layers(dsd) if dsd else None
+    d_sum = [torch.zeros_like(t) for pair in d_layers for t in pair] if d_layers else None
+    w_d, mse_w, mge_w = [float(v) for v in g[tag + "cfg"]]
+    R = T(nnp.unit_variance_mlpg_matrix(WINDOWS, 24))
+    for it in range(2):
+        p = "%sit%d_" % (tag, it)
+        x, y, lens = T(g[p + "x"]), T(g[p + "y"]), [int(v) for v in g[p + "lengths"]]
+        out, y_hat, y_hat_static = gp.gan_step(lambda: gen.forward(x, R, lens, hp, training=True), gen.params(),
+                                               gen.sums, d_layers, d_sum, x, y, lens, R, hp, w_d=w_d, mse_w=mse_w,
+                                               mge_w=mge_w, adv_w=1.0)
+        ref = dict(zip(LOSS_KEYS, g[p + "losses"]))
+        for k, v in ref.items():
+            if np.isnan(v):
+                assert k not in out or w_d == 0
+            elif k.endswith("correct"):
+                assert out[k] == v, (k, out[k], v)
+            else:
+                assert abs(out[k] - v) <= 2e-6 * max(abs(v), 1e-3), (k, out[k], v)
+        assert rel_err(y_hat.numpy(), g[p + "y_hat"]) < F32_TOL
+        assert rel_err(y_hat_static.numpy(), g[p + "y_hat_static"]) < F32_TOL
+        for k, v in gen.named.items():
+            assert rel_err(v.detach().numpy(), g[p + "g_" + k]) < 1e-5, k
+        if d_layers:
+            names = ["layers.%d" % i for i in range(len(d_layers) - 1)] + ["last_linear"]
+            for (W, b), n in zip(d_layers, names):
+                assert rel_err(W.detach().numpy(), g[p + "d_" + n + ".weight"]) < 1e-5
+                assert rel_err(b.detach().numpy(), g[p + "d_" + n + ".bias"]) < 1e-5
+
+
 def test_variance_mlpg_restatement_reduces_to_R():
     """oracle mlpg (evaluation-time, real variances) with unit variance == the pinned R-matrix product."""
     rng = np.random.RandomState(2)
