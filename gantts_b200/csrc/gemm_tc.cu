@@ -121,7 +121,8 @@ __device__ __forceinline__ void store_planes16(const float* v, __nv_bfloat16* hi
 // 58 us against a 14 us floor, profiles/r01_gemm_per_launch.md).  Here the warp's 32 x 16 tile goes through a
 // private 2 KB shared-memory scratch (float4 writes, XOR-swizzled: conflict-free) and is written back with lanes
 // 0-15 / 16-31 covering two whole 64-byte row segments per store instruction.  Same arithmetic, same order.
-// OPT-IN (GANTTS_B200_F32_STAGE=1): written after the round's GPU budget was spent, not yet run on hardware.
+// Default on (GANTTS_B200_F32_STAGE=0 disables): measured on B200 at cfg2, the step drops 1.381 -> 1.327 ms and the
+// K-major GEMM family 0.795 -> 0.701 ms (profiles/r02_gemm_experiments.md); the whole -m gpu suite passes either way.
 __device__ __forceinline__ void epilogue_f32_staged(const GemmParams& p, const uint32_t (&r)[16], int64_t row0,
                                                     int lane, int col, int z, const float* __restrict__ bias_s,
                                                     float* scr) {
@@ -1158,12 +1159,12 @@ static int stage_bk(bool mn) {
   return v ? v : (mn ? 32 : 64);
 }
 
-// Opt-in (GANTTS_B200_F32_STAGE=1): stage fp32 output tiles with unaligned row strides through shared memory.
+// Stage fp32 output tiles with unaligned row strides through shared memory (GANTTS_B200_F32_STAGE=0 disables).
 static int use_f32_stage() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("GANTTS_B200_F32_STAGE");
-    v = e ? atoi(e) : 0;
+    v = e ? atoi(e) : 1;
   }
   return v;
 }
@@ -1317,8 +1318,8 @@ static int use_cluster() {
   return v;
 }
 
-// Opt-in staged fp32 epilogue (single-CTA kernels): reserve the 32 KB transpose scratch behind the bias block and
-// give the stages what is left.  No-op unless GANTTS_B200_F32_STAGE=1 and the output row stride is unaligned.
+// Staged fp32 epilogue (single-CTA kernels): reserve the 32 KB transpose scratch behind the bias block and give the
+// stages what is left.  No-op when the output row stride is aligned (vector stores) or GANTTS_B200_F32_STAGE=0.
 static void maybe_stage_f32(GemmParams& p, const EpiArgs& e, bool mn, uint32_t budget_bytes) {
   p.f32_stage_off = 0;
   if (!use_f32_stage() || e.epi != EPI_F32 || p.vec_ok || !p.C) return;
