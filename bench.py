@@ -1,17 +1,24 @@
 """bench.py -- GAN-step frames/sec of the B200 hot path (BASELINE.json metric) + roofline + CPU baseline.
 
-    python bench.py --gpus N --steps K --warmup W            # our arm (N>1 under torchrun)
-    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path (oracle port)
+    python bench.py --gpus N --steps K --warmup W               # our arm (N>1 under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...      # the reference's CPU path (pinned oracle port)
+    python bench.py --workload cfg3|cfg5 ...                     # the recurrent-generator configurations
 
-A "step" is one full GAN training step (reference train.py:538-580: zero_grad, generator forward,
-MLPG, discriminator update, generator update, both clip+Adagrad steps) over one synthetic batch of
-the workload BASELINE.json quotes the metric on: cfg2 = TTS acoustic MLP generator
-(425-512-512-512-187) + MLP discriminator on the 58 masked mgc dims (58-256-256-256-1), B=32 x
-T=1000 padded frames PER GPU (weak scaling), dropout 0.5 in train mode, full-length utterances.
+A "step" is one full GAN training step (reference train.py:538-580: zero_grad, generator forward, MLPG,
+discriminator update, generator update, both clip+Adagrad steps) over one synthetic batch.  Default workload =
+cfg2, the configuration BASELINE.json quotes the metric on: TTS acoustic MLP generator (425-512-512-512-187) + MLP
+discriminator on the 58 masked mgc dims (58-256-256-256-1), B=32 x T=1000 padded frames PER GPU (weak scaling),
+dropout 0.5 in train mode, full-length utterances.  cfg3 = VC In2OutRNNHighwayNet (3 x 512 BiLSTM) + MLP D, B=16 x
+T=2000; cfg5 = TTS LSTMRNN (3 x 512 BiLSTM) + MLP D + MGE, B=64 x T=1500 per GPU.
+
+Timing: W untimed warm-up steps, then the K-step loop is timed with CUDA events between barriers; the loop is
+REPEATED until at least 0.5 s of timed work has accumulated (>= 3 repeats) and the MEDIAN repeat is reported
+(`steps` stays K; a 20-step loop of a 1.3 ms step is 0.03 s, too short to be stable on its own).
 
 One JSON line on stdout (rank 0); see the task contract for the keys.
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -26,27 +33,63 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(1, os.path.join(ROOT, "compat"))
 
-WORKLOAD = dict(B=32, T=1000, d_in=425, d_out=187, g_hidden=512, g_layers=3, d_in_adv=58, d_hidden=256,
-                d_layers=3, dropout_g=0.5, dropout_d=0.5)
-NUM_BATCHES = 4          # ring of distinct synthetic batches (4 x 78 MB > 126 MB L2)
+WINDOWS = [(0, 0, np.array([1.0])), (1, 1, np.array([-0.5, 0.0, 0.5])), (1, 1, np.array([1.0, -2.0, 1.0]))]
+TTS_HP = dict(stream_sizes=[180, 3, 1, 3], has_dynamic_features=[True, True, False, True],
+              adversarial_streams=[True, False, False, False], mask_nth_mgc_for_adv_loss=2, num_windows=3,
+              discriminator_linguistic_condition=False)
+VC_HP = dict(stream_sizes=[177], has_dynamic_features=[True], adversarial_streams=[True], mask_nth_mgc_for_adv_loss=0,
+             num_windows=3, discriminator_linguistic_condition=False)
+
+WORKLOADS = {
+    "cfg2": dict(kind="mlp", B=32, T=1000, d_in=425, d_out=187, g_hidden=512, g_layers=3, d_dims=[58, 256, 256, 256, 1],
+                 dropout_g=0.5, dropout_d=0.5, hp=TTS_HP, uniform_x=True,
+                 text="cfg2: TTS acoustic MLP G 425-512-512-512-187 + MLP D 58-256-256-256-1 (mgc adv, mask_nth=2), "
+                      "B=32 T=1000 per GPU, MGE(MLPG)+ADV, dropout 0.5, Adagrad"),
+    "cfg3": dict(kind="rnn_highway", B=16, T=2000, d_in=177, d_out=177, static_dim=59, g_hidden=512, g_layers=3,
+                 d_dims=[59, 256, 256, 1], dropout_g=0.5, dropout_d=0.5, hp=VC_HP, uniform_x=False,
+                 text="cfg3: VC In2OutRNNHighwayNet 177->177 (static 59, 3 x 512 bidirectional LSTM, dropout 0.5) + MLP D "
+                      "59-256-256-1, B=16 T=2000 per GPU, MGE(MLPG)+ADV, Adagrad"),
+    "cfg5": dict(kind="lstm", B=64, T=1500, d_in=425, d_out=187, g_hidden=512, g_layers=3, d_dims=[58, 256, 256, 256, 1],
+                 dropout_g=0.0, dropout_d=0.5, hp=TTS_HP, uniform_x=True,
+                 text="cfg5: TTS acoustic LSTMRNN 425->187 (3 x 512 bidirectional) + MLP D 58-256-256-256-1 (mgc adv, "
+                      "mask_nth=2), B=64 T=1500 per GPU, MGE(MLPG)+ADV, Adagrad"),
+}
+NUM_BATCHES = 4          # ring of distinct synthetic batches (larger than the 126 MB L2 for every workload)
+MIN_TIMED_SECONDS = 0.5
+MAX_REPEATS = 25
 
 
 def algorithmic_flops_per_frame(w):
-    """MAC/frame = 3 F_G - k0 + 8 F_D - 256 d_in  (de-duplicated GAN step)."""
-    g_dims = [w["d_in"]] + [w["g_hidden"]] * w["g_layers"] + [w["d_out"]]
-    d_dims = [w["d_in_adv"]] + [w["d_hidden"]] * w["d_layers"] + [1]
-    F_G = sum(a * b for a, b in zip(g_dims[:-1], g_dims[1:]))
-    F_D = sum(a * b for a, b in zip(d_dims[:-1], d_dims[1:]))
-    k0 = g_dims[0] * g_dims[1]
-    return 2.0 * (3 * F_G - k0 + 8 * F_D - w["d_hidden"] * w["d_in_adv"])
+    """SURVEY.md 8d, de-duplicated GAN step (1 MAC = 2 FLOP): generator fwd + one bwd (no input gradient), three
+    discriminator forwards, D bwd real (no input gradient) + fake, adv-D bwd (input gradient only):
+    MAC/frame = 3 F_G - k0 + 8 F_D - d_h1 d_in."""
+    dd = w["d_dims"]
+    F_D = sum(a * b for a, b in zip(dd[:-1], dd[1:]))
+    d_part = 8 * F_D - dd[1] * dd[0]
+    if w["kind"] == "mlp":
+        g_dims = [w["d_in"]] + [w["g_hidden"]] * w["g_layers"] + [w["d_out"]]
+        F_G = sum(a * b for a, b in zip(g_dims[:-1], g_dims[1:]))
+        return 2.0 * (3 * F_G - g_dims[0] * g_dims[1] + d_part)
+    H, dirs = w["g_hidden"], 2
+    F_L, inp = 0, w["d_in"]
+    for _ in range(w["g_layers"]):
+        F_L += dirs * 4 * H * (inp + H)
+        inp = dirs * H
+    F_O = dirs * H * w["d_out"]
+    gate = w.get("static_dim", 0) ** 2
+    return 2.0 * (3 * (F_L + F_O) - dirs * 4 * H * w["d_in"] + 2 * gate + d_part)
 
 
-def make_batches(w, seed, n, pinned):
+def make_batches(w, seed, n, pinned, B=None):
     g = torch.Generator().manual_seed(seed)
+    B = B or w["B"]
     out = []
     for _ in range(n):
-        x = torch.rand(w["B"], w["T"], w["d_in"], generator=g) * 0.98 + 0.01
-        y = torch.randn(w["B"], w["T"], w["d_out"], generator=g)
+        if w["uniform_x"]:
+            x = torch.rand(B, w["T"], w["d_in"], generator=g) * 0.98 + 0.01
+        else:
+            x = torch.randn(B, w["T"], w["d_in"], generator=g)
+        y = torch.randn(B, w["T"], w["d_out"], generator=g)
         if pinned:
             x, y = x.pin_memory(), y.pin_memory()
         out.append((x, y))
@@ -71,9 +114,8 @@ class ClockSampler(object):
             import pynvml
             pynvml.nvmlInit()
             self.nvml = pynvml
-            # CUDA_VISIBLE_DEVICES-relative index -> NVML handle through the PCI bus id
-            bus = torch.cuda.get_device_properties(self.index).pci_bus_id if hasattr(
-                torch.cuda.get_device_properties(self.index), "pci_bus_id") else None
+            props = torch.cuda.get_device_properties(self.index)
+            bus = props.pci_bus_id if hasattr(props, "pci_bus_id") else None
             self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.index) if bus is None else None
             if self.handle is None:
                 for i in range(pynvml.nvmlDeviceGetCount()):
@@ -146,41 +188,70 @@ class ClockSampler(object):
 
 # ------------------------------------------------------------------------------ CPU baseline
 def cpu_reference_step_runner(w, sample_B, threads):
-    """The reference's CPU path (oracle port of gantts/*.py + train.py step functions, torch CPU
-    fp32, dense-R MLPG exactly like the reference) on a bounded sample: `sample_B` utterances of the
-    workload's T and widths.  Returns a closure running one step and the frames it processes."""
+    """The reference's CPU path (pinned oracle port of gantts/*.py + train.py step functions, torch CPU fp32,
+    dense-R MLPG exactly like the reference) on `sample_B` utterances of the workload's T and widths.  Returns a
+    closure running one step, the frames it processes and the seconds the dense R construction took."""
     from oracle import gantts_port as gp
     from oracle import nnmnkwii_port as nnp
     torch.set_num_threads(threads)
     torch.manual_seed(1234)
-    mk = lambda i, o: (torch.nn.Linear(i, o).weight.detach().clone(), torch.zeros(o))
-    g_dims = [w["d_in"]] + [w["g_hidden"]] * w["g_layers"] + [w["d_out"]]
-    d_dims = [w["d_in_adv"]] + [w["d_hidden"]] * w["d_layers"] + [1]
-    state = gp.GanStepState([mk(a, b) for a, b in zip(g_dims[:-1], g_dims[1:])],
-                            [mk(a, b) for a, b in zip(d_dims[:-1], d_dims[1:])])
-    hp = dict(stream_sizes=[180, 3, 1, 3], has_dynamic_features=[True, True, False, True],
-              adversarial_streams=[True, False, False, False], mask_nth_mgc_for_adv_loss=2, num_windows=3,
-              discriminator_linguistic_condition=False)
-    windows = [(0, 0, np.array([1.0])), (1, 1, np.array([-0.5, 0.0, 0.5])), (1, 1, np.array([1.0, -2.0, 1.0]))]
-    (x, y), = make_batches(dict(w, B=sample_B), 1234, 1, False)
+    lin = lambda i, o: torch.nn.Linear(i, o)
+    dd = w["d_dims"]
+    d_layers = [(l.weight.detach().clone().requires_grad_(True), l.bias.detach().clone().requires_grad_(True))
+                for l in (lin(a, b) for a, b in zip(dd[:-1], dd[1:]))]
+    d_sum = [torch.zeros_like(t) for pair in d_layers for t in pair]
+    hp = w["hp"]
+    (x, y), = make_batches(w, 1234, 1, False, B=sample_B)
     lens = [w["T"]] * sample_B
-    R = torch.from_numpy(nnp.unit_variance_mlpg_matrix(windows, w["T"]))   # memoised: not re-timed per step
+    t0 = time.perf_counter()
+    R = torch.from_numpy(nnp.unit_variance_mlpg_matrix(WINDOWS, w["T"]))    # train.py:510-513, rebuilt per batch there
+    r_seconds = time.perf_counter() - t0
+    if w["kind"] == "mlp":
+        g_dims = [w["d_in"]] + [w["g_hidden"]] * w["g_layers"] + [w["d_out"]]
+        mods = [lin(a, b) for a, b in zip(g_dims[:-1], g_dims[1:])]
+        sd = {}
+        for i, m in enumerate(mods[:-1]):
+            sd["layers.%d.weight" % i], sd["layers.%d.bias" % i] = m.weight.detach().numpy(), m.bias.detach().numpy()
+        sd["last_linear.weight"], sd["last_linear.bias"] = mods[-1].weight.detach().numpy(), mods[-1].bias.detach().numpy()
+        gen = gp.GeneratorOracle("mlp", sd)
+    else:
+        lstm = torch.nn.LSTM(w["d_in"], w["g_hidden"], w["g_layers"], batch_first=True, bidirectional=True)
+        h2o = lin(2 * w["g_hidden"], w["d_out"])
+        sd = {"lstm." + k: v.detach().numpy() for k, v in lstm.state_dict().items()}
+        sd["hidden2out.weight"], sd["hidden2out.bias"] = h2o.weight.detach().numpy(), h2o.bias.detach().numpy()
+        kw = dict(num_hidden=w["g_layers"], hidden_dim=w["g_hidden"], bidirectional=True)
+        if w["kind"] == "rnn_highway":
+            gate = lin(w["static_dim"], w["static_dim"])
+            sd["T.weight"], sd["T.bias"] = gate.weight.detach().numpy(), gate.bias.detach().numpy()
+            gen = gp.GeneratorOracle("rnn_highway", sd, static_dim=w["static_dim"], **kw)
+        else:
+            gen = gp.GeneratorOracle("lstm", sd, **kw)
 
     def run():
-        gp.gan_step_mlp(state, x, y, lens, R, hp, w_d=1.0, mse_w=0.0, mge_w=1.0, adv_w=1.0,
-                        dropout_g=w["dropout_g"], dropout_d=w["dropout_d"], training=True)
-    return run, sample_B * w["T"]
+        gp.gan_step(lambda: gen.forward(x, R, lens, hp, w["dropout_g"], True), gen.params(), gen.sums, d_layers, d_sum,
+                    x, y, lens, R, hp, w_d=1.0, mse_w=0.0, mge_w=1.0, adv_w=1.0, dropout_d=w["dropout_d"], training=True)
+    return run, sample_B * w["T"], r_seconds
 
 
-def time_cpu_baseline(w, steps, warmup, sample_B=4):
-    """Reference CPU arm.  torch's CPU kernels do not scale to every core of a large host on these
-    shapes (128 threads were 3x slower than 32 on the B200 box), so a one-step probe picks the fastest
-    thread count among {16, 32, 64, all} and the timed run uses it; `cores` reports that choice."""
+def time_cpu_baseline(w, steps, warmup, full_batch):
+    """Reference CPU arm.  torch's CPU kernels do not scale to every core of a large host on these shapes (128
+    threads were 3x slower than 32 on the B200 box), so a one-step probe picks the fastest thread count among
+    {16, 32, 64, all}.  `full_batch`: time the whole B-utterance batch (same config as the GPU arm); when one step of
+    it takes longer than 30 s -- or for the default in-line baseline of the GPU arm -- a bounded sample of utterances
+    is timed instead (frames/s is per padded frame, so the sample measures the same quantity)."""
     ncpu = os.cpu_count() or 1
     cands = sorted(set(min(c, ncpu) for c in (16, 32, 64, ncpu)))
-    best, best_dt = cands[0], None
-    run, frames = cpu_reference_step_runner(w, sample_B, cands[0])
+    small = 2 if w["kind"] != "mlp" else 4
+    sample_B = w["B"] if full_batch else small
+    run, frames, r_s = cpu_reference_step_runner(w, sample_B, cands[0])
+    t0 = time.perf_counter()
     run()                                   # first-touch / allocator warm-up
+    first = time.perf_counter() - t0
+    if full_batch and first > 30.0:
+        sample_B = small
+        run, frames, r_s = cpu_reference_step_runner(w, sample_B, cands[0])
+        run()
+    best, best_dt = cands[0], None
     for c in cands:
         torch.set_num_threads(c)
         t0 = time.perf_counter()
@@ -196,34 +267,40 @@ def time_cpu_baseline(w, steps, warmup, sample_B=4):
         run()
     dt = (time.perf_counter() - t0) / steps
     return {"value": frames / dt, "unit": "frames/s", "cores": best, "kind": "port",
-            "sample": "%d of %d utterances x T=%d per step, %d timed steps, dense-R MLPG with R prebuilt, "
-                      "torch %s CPU fp32, thread count picked from %s of %d host cores by a one-step probe"
-                      % (sample_B, w["B"], w["T"], steps, torch.__version__, cands, ncpu),
-            "ms_per_step": dt * 1e3}
+            "sample": "%d of %d utterances x T=%d per step, %d timed steps, dense-R MLPG with R prebuilt (building R "
+                      "for T=%d takes %.2f s on this host; train.py:510-513 rebuilds it every batch: %.0f frames/s "
+                      "with that included), torch %s CPU fp32, thread count picked from %s of %d host cores by a "
+                      "one-step probe" % (sample_B, w["B"], w["T"], steps, w["T"], r_s, frames / (dt + r_s),
+                                          torch.__version__, cands, ncpu),
+            "ms_per_step": dt * 1e3, "same_config_as_gpu_arm": sample_B == w["B"],
+            "value_with_R_build": frames / (dt + r_s)}
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    w = WORKLOAD
-    steps, warmup = max(1, min(args.steps, 8)), max(1, min(args.warmup, 2))
-    cb = time_cpu_baseline(w, steps, warmup)
+    w = WORKLOADS[args.workload]
+    steps, warmup = max(2, min(args.steps, 4)), max(1, min(args.warmup, 2))
+    cb = time_cpu_baseline(w, steps, warmup, full_batch=True)
     line = {"impl": "reference", "metric": "gan_step_frames_per_sec", "value": cb["value"], "unit": "frames/s",
             "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": cb["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(w, "cpu"), "cpu_baseline": cb,
+            "config": workload_config(w, "cpu", args), "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "gpu_launches": 0,
+            "note": "CPU steps take seconds each: the arm times %d steps after %d warm-up regardless of larger "
+                    "--steps/--warmup so that the run ends within minutes" % (steps, warmup)}
     emit_json_line(line)
 
 
-def workload_config(w, engine):
-    return {"workload": "cfg2: TTS acoustic MLP G 425-512-512-512-187 + MLP D 58-256-256-256-1 (mgc adv, "
-                        "mask_nth=2), B=32 T=1000 per GPU, MGE(MLPG)+ADV, dropout 0.5, Adagrad",
-            "global_batch_per_gpu": w["B"], "seq_len": w["T"], "engine": engine,
-            "l2": "per-step working set ~1.3 GB and a ring of %d distinct input batches (%d MB) exceed the "
-                  "126 MB L2; no explicit flush" % (NUM_BATCHES, NUM_BATCHES * 78),
+def workload_config(w, engine, args=None):
+    bytes_per_batch = w["B"] * w["T"] * (w["d_in"] + w["d_out"]) * 4
+    return {"workload": w["text"], "global_batch_per_gpu": w["B"], "seq_len": w["T"], "engine": engine,
+            "l2": "per-step working set > 1 GB and a ring of %d distinct input batches (%d MB) exceed the 126 MB L2; "
+                  "no explicit flush" % (NUM_BATCHES, NUM_BATCHES * bytes_per_batch // (1 << 20)),
+            "timing": "median of R repeats of the K-step loop (>= 3 repeats and >= %.1f s of timed work), CUDA "
+                      "events, barrier + synchronize on both sides, max over ranks" % MIN_TIMED_SECONDS,
             "parallelism": "utterance-sharded data parallel, one NCCL SUM all-reduce per model per step"}
 
 
@@ -248,8 +325,25 @@ def emit_json_line(line):
 
 
 # ------------------------------------------------------------------------------------ B200 arm
+def build_models(w, dev):
+    import gantts_b200
+    M = gantts_b200.models
+    dd = w["d_dims"]
+    md = M.MLP(dd[0], 1, len(dd) - 2, dd[1], dropout=w["dropout_d"], last_sigmoid=True)
+    if w["kind"] == "mlp":
+        mg = M.MLP(w["d_in"], w["d_out"], w["g_layers"], w["g_hidden"], dropout=w["dropout_g"], last_sigmoid=False)
+    elif w["kind"] == "rnn_highway":
+        mg = M.In2OutRNNHighwayNet(in_dim=w["d_in"], out_dim=w["d_out"], static_dim=w["static_dim"],
+                                   num_hidden=w["g_layers"], hidden_dim=w["g_hidden"], bidirectional=True,
+                                   dropout=w["dropout_g"])
+    else:
+        mg = M.LSTMRNN(in_dim=w["d_in"], out_dim=w["d_out"], num_hidden=w["g_layers"], hidden_dim=w["g_hidden"],
+                       bidirectional=True, dropout=w["dropout_g"], last_sigmoid=False)
+    return mg.to(dev).train(), md.to(dev).train()
+
+
 def run_b200_arm(args):
-    if os.environ.get("GANTTS_B200_DBG", "0") not in ("", "0"):
+    if os.environ.get("GANTTS_B200_DBG", "0") not in ("", "0") or os.environ.get("GANTTS_B200_CHAIN_DBG", "0") not in ("", "0"):
         raise SystemExit("bench.py: GANTTS_B200_DBG is a phase-timing switch that skips work inside the kernels; "
                          "refusing to produce a benchmark line with it set")
     import __graft_entry__
@@ -273,38 +367,50 @@ def run_b200_arm(args):
     from nnmnkwii.paramgen import unit_variance_mlpg_matrix   # compat shim (product side, memoised)
     lib = _lib.load()
     config.engine = args.engine
-    w = WORKLOAD
+    w = WORKLOADS[args.workload]
+    fused_ok = w["kind"] == "mlp"
+    path = args.path if fused_ok else "modular"
     torch.manual_seed(1234)
-    mg = gantts_b200.models.MLP(w["d_in"], w["d_out"], w["g_layers"], w["g_hidden"], dropout=w["dropout_g"],
-                                last_sigmoid=False).to(dev).train()
-    md = gantts_b200.models.MLP(w["d_in_adv"], 1, w["d_layers"], w["d_hidden"], dropout=w["dropout_d"],
-                                last_sigmoid=True).to(dev).train()
-    hp = gstep.TTS_ACOUSTIC
+    mg, md = build_models(w, dev)
+    hpd = w["hp"]
+    hp = gstep.HParams(windows=WINDOWS, stream_sizes=hpd["stream_sizes"], has_dynamic_features=hpd["has_dynamic_features"],
+                       adversarial_streams=hpd["adversarial_streams"],
+                       mask_nth_mgc_for_adv_loss=hpd["mask_nth_mgc_for_adv_loss"],
+                       discriminator_linguistic_condition=False)
     lengths = torch.full((w["B"],), w["T"], dtype=torch.int64, device=dev)
-    frames_global = w["B"] * w["T"] * world
+    frames_per_step = w["B"] * w["T"] * world
 
     class Runner(object):
         """path 'fused': gantts_gan_step (one C call per mini-batch); 'modular': GanTrainer."""
 
         def __init__(self):
-            if args.path == "fused":
+            if path == "fused":
                 from gantts_b200 import fused
                 self.fs = fused.FusedGanStep(mg, md, hp, w["B"], w["T"], w_d=1.0, mse_w=0.0, mge_w=1.0)
             else:
                 self.tr = gstep.GanTrainer(mg, md, hp, w_d=1.0, mse_w=0.0, mge_w=1.0)
                 self.R = torch.from_numpy(unit_variance_mlpg_matrix(hp.windows, w["T"])).to(dev)
 
-        def step(self, x, y, lengths, R=None):
-            if args.path == "fused":
-                losses = self.fs.step(x, y, lengths, frames=frames_global)
-                return {"loss_d": losses[0], "loss_mge": losses[4], "loss_adv": losses[5], "loss_g": losses[6]}, None, None
-            return self.tr.step(x, y, lengths, self.R)
+        def step(self, x, y):
+            if path == "fused":
+                losses = self.fs.step(x, y, lengths, frames=frames_per_step)
+                return {"loss_d": losses[0], "loss_mge": losses[4], "loss_adv": losses[5], "loss_g": losses[6]}
+            return self.tr.step(x, y, lengths, self.R)[0]
+
+        def nccl_warmup(self):
+            if world == 1:
+                return
+            bufs = [self.fs.grad_buffer(0), self.fs.grad_buffer(1)] if path == "fused" else \
+                [self.tr.opt_g.flat_grad, self.tr.opt_d.flat_grad]
+            for _ in range(12):                      # NCCL sets its channels up lazily per message size
+                for b in bufs:
+                    parallel.allreduce_sum_(b)
+            for b in bufs:
+                b.zero_()
 
     trainer = Runner()
-    R = None
     host = make_batches(w, 1234 + rank, NUM_BATCHES, pinned=True)
     resident = [(x.to(dev), y.to(dev)) for x, y in host]
-    frames_per_step = w["B"] * w["T"] * world
 
     def barrier():
         if world > 1:
@@ -317,32 +423,48 @@ def run_b200_arm(args):
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         return float(t.item())
 
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed_repeats(loop):
+        """loop(K) enqueues K steps; returns (median ms per step, list of per-repeat ms per step)."""
+        per, total = [], 0.0
+        while True:
+            barrier()
+            e0.record()
+            loop(args.steps)
+            e1.record()
+            barrier()
+            ms = max_over_ranks(e0.elapsed_time(e1))
+            per.append(ms / args.steps)
+            total += ms
+            if (len(per) >= 3 and total >= MIN_TIMED_SECONDS * 1e3) or len(per) >= MAX_REPEATS:
+                break
+        return float(np.median(per)), per
+
     # ---------------- value: inputs resident in HBM
+    trainer.nccl_warmup()
     for i in range(args.warmup):
-        trainer.step(*resident[i % NUM_BATCHES], lengths, R)
+        trainer.step(*resident[i % NUM_BATCHES])
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    last = {}
+
+    def resident_loop(n):
+        for i in range(n):
+            last["out"] = trainer.step(*resident[i % NUM_BATCHES])
+
     launches0 = lib.gantts_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        out, _, _ = trainer.step(*resident[i % NUM_BATCHES], lengths, R)
-    e1.record()
-    barrier()
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
-    launches = lib.gantts_launch_count() - launches0
+    ms_per_step, repeats = timed_repeats(resident_loop)
+    launches = (lib.gantts_launch_count() - launches0) / float(len(repeats) * args.steps)
     clocks = sampler.stop() if rank == 0 else None
-    ms_per_step = ms_total / args.steps
     value = frames_per_step / (ms_per_step * 1e-3)
-    loss_g = float(out["loss_g"])
-    # ---------------- roofline pass: the same K steps again with CUDA events around every GEMM / MLPG launch
+    loss_g = float(last["out"]["loss_g"])
+    # ---------------- roofline pass: K steps again with CUDA events around every GEMM / chain / MLPG / LSTM launch
     # (kept out of the region `value` is timed on: the event records sit between consecutive kernels)
-    import ctypes
     lib.gantts_profile_enable(1)
-    for i in range(args.steps):
-        trainer.step(*resident[i % NUM_BATCHES], lengths, R)
+    resident_loop(args.steps)
     torch.cuda.synchronize()
     lib.gantts_profile_enable(0)
     pms, pwork, pn = (ctypes.c_double * 8)(), (ctypes.c_double * 8)(), (ctypes.c_longlong * 8)()
@@ -370,26 +492,55 @@ def run_b200_arm(args):
                 prefetch(i + 1)
             slot = i % 2
             torch.cuda.current_stream().wait_event(ready[slot])
-            o, _, _ = trainer.step(bufs[slot][0], bufs[slot][1], lengths, R)
+            o = trainer.step(bufs[slot][0], bufs[slot][1])
             consumed[slot].record()
-            loss_host.copy_(torch.stack([o["loss_g"], o["loss_d"], o["loss_mge"], o["loss_adv"]]), non_blocking=True)
+            loss_host.copy_(torch.stack([o["loss_g"], o["loss_d"], o["loss_mge"], o["loss_adv"]]).detach(),
+                            non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
     for ev in consumed:
         ev.record()
     e2e_loop(max(2, min(args.warmup, 4)))
-    barrier()
-    t0 = time.perf_counter()
-    e0.record()
-    e2e_loop(args.steps)
-    e1.record()
-    barrier()
-    e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    e2e_ms, e2e_repeats = timed_repeats(e2e_loop)
     h2d = sum(t.numel() * 4 for t in host[0])
+
+    # ---------------- drop-in path (cfg2, one process): the reference's own per-batch logic -- tests/trainpy_mirror.py =
+    # train.py:528-580 with its inline BCE, its .item() calls, clip_grad_norm_ and torch.optim.Adagrad -- on the
+    # `gantts` alias package (the B200 modules), dense R on the device as train.py builds it
+    dropin = None
+    if world == 1 and w["kind"] == "mlp" and not args.no_dropin:
+        sys.path.insert(1, os.path.join(ROOT, "tests"))
+        import trainpy_mirror
+        torch.manual_seed(1234)
+        g2, d2 = build_models(w, dev)
+        og = torch.optim.Adagrad(g2.parameters(), lr=0.01, weight_decay=1e-7)
+        od = torch.optim.Adagrad(d2.parameters(), lr=0.01, weight_decay=1e-7)
+        Rd = torch.from_numpy(unit_variance_mlpg_matrix(hp.windows, w["T"])).to(dev)
+        cpu_lengths = [w["T"]] * w["B"]
+
+        def dropin_loop(n):
+            for i in range(n):
+                x, y = resident[i % NUM_BATCHES]
+                trainpy_mirror.train_step(g2, d2, og, od, x, y, lengths, Rd, hp)
+        dropin_loop(3)
+        torch.cuda.synchronize()
+        l0 = lib.gantts_launch_count()
+        n_d = max(10, min(args.steps, 30))
+        t0 = time.perf_counter()
+        dropin_loop(n_d)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / n_d
+        dropin = {"ms_per_step": dt * 1e3, "frames_per_sec": w["B"] * w["T"] / dt,
+                  "native_launches_per_step": (lib.gantts_launch_count() - l0) / n_d, "host_syncs_per_step": 10,
+                  "vs_fused_step": dt * 1e3 / ms_per_step,
+                  "how": "tests/trainpy_mirror.train_step (reference train.py:528-580 re-typed: 10 .item() host "
+                         "syncs, torch clip_grad_norm_, torch.optim.Adagrad) on gantts.models.MLP x 2, dense R "
+                         "resident on the device; wall clock over %d steps" % n_d}
+        del g2, d2, og, od
 
     if rank != 0:
         return
-    # ---------------- roofline of the dominant kernel (tcgen05 GEMM, K-major instance)
+    # ---------------- roofline of the dominant kernel family
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -397,17 +548,27 @@ def run_b200_arm(args):
         pass
     peak_tf = peaks.get("bf16_tflops_sustained") or 1400.0
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)"
-    kinds = {0: "gemm_bf16x3_kernel<K-major>", 1: "gemm_bf16x3_kernel<MN-major>", 2: "mlpg_fwd_kernel", 3: "mlpg_bwd_kernel"}
+    kinds = {0: "gemm_bf16x3_kernel<K-major>", 1: "gemm_bf16x3_kernel<MN-major>", 2: "mlpg_fwd_kernel",
+             3: "mlpg_bwd_kernel", 4: "lstm_fwd_kernel", 5: "lstm_bwd_kernel", 6: "chain_pair_kernel"}
     per_kind = {}
     for k, name in kinds.items():
         if pn[k]:
             per_kind[name] = {"ms_per_step": pms[k] / args.steps, "launches_per_step": pn[k] / args.steps,
-                              "work_per_step": pwork[k] / args.steps}
-    dom = max((0, 1), key=lambda k: pms[k])
+                              "work_per_step": pwork[k] / args.steps,
+                              "achieved": (pwork[k] / (pms[k] * 1e-3)) / (1e9 if k in (2, 3) else 1e12),
+                              "unit": "GB/s" if k in (2, 3) else "TFLOP/s"}
+    tensor_kinds = (0, 1, 6)
+    fam_ms = sum(pms[k] for k in tensor_kinds)
+    fam_work = sum(pwork[k] for k in tensor_kinds)
+    fam_ach = (fam_work / (fam_ms * 1e-3)) / 1e12 if fam_ms else 0.0
+    if w["kind"] == "mlp":
+        dom = max(tensor_kinds, key=lambda k: pms[k])
+    else:
+        dom = max((4, 5), key=lambda k: pms[k])
     ach = (pwork[dom] / (pms[dom] * 1e-3)) / 1e12 if pms[dom] else 0.0
     traffic = None
     try:
-        prof = json.load(open(os.path.join(ROOT, "profiles", "r01_top_kernel.json")))
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r02_top_kernel.json")))
         traffic = prof.get("dram_bytes_per_launch")
     except Exception:
         pass
@@ -416,25 +577,36 @@ def run_b200_arm(args):
                 "note": "achieved = algorithmic fp32-equivalent FLOPs (2MNK per GEMM) / CUDA-event time of the "
                         "launches (second pass of the same K steps with an event pair around every launch); the "
                         "bf16x3 split executes 3 tensor-core MMAs per algorithmic product, so executed bf16 pipe "
-                        "rate = 3 x achieved",
-                "tensor_pipe_frac_executed": 3.0 * ach / peak_tf,
+                        "rate = 3 x achieved" if w["kind"] == "mlp" else
+                        "dominant kernel = the LSTM recurrence (one cooperative launch per layer: T sequential steps, "
+                        "exact-fp32 FFMA with W_hh in registers): latency-bound, reported against the tensor peak as "
+                        "the contract asks; its share of the step is what matters",
+                "tensor_pipe_frac_executed": 3.0 * ach / peak_tf if w["kind"] == "mlp" else None,
+                "gemm_family": {"ms_per_step": fam_ms / args.steps, "achieved_tflops_algorithmic": fam_ach,
+                                "frac_algorithmic": fam_ach / peak_tf, "tensor_pipe_frac_executed": 3.0 * fam_ach / peak_tf,
+                                "launches_per_step": sum(pn[k] for k in tensor_kinds) / args.steps},
                 "share_of_step": (pms[dom] / args.steps) / ms_per_step,
                 "kernels": per_kind}
-    cb = time_cpu_baseline(w, steps=3, warmup=1) if world == 1 and not args.no_cpu_baseline else None
+    cb = None
+    if world == 1 and not args.no_cpu_baseline:
+        cb = time_cpu_baseline(w, steps=3 if w["kind"] == "mlp" else 2, warmup=1, full_batch=False)
     line = {"metric": "gan_step_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 (GEMMs: bf16x3 split on tcgen05, fp32 accumulate)" if args.engine == "tc" else "f32",
-            "data": "synthetic", "config": workload_config(w, args.engine), "clocks": clocks,
+            "data": "synthetic", "config": workload_config(w, args.engine, args), "clocks": clocks,
+            "timed_repeats": {"n": len(repeats), "ms_per_step_min": min(repeats), "ms_per_step_max": max(repeats)},
             "e2e": {"value": frames_per_step / (e2e_ms * 1e-3), "unit": "frames/s", "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16, "repeats": len(e2e_repeats),
                     "how": "pinned host x,y -> double-buffered cudaMemcpyAsync on a copy stream -> one step through the "
-                           "public API (%s) -> 4 loss scalars D2H; copies inside the timed region" % args.path},
-            "gpu_launches": int(launches), "gpu_launches_per_step": launches / args.steps,
+                           "public API (%s) -> 4 loss scalars D2H; copies inside the timed region" % path},
+            "gpu_launches": int(round(launches * args.steps)), "gpu_launches_per_step": launches,
             "algorithmic_gflop_per_step": algorithmic_flops_per_frame(w) * w["B"] * w["T"] / 1e9,
             "step_tflops_algorithmic": algorithmic_flops_per_frame(w) * frames_per_step / (ms_per_step * 1e-3) / 1e12 / world,
             "roofline": roofline, "loss_g_last": loss_g,
-            "path": "gantts_gan_step (one C call per mini-batch)" if args.path == "fused" else "GanTrainer (python-orchestrated native ops)"}
+            "path": "gantts_gan_step (one C call per mini-batch)" if path == "fused" else "GanTrainer (python-orchestrated native ops)"}
+    if dropin is not None:
+        line["dropin"] = dropin
     if cb is not None:
         line["cpu_baseline"] = cb
     emit_json_line(line)
@@ -443,14 +615,18 @@ def run_b200_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--engine", default=os.environ.get("GANTTS_B200_ENGINE", "tc"), choices=["tc", "simt"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-dropin", action="store_true")
     ap.add_argument("--path", default="fused", choices=["fused", "modular"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.workload != "cfg2" and args.steps > 10:
+        args.steps = 10                    # recurrent workloads: ~0.1 - 1 s per step
     if args.impl == "reference":
         run_reference_arm(args)
     else:

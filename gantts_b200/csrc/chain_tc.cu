@@ -78,6 +78,8 @@ struct ChainParams {
   int64_t ldc;
   int64_t c_row0;
   int c_accumulate;
+  uint32_t dbg;   // timing experiments (GANTTS_B200_CHAIN_DBG): 1 no HBM plane/code stores, 2 no dropout hash, 4 no proxy fence,
+                  // 8 no shared-memory A stores, 16 no MMAs -- RESULTS ARE WRONG with any bit set
 };
 
 struct ChainMaps {
@@ -279,7 +281,7 @@ chain_pair_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
               ptx::tc_fence_after();
               const uint32_t sb_hi = ring0 + s * CH_SLOT, sb_lo = sb_hi + 8192u;
 #pragma unroll
-              for (int k = 0; k < 2; ++k) {
+              for (int k = 0; k < ((p.dbg & 16u) ? 0 : 2); ++k) {
                 const uint32_t ao = (uint32_t)(half * 2 + k) * 32u, bo = (uint32_t)k * 32u;
                 const uint64_t da_hi = ptx::make_smem_desc(a_hi + ao, 0u, 1024u, 2u);
                 const uint64_t da_lo = ptx::make_smem_desc(a_lo + ao, 0u, 1024u, 2u);
@@ -387,7 +389,7 @@ chain_pair_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
             }
 #pragma unroll
             for (int e = 0; e < 16; ++e) v[e] = fmaxf(v[e], v[e] * p.slope);
-            if (p.thresh) {
+            if (p.thresh && !(p.dbg & 2u)) {
               const uint32_t half_n = (uint32_t)(L.n_valid + 1) >> 1;
 #pragma unroll
               for (int e = 0; e < 16; e += 2) {
@@ -407,8 +409,8 @@ chain_pair_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
               if (v[e] == 0.f) code |= 1u << (2 * e);
               if (v[e] < 0.f) code |= 2u << (2 * e);
             }
-            if (feeds_next) store_a_chunk16(base + c * CH_A_CHUNK, r, j * 16, v);
-            if (row_ok && col < L.n_valid) {
+            if (feeds_next && !(p.dbg & 8u)) store_a_chunk16(base + c * CH_A_CHUNK, r, j * 16, v);
+            if (row_ok && col < L.n_valid && !(p.dbg & 1u)) {
               if (L.out_hi)
                 store_planes16(v, L.out_hi + row * L.out_pitch + col, L.out_lo + row * L.out_pitch + col, col, L.out_pitch);
               if (L.code) L.code[row * L.code_pitch + c * 4 + j] = code;
@@ -417,7 +419,7 @@ chain_pair_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
 #pragma unroll
               for (int e = 0; e < 16; ++e) gemv = fmaf(v[e], vec_s[col + e], gemv);
             }
-          } else if (!last || p.C == nullptr) {
+          } else if (l != NL - 1 || p.C == nullptr) {
             // gZ_{l-1} = acc * act'(H_l): derivative class from the saved 2-bit codes
             const float dpos = p.keep_scale, dneg = p.slope * p.keep_scale, dzero = p.thresh ? 0.f : p.slope;
 #pragma unroll
@@ -425,8 +427,8 @@ chain_pair_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
               const uint32_t ce = (cw[c] >> (2 * e)) & 3u;
               v[e] *= (ce & 1u) ? dzero : ((ce & 2u) ? dneg : dpos);
             }
-            if (feeds_next) store_a_chunk16(base + c * CH_A_CHUNK, r, j * 16, v);
-            if (L.out_hi && row_ok && col < L.n_valid)
+            if (feeds_next && !(p.dbg & 8u)) store_a_chunk16(base + c * CH_A_CHUNK, r, j * 16, v);
+            if (L.out_hi && row_ok && col < L.n_valid && !(p.dbg & 1u))
               store_planes16(v, L.out_hi + row * L.out_pitch + col, L.out_lo + row * L.out_pitch + col, col, L.out_pitch);
           } else {
             // input gradient: fp32, rows >= c_row0, optionally accumulated into a column window of a wider matrix
@@ -438,7 +440,7 @@ chain_pair_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
             }
           }
           if (feeds_next) {
-            ptx::fence_proxy_async();
+            if (!(p.dbg & 4u)) ptx::fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
               if (leader) ptx::mbar_arrive(aready0 + 8 * c);
@@ -497,8 +499,22 @@ static bool chain_shape_ok(const gantts_mlp_t* m) {
   return true;
 }
 
+static uint32_t chain_dbg() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GANTTS_B200_CHAIN_DBG");
+    v = e ? atoi(e) : 0;
+    if (v)
+      fprintf(stderr, "gantts_b200: GANTTS_B200_CHAIN_DBG=%d removes parts of the chain kernel (phase timing only): "
+                      "RESULTS ARE WRONG, do not use for training or benchmarks\n", v);
+  }
+  return (uint32_t)v;
+}
+
 template <bool BWD>
-static int launch_chain(const ChainMaps& maps, const ChainParams& p, cudaStream_t st) {
+static int launch_chain(const ChainMaps& maps, const ChainParams& p_in, cudaStream_t st) {
+  ChainParams p = p_in;
+  p.dbg = chain_dbg();
   static bool attr[64] = {};
   const int dev = current_device();
   if (dev < 0 || dev >= 64 || !attr[dev]) {
@@ -509,7 +525,7 @@ static int launch_chain(const ChainMaps& maps, const ChainParams& p, cudaStream_
   int grid = (int)(tiles * 2 < num_sms() ? tiles * 2 : num_sms() / 2 * 2);
   double flops = 0.0;
   for (int l = 0; l < p.num_layers; ++l) flops += 2.0 * (double)p.M * p.L[l].n_valid * (double)p.L[l].K;
-  prof_begin(PROF_GEMM_KK, flops, st);
+  prof_begin(PROF_CHAIN, flops, st);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(TC_THREADS);

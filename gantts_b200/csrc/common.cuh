@@ -37,7 +37,8 @@ int cuda_fail(cudaError_t e, const char* what);
 // Kernel-launch counter (gantts_launch_count) and optional CUDA-event profiling of selected kernels
 // (gantts_profile_*): event pairs are recorded on the launching stream around each profiled launch.
 void count_launch();
-enum ProfKind { PROF_GEMM_KK = 0, PROF_GEMM_MN = 1, PROF_MLPG_FWD = 2, PROF_MLPG_BWD = 3, PROF_KINDS = 8 };
+enum ProfKind { PROF_GEMM_KK = 0, PROF_GEMM_MN = 1, PROF_MLPG_FWD = 2, PROF_MLPG_BWD = 3, PROF_LSTM_FWD = 4,
+                PROF_LSTM_BWD = 5, PROF_CHAIN = 6, PROF_KINDS = 8 };
 void prof_begin(int kind, double work, cudaStream_t st);   // work: algorithmic flops or bytes
 void prof_end(cudaStream_t st);
 

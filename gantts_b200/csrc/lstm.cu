@@ -576,7 +576,10 @@ static int lstm_launch(bool bwd, LstmParams& p, cudaStream_t st) {
   GANTTS_CUDA(cudaMemsetAsync(p.bar, 0, 4 * sizeof(unsigned int), st));
   void* args[] = {&p};
   dim3 grid(p.slices * p.ndir), block(LSTM_THREADS);
+  // work = recurrent-matmul flops: 2 * B * T * dirs * 4H * H forward, twice that backward (dh and the gate chain)
+  prof_begin(bwd ? PROF_LSTM_BWD : PROF_LSTM_FWD, (bwd ? 2.0 : 1.0) * 8.0 * p.B * (double)p.T * p.ndir * (double)H * H, st);
   cudaError_t e = cudaLaunchCooperativeKernel(fn, grid, block, args, smem, st);
+  prof_end(st);
   if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchCooperativeKernel(lstm)");
   count_launch();
   return GANTTS_OK;
@@ -609,7 +612,9 @@ static int lstm_launch_reg(bool bwd, LstmParams& p, cudaStream_t st) {
   GANTTS_CUDA(cudaMemsetAsync(p.bar, 0, 4 * sizeof(unsigned int), st));
   void* args[] = {&p};
   dim3 grid(p.slices * p.ndir), block(LSTM_THREADS);
+  prof_begin(bwd ? PROF_LSTM_BWD : PROF_LSTM_FWD, (bwd ? 2.0 : 1.0) * 8.0 * p.B * (double)p.T * p.ndir * (double)H * H, st);
   cudaError_t e = cudaLaunchCooperativeKernel(fn, grid, block, args, smem, st);
+  prof_end(st);
   if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchCooperativeKernel(lstm reg)");
   count_launch();
   return GANTTS_OK;
