@@ -4,29 +4,34 @@
 //
 //   forward  (BWD = false):  H_{l+1} = Dropout(LeakyReLU(H_l W_l^T + b_l)),  y = sigmoid(H_L w + b)
 //       A_0 (input planes) arrives by TMA; the epilogue of layer l converts the fp32 accumulator (TMEM) into bf16
-//       hi/lo planes and writes them (a) into shared memory in the UMMA K-major SWIZZLE_128B layout as the A
-//       operand of layer l+1 and (b) to the tape in HBM (planes + 2-bit derivative codes) for the backward.  The
-//       last hidden layer's epilogue folds the single-output Linear + sigmoid (a GEMV) in.
+//       hi/lo planes and writes them into shared memory in the UMMA K-major SWIZZLE_128B layout: that tile is (a) the
+//       A operand of layer l+1 and (b) the source of a TMA bulk store to the tape in HBM (planes for the backward;
+//       the 2-bit derivative codes go out with ordinary stores).  The last hidden layer's epilogue folds the
+//       single-output Linear + sigmoid (a GEMV) in.
 //   backward (BWD = true):   gZ_{l-1} = (gZ_l W_l) * act'(H_l),  gx = gZ_0 W_0
 //       the head gZ_L = (gy * sigma'(y)) w^T * act'(H_L) is produced by the epilogue warps straight into shared
-//       memory (it is elementwise in gy, w and the saved codes); gradient planes are written to HBM only when the
+//       memory (it is elementwise in gy, w and the saved codes); gradient planes are stored to HBM only when the
 //       weight-gradient GEMMs need them; the last layer's fp32 result may be accumulated into a column window of a
 //       wider matrix (the scatter into g_static of the fused step).
 //
 // Only the weights stream (L2-resident, 0.6 MB): per pair tile the L2 -> SM operand traffic halves and the HBM
 // traffic drops to the tape writes.  Pipeline per CTA pair (persistent, one pair tile = 2 x 128 rows):
-//   warp 0   TMA producer: ring of 16 KB slots carrying, in consumption order, [A_0 hi, A_0 lo,] then for every layer
-//            and every 32-wide reduction block the CTA's half of the weight tile (N/2 rows, hi+lo, SWIZZLE_64B)
-//   warp 1   MMA issuer (leader CTA): 3 tcgen05.mma (hi*hi, hi*lo, lo*hi) per K=16 step, accumulators ping-pong
-//            between two 256-column TMEM buffers, so the MMAs of layer l+1 start as soon as the epilogue of layer l has
-//            delivered the FIRST 64-column chunk of its output (chunk c of the output = reduction chunk c of l+1)
+//   warp 0      TMA producer: ring of 16 KB slots carrying, in consumption order, [A_0 hi, A_0 lo,] then for every layer
+//               and every 32-wide reduction block the CTA's half of the weight tile (N/2 rows, hi+lo, SWIZZLE_64B)
+//   warp 1      MMA issuer (leader CTA): 3 tcgen05.mma (hi*hi, hi*lo, lo*hi) per K=16 step, accumulators ping-pong
+//               between two 256-column TMEM buffers, so the MMAs of layer l+1 start as soon as the epilogue of layer l
+//               has delivered the FIRST 64-column chunk of its output (chunk c of the output = reduction chunk c of l+1)
 //   warps 2-17  epilogue: all sixteen warps work on the same 64-column chunk (16 columns each), chunk after chunk
+//   warp 18     plane store: one thread issues the TMA bulk stores of each finished chunk and tells the epilogue warps
+//               when the shared-memory tile may be overwritten
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
 namespace gantts {
 
 constexpr int CH_MAX_LAYERS = 4;               // MMA layers per chain
+constexpr int CH_THREADS = TC_THREADS + 32;    // + the plane-store warp
+constexpr int CH_STORE_WARP = TC_THREADS / 32;
 constexpr uint32_t CH_SLOT = 16384;            // ring slot: 128 rows x 128 B (A_0 plane) or 2 x [128 rows x 64 B] (B hi|lo)
 constexpr int CH_SLOTS = 5;
 constexpr uint32_t CH_A_CHUNK = 32768;         // one 64-wide K chunk of A: hi 16 KB | lo 16 KB
@@ -43,8 +48,7 @@ struct ChainLayer {
   int n_valid;           // real output columns
   int K;                 // reduction extent, padded to a multiple of 64 (<= 256)
   const float* bias;     // fwd: [n_valid]
-  __nv_bfloat16 *out_hi, *out_lo;   // output planes in HBM (fwd: tape H_{l+1}; bwd: gZ for the weight gradients) or null
-  int64_t out_pitch;
+  int store_planes;      // the layer's output planes go to HBM (ChainMaps::s_hi/s_lo: fwd tape H_{l+1}; bwd gZ planes)
   uint32_t* code;        // fwd: derivative codes of this layer's output (written); bwd: codes of H_l (read), null on the last
   int64_t code_pitch;
   uint64_t seed;         // fwd: dropout seed of this layer
@@ -71,20 +75,19 @@ struct ChainParams {
   int head_valid;                       // real number of head columns (w_head entries)
   const uint32_t* code_head;
   int64_t code_head_pitch;
-  __nv_bfloat16 *head_hi, *head_lo;     // optional copy of the head planes in HBM
-  int64_t head_pitch;
   // backward tail: fp32 result of the last layer, rows >= c_row0 only
   float* C;
   int64_t ldc;
   int64_t c_row0;
   int c_accumulate;
-  uint32_t dbg;   // timing experiments (GANTTS_B200_CHAIN_DBG): 1 no HBM plane/code stores, 2 no dropout hash, 4 no proxy fence,
+  uint32_t dbg;   // timing experiments (GANTTS_B200_CHAIN_DBG): 1 no plane/code stores, 2 no dropout hash, 4 no proxy fence,
                   // 8 no shared-memory A stores, 16 no MMAs -- RESULTS ARE WRONG with any bit set
 };
 
 struct ChainMaps {
-  CUtensorMap a_hi, a_lo;                        // forward input planes, box [128 rows][64]
-  CUtensorMap b_hi[CH_MAX_LAYERS], b_lo[CH_MAX_LAYERS];   // weight planes, box [N/2 rows][32]
+  CUtensorMap a_hi, a_lo;                                   // forward input planes, box [128 rows][64]
+  CUtensorMap b_hi[CH_MAX_LAYERS], b_lo[CH_MAX_LAYERS];     // weight planes, box [N/2 rows][32]
+  CUtensorMap s_hi[CH_MAX_LAYERS], s_lo[CH_MAX_LAYERS];     // output planes of layer l (store), box [128 rows][64]
 };
 
 namespace ptx {
@@ -117,6 +120,17 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+// 2D tile store shared -> global (bulk async-group completion)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all committed bulk groups of this thread have finished READING their shared-memory source
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 }  // namespace ptx
 
 // 16 fp32 values of row `r` (0..127 within the CTA), columns [kcol, kcol+16) of a 64-wide chunk -> the chunk's hi and lo
@@ -135,7 +149,7 @@ __device__ __forceinline__ void store_a_chunk16(uint32_t chunk_base, int r, int 
 }
 
 template <bool BWD>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1)
 chain_pair_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
@@ -148,8 +162,10 @@ chain_pair_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
   const uint32_t bar0 = base + CH_OFF_BAR;
   const uint32_t full0 = bar0, empty0 = bar0 + 8 * CH_SLOTS;            // ring
   const uint32_t tfull0 = bar0 + 16 * CH_SLOTS, tempty0 = tfull0 + 16;  // accumulators (2 each)
-  const uint32_t aready0 = tempty0 + 16;                                // A chunk c written by the epilogue warps (4)
-  const uint32_t tmem_slot = aready0 + 32;
+  const uint32_t aready0 = tempty0 + 16;     // A chunk c written by the epilogue warps of BOTH CTAs (4, leader's copy)
+  const uint32_t cready0 = aready0 + 32;     // chunk c written by THIS CTA's epilogue warps: ready for the plane store (4)
+  const uint32_t sfree0 = cready0 + 32;      // the plane stores of a layer have finished reading shared memory (1)
+  const uint32_t tmem_slot = sfree0 + 8;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t crank = ptx::cluster_ctarank();
   const bool leader = crank == 0;
@@ -164,7 +180,11 @@ chain_pair_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
       ptx::mbar_init(tfull0 + 8 * a, 1);
       ptx::mbar_init(tempty0 + 8 * a, 2 * TC_EPI_WARPS);     // both CTAs' epilogue warps (leader's copy is used)
     }
-    for (int c = 0; c < 4; ++c) ptx::mbar_init(aready0 + 8 * c, 2 * TC_EPI_WARPS);
+    for (int c = 0; c < 4; ++c) {
+      ptx::mbar_init(aready0 + 8 * c, 2 * TC_EPI_WARPS);
+      ptx::mbar_init(cready0 + 8 * c, TC_EPI_WARPS);
+    }
+    ptx::mbar_init(sfree0, 1);
     ptx::fence_barrier_init();
     if (!BWD) {
       ptx::prefetch_tensormap(&maps.a_hi);
@@ -173,6 +193,10 @@ chain_pair_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
     for (int l = 0; l < NL; ++l) {
       ptx::prefetch_tensormap(&maps.b_hi[l]);
       ptx::prefetch_tensormap(&maps.b_lo[l]);
+      if (p.L[l].store_planes) {
+        ptx::prefetch_tensormap(&maps.s_hi[l]);
+        ptx::prefetch_tensormap(&maps.s_lo[l]);
+      }
     }
   }
   if (warp == 1) {
@@ -182,14 +206,14 @@ chain_pair_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
   ptx::pdl_launch_dependents();
   ptx::pdl_wait();
   if (!BWD) {
-    for (int i = threadIdx.x; i < NL * 256; i += TC_THREADS) {
+    for (int i = threadIdx.x; i < NL * 256; i += CH_THREADS) {
       const int l = i >> 8, c = i & 255;
       bias_s[i] = (c < p.L[l].n_valid && p.L[l].bias) ? p.L[l].bias[c] : 0.f;
     }
     if (p.w_last)
-      for (int i = threadIdx.x; i < 256; i += TC_THREADS) vec_s[i] = i < p.L[NL - 1].n_valid ? p.w_last[i] : 0.f;
+      for (int i = threadIdx.x; i < 256; i += CH_THREADS) vec_s[i] = i < p.L[NL - 1].n_valid ? p.w_last[i] : 0.f;
   } else {
-    for (int i = threadIdx.x; i < 256; i += TC_THREADS) vec_s[i] = (i < p.head_valid && p.w_head) ? p.w_head[i] : 0.f;
+    for (int i = threadIdx.x; i < 256; i += CH_THREADS) vec_s[i] = (i < p.head_valid && p.w_head) ? p.w_head[i] : 0.f;
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -205,6 +229,7 @@ chain_pair_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
     if (BWD && (tile + 1) * (2 * TC_BM) <= p.c_row0) return NL - 1;
     return NL;
   };
+  const bool no_store = (p.dbg & 1u) != 0;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -305,6 +330,29 @@ chain_pair_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
         }
       }
     }
+  } else if (warp == CH_STORE_WARP) {
+    if (lane == 0 && !no_store) {
+      // ------------------------------------------------------------ plane store (both CTAs, own 128 rows)
+      uint32_t cr_par = 0;               // bit c = parity of the next phase of cready[c]
+      for (int64_t tile = first_tile; tile < num_tiles; tile += tile_step) {
+        const int32_t row0 = (int32_t)(tile * 2 * TC_BM + (int64_t)crank * TC_BM);
+        const int nl = layers_of_tile(tile);
+        for (int l = 0; l < nl; ++l) {
+          if (!p.L[l].store_planes) continue;
+          const int nch = p.L[l].N / 64;
+          for (int c = 0; c < nch; ++c) {
+            ptx::mbar_wait(cready0 + 8 * c, (cr_par >> c) & 1u);
+            cr_par ^= 1u << c;
+            ptx::tma_store_2d(&maps.s_hi[l], base + c * CH_A_CHUNK, c * 64, row0);
+            ptx::tma_store_2d(&maps.s_lo[l], base + c * CH_A_CHUNK + 16384u, c * 64, row0);
+            ptx::bulk_commit();
+          }
+          ptx::bulk_wait_read0();         // shared memory of this layer's tile has been read out
+          ptx::mbar_arrive(sfree0);
+        }
+      }
+      ptx::bulk_wait0();                  // every store has landed before the CTA retires
+    }
   } else {
     // -------------------------------------------------------------- epilogue warps (both CTAs, own 128 rows)
     const int q = warp & 3;                  // TMEM lane quarter this warp may access
@@ -313,7 +361,28 @@ chain_pair_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
     const uint32_t aready_leader = ptx::mapa(aready0, 0);
     const uint32_t tempty_leader = ptx::mapa(tempty0, 0);
     uint32_t acc_cnt = 0;
-    // backward head of one tile: gZ_head chunk by chunk into shared memory (and optionally to HBM)
+    uint32_t st_issued = 0, st_waited = 0;   // layers handed to the store warp / whose sfree phase has been consumed
+    // before the A buffer is overwritten: every plane store issued so far must have read it out
+    auto wait_stores = [&]() {
+      while (st_waited < st_issued) {
+        if (lane == 0) ptx::mbar_wait(sfree0, st_waited & 1u);
+        __syncwarp();
+        ++st_waited;
+      }
+    };
+    // chunk c of the A buffer is complete as far as this warp is concerned
+    auto publish = [&](int c, bool to_mma, bool to_store) {
+      if (!(p.dbg & 4u)) ptx::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        if (to_mma) {
+          if (leader) ptx::mbar_arrive(aready0 + 8 * c);
+          else ptx::mbar_arrive_cluster(aready_leader + 8 * c);
+        }
+        if (to_store) ptx::mbar_arrive(cready0 + 8 * c);
+      }
+    };
+    // backward head of one tile: gZ_head chunk by chunk into shared memory
     auto head = [&](int64_t tile) {
       const int64_t row = tile * 2 * TC_BM + (int64_t)crank * TC_BM + r;
       const bool row_ok = row < p.M;
@@ -330,6 +399,7 @@ chain_pair_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
       if (row_ok)
         for (int c = 0; c < nch; ++c) cw[c] = __ldg(p.code_head + row * p.code_head_pitch + c * 4 + j);
       const float dpos = p.keep_scale, dneg = p.slope * p.keep_scale, dzero = p.thresh ? 0.f : p.slope;
+      wait_stores();
       for (int c = 0; c < nch; ++c) {
         const int col = c * 64 + j * 16;
         float v[16];
@@ -339,14 +409,7 @@ chain_pair_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
           v[e] = g * vec_s[col + e] * ((ce & 1u) ? dzero : ((ce & 2u) ? dneg : dpos));
         }
         store_a_chunk16(base + c * CH_A_CHUNK, r, j * 16, v);
-        if (p.head_hi && row_ok && col < p.head_valid)
-          store_planes16(v, p.head_hi + row * p.head_pitch + col, p.head_lo + row * p.head_pitch + col, col, p.head_pitch);
-        ptx::fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) {
-          if (leader) ptx::mbar_arrive(aready0 + 8 * c);
-          else ptx::mbar_arrive_cluster(aready_leader + 8 * c);
-        }
+        publish(c, true, false);
       }
     };
     if (BWD && first_tile < num_tiles) head(first_tile);
@@ -359,6 +422,9 @@ chain_pair_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
         const int acc = acc_cnt & 1;
         const bool last = l == nl - 1;
         const bool feeds_next = !last;                       // output is the A operand of layer l+1
+        const bool is_out = BWD && l == NL - 1 && p.C != nullptr;          // fp32 input gradient, no planes
+        const bool to_store = !is_out && L.store_planes && !no_store;
+        const bool to_smem = (feeds_next || to_store) && !(p.dbg & 8u);
         const int nch = L.N / 64;
         // backward: derivative codes of this layer's output columns (act' of H_l), prefetched before the wait
         uint32_t cw[4] = {0u, 0u, 0u, 0u};
@@ -366,19 +432,18 @@ chain_pair_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
           for (int c = 0; c < nch; ++c) cw[c] = __ldg(L.code + row * L.code_pitch + c * 4 + j);
         ptx::mbar_wait(tfull0 + 8 * acc, (acc_cnt >> 1) & 1);
         ptx::tc_fence_after();
-        // backward: the A buffer is free once the LAST layer's MMAs are done -> start the next tile's head first,
+        // backward: the A buffer is free once the LAST layer's MMAs are done -> produce the next tile's head first,
         // so that its first MMAs run under this tile's last epilogue
         if (BWD && last && tile + tile_step < num_tiles) head(tile + tile_step);
+        if (to_smem) wait_stores();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256;
         float gemv = 0.f;
-        for (int c = 0; c < nch; ++c) {
+        // one 16-column piece of chunk c: accumulator registers -> activation / gradient -> shared memory (+ codes)
+        auto process = [&](int c, const uint32_t (&src)[16]) {
           const int col = c * 64 + j * 16;
-          uint32_t rr[16];
-          ptx::tmem_ld16(taddr + col, rr);
-          ptx::tmem_ld_wait();
           float v[16];
 #pragma unroll
-          for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(rr[e]);
+          for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(src[e]);
           if (!BWD) {
             // reference gantts/models.py:137-139: Dropout(LeakyReLU(Linear(x)))
             const float* bs = bias_s + l * 256 + col;
@@ -409,17 +474,13 @@ chain_pair_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
               if (v[e] == 0.f) code |= 1u << (2 * e);
               if (v[e] < 0.f) code |= 2u << (2 * e);
             }
-            if (feeds_next && !(p.dbg & 8u)) store_a_chunk16(base + c * CH_A_CHUNK, r, j * 16, v);
-            if (row_ok && col < L.n_valid && !(p.dbg & 1u)) {
-              if (L.out_hi)
-                store_planes16(v, L.out_hi + row * L.out_pitch + col, L.out_lo + row * L.out_pitch + col, col, L.out_pitch);
-              if (L.code) L.code[row * L.code_pitch + c * 4 + j] = code;
-            }
+            if (to_smem) store_a_chunk16(base + c * CH_A_CHUNK, r, j * 16, v);
+            if (L.code && row_ok && col < L.n_valid && !no_store) L.code[row * L.code_pitch + c * 4 + j] = code;
             if (last && p.w_last) {
 #pragma unroll
               for (int e = 0; e < 16; ++e) gemv = fmaf(v[e], vec_s[col + e], gemv);
             }
-          } else if (l != NL - 1 || p.C == nullptr) {
+          } else if (!is_out) {
             // gZ_{l-1} = acc * act'(H_l): derivative class from the saved 2-bit codes
             const float dpos = p.keep_scale, dneg = p.slope * p.keep_scale, dzero = p.thresh ? 0.f : p.slope;
 #pragma unroll
@@ -427,9 +488,7 @@ chain_pair_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
               const uint32_t ce = (cw[c] >> (2 * e)) & 3u;
               v[e] *= (ce & 1u) ? dzero : ((ce & 2u) ? dneg : dpos);
             }
-            if (feeds_next && !(p.dbg & 8u)) store_a_chunk16(base + c * CH_A_CHUNK, r, j * 16, v);
-            if (L.out_hi && row_ok && col < L.n_valid && !(p.dbg & 1u))
-              store_planes16(v, L.out_hi + row * L.out_pitch + col, L.out_lo + row * L.out_pitch + col, col, L.out_pitch);
+            if (to_smem) store_a_chunk16(base + c * CH_A_CHUNK, r, j * 16, v);
           } else {
             // input gradient: fp32, rows >= c_row0, optionally accumulated into a column window of a wider matrix
             if (row_ok && row >= p.c_row0) {
@@ -439,15 +498,22 @@ chain_pair_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
                 if (col + e < L.n_valid) crow[e] = p.c_accumulate ? crow[e] + v[e] : v[e];
             }
           }
-          if (feeds_next) {
-            if (!(p.dbg & 4u)) ptx::fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) {
-              if (leader) ptx::mbar_arrive(aready0 + 8 * c);
-              else ptx::mbar_arrive_cluster(aready_leader + 8 * c);
-            }
+          if (feeds_next || to_store) publish(c, feeds_next, to_store);
+        };
+        // two register sets: the next chunk's accumulator columns travel (tcgen05.ld) while this one is processed
+        uint32_t ra[16], rb[16];
+        ptx::tmem_ld16(taddr + j * 16, ra);
+        for (int c = 0; c < nch; c += 2) {
+          ptx::tmem_ld_wait();
+          if (c + 1 < nch) ptx::tmem_ld16(taddr + (c + 1) * 64 + j * 16, rb);
+          process(c, ra);
+          if (c + 1 < nch) {
+            ptx::tmem_ld_wait();
+            if (c + 2 < nch) ptx::tmem_ld16(taddr + (c + 2) * 64 + j * 16, ra);
+            process(c + 1, rb);
           }
         }
+        if (to_store) ++st_issued;
         // accumulator drained
         ptx::tc_fence_before();
         __syncwarp();
@@ -478,21 +544,26 @@ chain_pair_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
 }
 
 // ---------------------------------------------------------------------------- host side
+// Where the chain kernel replaces the per-layer launches (GANTTS_B200_CHAIN, bit mask): 1 = forward, 2 = backward
+// without weight gradients (the adversarial pass: nothing but the input gradient leaves the chip), 4 = backward with
+// weight gradients (the gradient planes still go to HBM for the weight-gradient GEMMs).  Measured on B200 at cfg2
+// (profiles/r02_chain.md).
+constexpr int CHAIN_FWD = 1, CHAIN_BWD_NOGRAD = 2, CHAIN_BWD_GRAD = 4;
 static int use_chain() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("GANTTS_B200_CHAIN");
-    v = e ? atoi(e) : 1;
+    v = e ? atoi(e) : (CHAIN_FWD | CHAIN_BWD_NOGRAD);
   }
   return v;
 }
 
 static inline int pad64(int v) { return (v + 63) / 64 * 64; }
 
-// Shapes the chain kernel covers: input width <= 64, hidden widths <= 256, a single output column, 1..4 hidden layers.
-static bool chain_shape_ok(const gantts_mlp_t* m) {
+// Shapes the chain kernel covers: input width <= 64, hidden widths <= 256, a single output column, 2..4 hidden layers.
+static bool chain_shape_ok(const gantts_mlp_t* m, int mode) {
   const int L = m->num_layers;
-  if (!use_chain() || L < 3 || L - 1 > CH_MAX_LAYERS) return false;   // >= 2 hidden layers (see mlp_bwd_impl)
+  if (!(use_chain() & mode) || L < 3 || L - 1 > CH_MAX_LAYERS) return false;   // >= 2 hidden layers (see mlp_bwd_impl)
   if (m->dims[L] != 1 || m->dims[0] > 64) return false;
   for (int l = 1; l < L; ++l)
     if (m->dims[l] > 256 || m->dims[l] < 16 || (m->dims[l] & 15)) return false;
@@ -524,11 +595,15 @@ static int launch_chain(const ChainMaps& maps, const ChainParams& p_in, cudaStre
   const int64_t tiles = (p.M + 2 * TC_BM - 1) / (2 * TC_BM);
   int grid = (int)(tiles * 2 < num_sms() ? tiles * 2 : num_sms() / 2 * 2);
   double flops = 0.0;
-  for (int l = 0; l < p.num_layers; ++l) flops += 2.0 * (double)p.M * p.L[l].n_valid * (double)p.L[l].K;
+  for (int l = 0; l < p.num_layers; ++l) {
+    const bool tail = BWD && l == p.num_layers - 1;
+    if (tail && !p.C) continue;
+    flops += 2.0 * (double)(tail ? p.M - p.c_row0 : p.M) * p.L[l].n_valid * (double)p.L[l].K;
+  }
   prof_begin(PROF_CHAIN, flops, st);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(TC_THREADS);
+  cfg.blockDim = dim3(CH_THREADS);
   cfg.dynamicSmemBytes = CH_SMEM;
   cfg.stream = st;
   cudaLaunchAttribute at[1];

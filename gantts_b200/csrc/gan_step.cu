@@ -48,6 +48,35 @@ __global__ void gather_cols_list_kernel(const float* __restrict__ in, int64_t in
     for (int j = lane; j < cols.n; j += 32) out[r * out_rs + j] = in[r * in_rs + sc[j]];
 }
 
+// Column gather of up to two row blocks straight into bf16 hi/lo operand planes (the discriminator's input: rows
+// [0, rows_a) = selected columns of `a`, rows [rows_a, rows_a + rows_b) = selected columns of `b`): replaces
+// gather -> fp32 matrix -> split_planes.  One warp per row, a lane converts PAIRS of columns (4-byte stores).
+__global__ void gather_planes_kernel(const float* __restrict__ a, int64_t a_rs, ColList ca, int64_t rows_a,
+                                     const float* __restrict__ b, int64_t b_rs, ColList cb, int64_t rows_b,
+                                     __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int64_t pitch) {
+  __shared__ int sa[GANTTS_MAX_COLS], sb[GANTTS_MAX_COLS];
+  for (int i = threadIdx.x; i < ca.n; i += blockDim.x) sa[i] = ca.c[i];
+  for (int i = threadIdx.x; i < cb.n; i += blockDim.x) sb[i] = cb.c[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < rows_a + rows_b; r += nwarps) {
+    const bool first = r < rows_a;
+    const float* src = first ? a + r * a_rs : b + (r - rows_a) * b_rs;
+    const int* sc = first ? sa : sb;
+    const int n = first ? ca.n : cb.n;
+    uint32_t* hr = reinterpret_cast<uint32_t*>(hi + r * pitch);
+    uint32_t* lr = reinterpret_cast<uint32_t*>(lo + r * pitch);
+    for (int c = 2 * lane; c < n; c += 64) {
+      const float v0 = src[sc[c]], v1 = (c + 1 < n) ? src[sc[c + 1]] : 0.f;
+      const uint32_t hp = pack_bf16x2(v0, v1);
+      hr[c >> 1] = hp;
+      lr[c >> 1] = pack_bf16x2(v0 - __uint_as_float(hp << 16), v1 - __uint_as_float(hp & 0xffff0000u));
+    }
+  }
+}
+
 __global__ void scatter_cols_list_add_kernel(const float* __restrict__ go, int64_t go_rs, float* __restrict__ gi,
                                              int64_t gi_rs, ColList cols, int64_t rows) {
   __shared__ int sc[GANTTS_MAX_COLS];
@@ -60,10 +89,20 @@ __global__ void scatter_cols_list_add_kernel(const float* __restrict__ go, int64
     for (int j = lane; j < cols.n; j += 32) gi[r * gi_rs + sc[j]] += go[r * go_rs + j];
 }
 
+// inv_frames <= 0: derive the normaliser on the device, 1 / sum_b min(len_b, T) (= mask.sum() of train.py:258,286) --
+// single-process use; a data-parallel caller passes 1 / (GLOBAL number of valid frames).
 __global__ void set_scales_kernel(float* scal, float inv_frames, float adv_w, float mge_w, float mse_w,
-                                  int zero_norms) {
+                                  int zero_norms, const int64_t* __restrict__ lengths, int B, int T) {
   if (threadIdx.x == 0) {
     if (zero_norms) scal[S_DSUMSQ] = scal[S_GSUMSQ] = 0.f;
+    if (!(inv_frames > 0.f)) {
+      int64_t n = 0;
+      for (int b = 0; b < B; ++b) {
+        const int64_t l = lengths[b];
+        n += l < 0 ? 0 : (l > T ? T : l);
+      }
+      inv_frames = n > 0 ? 1.f / (float)n : 0.f;
+    }
     scal[S_INV_T] = inv_frames;
     scal[S_ADV_SCALE] = adv_w * inv_frames;
     scal[S_MGE_SCALE] = mge_w * inv_frames;
@@ -71,15 +110,136 @@ __global__ void set_scales_kernel(float* scal, float inv_frames, float adv_w, fl
   }
 }
 
+// Deferred reductions: every loss kernel of the step leaves per-block partial sums in its own slot; the single
+// finalize kernel at the end of the step reduces all of them (deterministic: fixed block order) -- no per-loss
+// "finish" launch on the way.
+enum RedSlot { R_REAL = 0, R_FAKE = 1, R_ADV = 2, R_MGE = 3, R_MSE = 4, R_COUNT = 5 };
+
+struct RedCounts {
+  int n[R_COUNT];      // blocks that wrote partials into slot i (0 = slot unused this step)
+};
+
+// Adversarial BCE terms of train.py:262-270,307-308 for one or two halves of a stacked discriminator output, forward
+// sums AND the gradient w.r.t. D in one pass: half 0 = rows [0, M) with kind0, half 1 = rows [M, 2M) with kind1
+// (kind 0: -log(D + eps) * m, correct = D > 0.5; kind 1: -log(1 - D + eps) * m, correct = D < 0.5).  mask is [M] for
+// both halves.  Blocks [0, nbh) serve half 0 and write ws0, blocks [nbh, 2 nbh) serve half 1 and write ws1.
+__global__ void __launch_bounds__(RED_THREADS)
+bce_fwd_bwd_kernel(const float* __restrict__ Dv, const float* __restrict__ mask, int64_t M, int kind0, int kind1,
+                   int nbh, const float* __restrict__ scale, float* __restrict__ gD, RedWs* ws0, RedWs* ws1) {
+  __shared__ float sm[RED_NV * 32];
+  const int half = blockIdx.x >= nbh ? 1 : 0;
+  const int kind = half ? kind1 : kind0;
+  const int blk = blockIdx.x - half * nbh;
+  const float* d = Dv + (int64_t)half * M;
+  float* g = gD ? gD + (int64_t)half * M : nullptr;
+  const float s = scale[0];
+  float v[RED_NV] = {0.f, 0.f, 0.f, 0.f};
+  for (int64_t i = (int64_t)blk * RED_THREADS + threadIdx.x; i < M; i += (int64_t)nbh * RED_THREADS) {
+    const float dv = d[i], m = mask[i];
+    const float arg = kind == 0 ? (dv + 1e-20f) : (1.f - dv + 1e-20f);
+    v[0] -= logf(arg) * m;
+    const bool hit = kind == 0 ? (dv > 0.5f) : (dv < 0.5f);
+    v[1] += hit ? m : 0.f;
+    v[2] += m;
+    if (g) g[i] = kind == 0 ? (-s * m / (dv + 1e-20f)) : (s * m / (1.f - dv + 1e-20f));
+  }
+  block_sum<RED_NV>(v, sm);
+  if (threadIdx.x == 0) {
+    RedWs* ws = half ? ws1 : ws0;
+#pragma unroll
+    for (int k = 0; k < RED_NV; ++k) ws->partial[blk][k] = v[k];
+  }
+}
+
+// MaskedMSELoss forward sums (gantts/seqloss.py:41-43) AND its gradient 2 * scale * (a m - b m) * m in one pass
+// (ga == nullptr: forward only).  The gradient is STORED (not accumulated): this launch initialises the buffer.
+__global__ void __launch_bounds__(RED_THREADS)
+sse_fwd_bwd_kernel(const float* __restrict__ a, int64_t a_rs, const float* __restrict__ b, int64_t b_rs,
+                   const float* __restrict__ mask, int64_t rows, int D, const float* __restrict__ scale,
+                   float* __restrict__ ga, int64_t ga_rs, RedWs* ws) {
+  __shared__ float sm[RED_NV * 32];
+  float v[RED_NV] = {0.f, 0.f, 0.f, 0.f};
+  const float s2 = ga ? 2.f * scale[0] : 0.f;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * RED_THREADS + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * RED_THREADS) >> 5;
+  for (int64_t r = warp; r < rows; r += nwarps) {
+    const float m = mask[r];
+    const float* ar = a + r * a_rs;
+    const float* br = b + r * b_rs;
+#pragma unroll 4
+    for (int d = lane; d < D; d += 32) {
+      const float x = ar[d] * m - br[d] * m;
+      v[0] = fmaf(x, x, v[0]);
+      if (ga) ga[r * ga_rs + d] = s2 * x * m;
+    }
+    if (lane == 0) v[1] += m;
+  }
+  block_sum<RED_NV>(v, sm);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < RED_NV; ++k) ws->partial[blockIdx.x][k] = v[k];
+  }
+}
+
+// clip_grad_norm_ + Adagrad with the sum of squares taken from the per-block partials of sumsq_partial_kernel:
+// every block re-reduces the (<= 592) partials itself in the same fixed order, which removes the finish launch.
+__global__ void __launch_bounds__(OPT_THREADS)
+clip_adagrad_partials_kernel(TensorList tl, const float* __restrict__ partial, int npartial, float* __restrict__ sumsq_out,
+                             float max_norm, float lr, float wd, float eps) {
+  __shared__ float sm[32];
+  __shared__ float total_s;
+  float v[1] = {0.f};
+  for (int i = threadIdx.x; i < npartial; i += OPT_THREADS) v[0] += partial[i];
+  block_sum<1>(v, sm);
+  if (threadIdx.x == 0) {
+    total_s = v[0];
+    if (blockIdx.x == 0) sumsq_out[0] = v[0];
+  }
+  __syncthreads();
+  const float total_norm = sqrtf(total_s);
+  float coef = max_norm / (total_norm + 1e-6f);
+  coef = coef < 1.f ? coef : 1.f;
+  const int64_t total = tl.off[tl.n];
+  for (int64_t i = (int64_t)blockIdx.x * OPT_THREADS + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * OPT_THREADS) {
+    int k = find_tensor(tl, i);
+    int64_t j = i - tl.off[k];
+    float g = tl.g[k][j] * coef;
+    tl.g[k][j] = g;
+    float p = tl.p[k][j];
+    g = fmaf(wd, p, g);
+    float s = fmaf(g, g, tl.s[k][j]);
+    tl.s[k][j] = s;
+    tl.p[k][j] = p - lr * g / (sqrtf(s) + eps);
+  }
+}
+
 // losses[0..11] = loss_d, loss_fake_d, loss_real_d, loss_mse, loss_mge, loss_adv, loss_g,
 //                 real_correct, fake_correct, frames(local sum of mask), d_grad_norm, g_grad_norm
-__global__ void finalize_losses_kernel(const float* scal, float* losses, float adv_w, float mge_w, float mse_w,
-                                       int has_d) {
+__global__ void __launch_bounds__(RED_THREADS)
+finalize_losses_kernel(const float* scal, float* losses, const RedWs* red, RedCounts cnt, float adv_w, float mge_w,
+                       float mse_w, int has_d) {
+  __shared__ float sm[RED_NV * 32];
+  __shared__ float tot[R_COUNT][RED_NV];
+  for (int sl = 0; sl < R_COUNT; ++sl) {
+    float v[RED_NV] = {0.f, 0.f, 0.f, 0.f};
+    for (int i = threadIdx.x; i < cnt.n[sl]; i += RED_THREADS) {
+#pragma unroll
+      for (int k = 0; k < RED_NV; ++k) v[k] += red[sl].partial[i][k];
+    }
+    block_sum<RED_NV>(v, sm);
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int k = 0; k < RED_NV; ++k) tot[sl][k] = v[k];
+    }
+    __syncthreads();
+  }
   if (threadIdx.x != 0) return;
   const float invT = scal[S_INV_T];
-  const float real = has_d ? scal[S_REAL] * invT : 0.f, fake = has_d ? scal[S_FAKE] * invT : 0.f;
-  const float adv = (has_d && adv_w > 0.f) ? scal[S_ADV] * invT : 0.f;
-  const float mge = scal[S_MGE] * invT, mse = scal[S_MSE] * invT;
+  const float real = has_d ? tot[R_REAL][0] * invT : 0.f, fake = has_d ? tot[R_FAKE][0] * invT : 0.f;
+  const float adv = (has_d && adv_w > 0.f) ? tot[R_ADV][0] * invT : 0.f;
+  const float mge = tot[R_MGE][0] * invT, mse = tot[R_MSE][0] * invT;
   losses[0] = real + fake;
   losses[1] = fake;
   losses[2] = real;
@@ -87,9 +247,9 @@ __global__ void finalize_losses_kernel(const float* scal, float* losses, float a
   losses[4] = mge;
   losses[5] = adv;
   losses[6] = (mse_w * mse + mge_w * mge) + adv_w * adv;
-  losses[7] = has_d ? scal[S_REAL + 1] : 0.f;
-  losses[8] = has_d ? scal[S_FAKE + 1] : 0.f;
-  losses[9] = scal[S_MGE + 1];
+  losses[7] = has_d ? tot[R_REAL][1] : 0.f;
+  losses[8] = has_d ? tot[R_FAKE][1] : 0.f;
+  losses[9] = tot[R_MGE][1];
   losses[10] = has_d ? sqrtf(scal[S_DSUMSQ]) : 0.f;
   losses[11] = sqrtf(scal[S_GSUMSQ]);
 }
@@ -132,8 +292,8 @@ struct StepLayout {
   size_t d_tape_bytes;
   char* mlp_ws;
   size_t mlp_ws_bytes;
-  char* red_ws;
-  size_t red_ws_bytes;
+  RedWs* red;             // [R_COUNT] deferred loss partials
+  float* opt_partial;     // [OPT_MAX_BLOCKS] sum-of-squares partials of the model being stepped
   size_t total;
 };
 
@@ -166,9 +326,8 @@ static void layout(const gantts_gan_step_t* c, char* base, StepLayout* L) {
   size_t a = gantts_mlp_workspace_bytes(&c->g, M), b = gantts_mlp_workspace_bytes(&c->d, 2 * M);
   L->mlp_ws_bytes = a > b ? a : b;
   L->mlp_ws = take(L->mlp_ws_bytes);
-  size_t r1 = gantts_masked_sse_workspace_bytes(), r2 = gantts_optim_workspace_bytes();
-  L->red_ws_bytes = r1 > r2 ? r1 : r2;
-  L->red_ws = take(L->red_ws_bytes);
+  L->red = (RedWs*)take(R_COUNT * sizeof(RedWs));
+  L->opt_partial = (float*)take(OPT_MAX_BLOCKS * sizeof(float));
   L->total = (size_t)(cur - base) + 256;
 }
 
@@ -192,6 +351,39 @@ static void param_list(const gantts_mlp_t& m, float* const* sumW, float* const* 
     cur += nb;
   }
   pl->total = cur - flat;
+}
+
+static inline int bce_blocks(int64_t rows) { return grid_for(rows, RED_THREADS); }
+static inline int sse_blocks(int64_t rows, int D) { return grid_for(rows * D, RED_THREADS * 4); }
+
+// BCE of a stacked discriminator output: halves = 2 -> rows [0,M) kind0 into slot0 and rows [M,2M) kind1 into slot1
+static int launch_bce(const float* Dv, const float* mask, int64_t M, int halves, int kind0, int kind1, const float* scale,
+                      float* gD, RedWs* ws0, RedWs* ws1, cudaStream_t st) {
+  const int nbh = bce_blocks(M);
+  bce_fwd_bwd_kernel<<<nbh * halves, RED_THREADS, 0, st>>>(Dv, mask, M, kind0, kind1, nbh, scale, gD, ws0, ws1);
+  GANTTS_LAUNCH_CHECK("bce_fwd_bwd_kernel");
+  return GANTTS_OK;
+}
+
+static int launch_sse(const float* a, int64_t a_rs, const float* b, int64_t b_rs, const float* mask, int64_t rows, int D,
+                      const float* scale, float* ga, int64_t ga_rs, RedWs* ws, cudaStream_t st) {
+  sse_fwd_bwd_kernel<<<sse_blocks(rows, D), RED_THREADS, 0, st>>>(a, a_rs, b, b_rs, mask, rows, D, scale, ga, ga_rs, ws);
+  GANTTS_LAUNCH_CHECK("sse_fwd_bwd_kernel");
+  return GANTTS_OK;
+}
+
+// clip_grad_norm_ + Adagrad over one model's parameter list: two launches (partials, update), no finish kernel
+static int clip_adagrad_model(const ParamList& pl, float* partial, float* sumsq_out, float max_norm, float lr, float wd,
+                              float eps, cudaStream_t st) {
+  TensorList tl;
+  int rc = fill(tl, pl.p, pl.g, pl.s, nullptr, pl.sizes, 0, pl.n);
+  if (rc) return rc;
+  const int nb = blocks_for(tl.off[tl.n], OPT_MAX_BLOCKS);
+  sumsq_partial_kernel<<<nb, OPT_THREADS, 0, st>>>(tl, partial);
+  GANTTS_LAUNCH_CHECK("sumsq_partial_kernel");
+  clip_adagrad_partials_kernel<<<nb, OPT_THREADS, 0, st>>>(tl, partial, nb, sumsq_out, max_norm, lr, wd, eps);
+  GANTTS_LAUNCH_CHECK("clip_adagrad_partials_kernel");
+  return GANTTS_OK;
 }
 
 static int check_step(const gantts_gan_step_t* c) {
@@ -271,16 +463,27 @@ extern "C" int gantts_gan_step(const gantts_gan_step_t* c, int phases, const flo
   for (int i = 0; i < c->n_static_cols; ++i) static_cols.c[i] = c->static_cols[i];
   adv_cols.n = has_d ? c->n_adv : 0;
   for (int i = 0; i < adv_cols.n; ++i) adv_cols.c[i] = c->adv_cols[i];
+  // the adversarial columns are one contiguous window of y_hat_static (mgc with the first coefficients masked, the
+  // hparams case): the discriminator's input gradient can be accumulated in place
+  bool adv_window = has_d && !cond_w && adv_cols.n >= 1;
+  for (int i = 1; i < adv_cols.n; ++i) adv_window = adv_window && adv_cols.c[i] == adv_cols.c[0] + i;
+  ColList real_cols;          // adversarial columns taken from y directly: static_cols o adv_cols
+  real_cols.n = adv_cols.n;
+  for (int i = 0; i < adv_cols.n; ++i) {
+    GANTTS_CHECK_ARG(adv_cols.c[i] >= 0 && adv_cols.c[i] < c->n_static_cols, "gan_step: adversarial column out of range");
+    real_cols.c[i] = static_cols.c[adv_cols.c[i]];
+  }
   gantts_mlp_t g = c->g, d = c->d;
   g.seed = gantts_gan_step_seed(seed, 0);
 
+  RedCounts cnt{};
   if (phases & GANTTS_STEP_EVAL) {
     // ---- "test" phase of train.py:481-486 (model.eval(), phase != "train" at :273,:315): forwards and losses only
     GANTTS_CHECK_ARG(phases == GANTTS_STEP_EVAL, "gan_step: GANTTS_STEP_EVAL cannot be combined with training phases");
     g.dropout_p = 0.f;
     d.dropout_p = 0.f;
     if ((rc = gantts_sequence_mask(lengths_dev, L.mask, c->B, c->T, stream))) return rc;
-    set_scales_kernel<<<1, 32, 0, st>>>(L.scal, inv_frames, has_adv ? c->adv_w : 0.f, c->mge_w, c->mse_w, 1);
+    set_scales_kernel<<<1, 32, 0, st>>>(L.scal, inv_frames, has_adv ? c->adv_w : 0.f, c->mge_w, c->mse_w, 1, lengths_dev, c->B, c->T);
     GANTTS_LAUNCH_CHECK("set_scales_kernel");
     gather_cols_list_kernel<<<blocks_1d(M * nS, 1024), 256, 0, st>>>(y, d_out, L.y_static, nS, static_cols, M);
     GANTTS_LAUNCH_CHECK("gather_cols_list_kernel(y_static)");
@@ -302,20 +505,23 @@ extern "C" int gantts_gan_step(const gantts_gan_step_t* c, int phases, const flo
                                       (size_t)cond_w * sizeof(float), (size_t)M, cudaMemcpyDeviceToDevice, st));
       }
       if ((rc = gantts_mlp_fwd(&d, L.d_in, dD, 2 * M, L.d_out, 1, L.d_tape, L.d_tape_bytes, stream))) return rc;
-      if ((rc = gantts_masked_bce_fwd(L.d_out, L.mask, M, 0, L.scal + S_REAL, L.red_ws, L.red_ws_bytes, stream))) return rc;
-      if ((rc = gantts_masked_bce_fwd(L.d_out + M, L.mask, M, 1, L.scal + S_FAKE, L.red_ws, L.red_ws_bytes, stream))) return rc;
-      if (has_adv &&
-          (rc = gantts_masked_bce_fwd(L.d_out + M, L.mask, M, 0, L.scal + S_ADV, L.red_ws, L.red_ws_bytes, stream)))
+      if ((rc = launch_bce(L.d_out, L.mask, M, 2, 0, 1, L.scal + S_INV_T, nullptr, &L.red[R_REAL], &L.red[R_FAKE], st)))
         return rc;
+      cnt.n[R_REAL] = cnt.n[R_FAKE] = bce_blocks(M);
+      if (has_adv) {
+        if ((rc = launch_bce(L.d_out + M, L.mask, M, 1, 0, 0, L.scal + S_INV_T, nullptr, &L.red[R_ADV], nullptr, st)))
+          return rc;
+        cnt.n[R_ADV] = bce_blocks(M);
+      }
     }
-    if ((rc = gantts_masked_sse_fwd(y_hat_static, nS, L.y_static, nS, L.mask, M, nS, L.scal + S_MGE, L.red_ws,
-                                    L.red_ws_bytes, stream)))
+    if ((rc = launch_sse(y_hat_static, nS, L.y_static, nS, L.mask, M, nS, L.scal + S_MGE_SCALE, nullptr, 0, &L.red[R_MGE], st)))
       return rc;
-    if ((rc = gantts_masked_sse_fwd(y_hat, d_out, y, d_out, L.mask, M, d_out, L.scal + S_MSE, L.red_ws,
-                                    L.red_ws_bytes, stream)))
+    if ((rc = launch_sse(y_hat, d_out, y, d_out, L.mask, M, d_out, L.scal + S_MSE_SCALE, nullptr, 0, &L.red[R_MSE], st)))
       return rc;
-    finalize_losses_kernel<<<1, 32, 0, st>>>(L.scal, losses_dev, has_adv ? c->adv_w : 0.f, c->mge_w, c->mse_w,
-                                             has_d ? 1 : 0);
+    cnt.n[R_MGE] = sse_blocks(M, nS);
+    cnt.n[R_MSE] = sse_blocks(M, d_out);
+    finalize_losses_kernel<<<1, RED_THREADS, 0, st>>>(L.scal, losses_dev, L.red, cnt, has_adv ? c->adv_w : 0.f, c->mge_w,
+                                                      c->mse_w, has_d ? 1 : 0);
     GANTTS_LAUNCH_CHECK("finalize_losses_kernel");
     return GANTTS_OK;
   }
@@ -323,100 +529,124 @@ extern "C" int gantts_gan_step(const gantts_gan_step_t* c, int phases, const flo
   if (phases & 1) {
     // ---- prologue: mask, scales, y_static (train.py:528-535)
     if ((rc = gantts_sequence_mask(lengths_dev, L.mask, c->B, c->T, stream))) return rc;
-    set_scales_kernel<<<1, 32, 0, st>>>(L.scal, inv_frames, has_adv ? c->adv_w : 0.f, c->mge_w, c->mse_w, 0);
+    set_scales_kernel<<<1, 32, 0, st>>>(L.scal, inv_frames, has_adv ? c->adv_w : 0.f, c->mge_w, c->mse_w, 0, lengths_dev, c->B, c->T);
     GANTTS_LAUNCH_CHECK("set_scales_kernel");
     gather_cols_list_kernel<<<blocks_1d(M * nS, 1024), 256, 0, st>>>(y, d_out, L.y_static, nS, static_cols, M);
     GANTTS_LAUNCH_CHECK("gather_cols_list_kernel(y_static)");
-    GANTTS_CUDA(cudaMemsetAsync(L.g_static, 0, (size_t)M * nS * sizeof(float), st));
     // ---- apply_generator (train.py:336-355): G forward + MLPG
     if ((rc = gantts_mlp_fwd(&g, x, d_in, M, y_hat, d_out, L.g_tape, L.g_tape_bytes, stream))) return rc;
     if ((rc = gantts_mlpg_fwd(y_hat, (int64_t)c->T * d_out, d_out, y_hat_static, (int64_t)c->T * nS, nS,
                               c->mlpg_table, &c->streams, &c->windows, c->B, c->T, stream)))
       return rc;
+    // MGE loss (train.py:291) and its gradient in one pass; the gradient INITIALISES g_static, the two discriminator
+    // passes then accumulate their input gradients on top of it
+    if ((rc = launch_sse(y_hat_static, nS, L.y_static, nS, L.mask, M, nS, L.scal + S_MGE_SCALE, L.g_static, nS,
+                         &L.red[R_MGE], st)))
+      return rc;
     if (has_d) {
       // ---- update_discriminator (train.py:245-279): stacked real | fake batch of 2M rows
-      gather_cols_list_kernel<<<blocks_1d(M * nA, 1024), 256, 0, st>>>(L.y_static, nS, L.d_in + cond_w, dD, adv_cols,
-                                                                       M);
-      GANTTS_LAUNCH_CHECK("gather_cols_list_kernel(real)");
-      gather_cols_list_kernel<<<blocks_1d(M * nA, 1024), 256, 0, st>>>(y_hat_static, nS, L.d_in + M * dD + cond_w, dD,
-                                                                       adv_cols, M);
-      GANTTS_LAUNCH_CHECK("gather_cols_list_kernel(fake)");
-      if (cond_w) {
+      d.seed = gantts_gan_step_seed(seed, 1);
+      if (!cond_w) {
+        // selected columns of y (real) and y_hat_static (fake) straight into the discriminator's input planes
+        Planes din;
+        if ((rc = mlp_tape_input_planes(&d, 2 * M, L.d_tape, L.d_tape_bytes, &din))) return rc;
+        gather_planes_kernel<<<blocks_1d(2 * M * nA, 1024), 256, 0, st>>>(y, d_out, real_cols, M, y_hat_static, nS,
+                                                                          adv_cols, M, din.hi, din.lo, din.pitch);
+        GANTTS_LAUNCH_CHECK("gather_planes_kernel(real|fake)");
+        if ((rc = mlp_fwd_impl(&d, nullptr, 0, 2 * M, L.d_out, 1, L.d_tape, L.d_tape_bytes, stream, true))) return rc;
+      } else {
+        gather_cols_list_kernel<<<blocks_1d(M * nA, 1024), 256, 0, st>>>(L.y_static, nS, L.d_in + cond_w, dD, adv_cols,
+                                                                         M);
+        GANTTS_LAUNCH_CHECK("gather_cols_list_kernel(real)");
+        gather_cols_list_kernel<<<blocks_1d(M * nA, 1024), 256, 0, st>>>(y_hat_static, nS, L.d_in + M * dD + cond_w, dD,
+                                                                         adv_cols, M);
+        GANTTS_LAUNCH_CHECK("gather_cols_list_kernel(fake)");
         GANTTS_CUDA(cudaMemcpy2DAsync(L.d_in, (size_t)dD * sizeof(float), x, (size_t)d_in * sizeof(float),
                                       (size_t)cond_w * sizeof(float), (size_t)M, cudaMemcpyDeviceToDevice, st));
         GANTTS_CUDA(cudaMemcpy2DAsync(L.d_in + M * dD, (size_t)dD * sizeof(float), x, (size_t)d_in * sizeof(float),
                                       (size_t)cond_w * sizeof(float), (size_t)M, cudaMemcpyDeviceToDevice, st));
+        if ((rc = gantts_mlp_fwd(&d, L.d_in, dD, 2 * M, L.d_out, 1, L.d_tape, L.d_tape_bytes, stream))) return rc;
       }
-      d.seed = gantts_gan_step_seed(seed, 1);
-      if ((rc = gantts_mlp_fwd(&d, L.d_in, dD, 2 * M, L.d_out, 1, L.d_tape, L.d_tape_bytes, stream))) return rc;
-      if ((rc = gantts_masked_bce_fwd(L.d_out, L.mask, M, 0, L.scal + S_REAL, L.red_ws, L.red_ws_bytes, stream))) return rc;
-      if ((rc = gantts_masked_bce_fwd(L.d_out + M, L.mask, M, 1, L.scal + S_FAKE, L.red_ws, L.red_ws_bytes, stream))) return rc;
-      if ((rc = gantts_masked_bce_bwd(L.d_out, L.mask, M, 0, L.scal + S_INV_T, L.g_dout, stream))) return rc;
-      if ((rc = gantts_masked_bce_bwd(L.d_out + M, L.mask, M, 1, L.scal + S_INV_T, L.g_dout + M, stream))) return rc;
-      // loss_d.backward(): D parameter gradients + gradient w.r.t. the (fake) D input
-      // (input gradient for the fake half only: rows M..2M-1)
-      if ((rc = mlp_bwd_impl(&d, L.g_dout, 1, L.d_out, 1, 2 * M, L.d_tape, L.d_tape_bytes, L.g_din, dD, M, pd.gW,
-                             pd.gb, 0, L.mlp_ws, L.mlp_ws_bytes, stream)))
+      // real and fake BCE terms, counts and dL/dD of both halves (train.py:262-270) in one launch
+      if ((rc = launch_bce(L.d_out, L.mask, M, 2, 0, 1, L.scal + S_INV_T, L.g_dout, &L.red[R_REAL], &L.red[R_FAKE], st)))
         return rc;
-      scatter_cols_list_add_kernel<<<blocks_1d(M * nA, 1024), 256, 0, st>>>(L.g_din + M * dD + cond_w, dD, L.g_static,
-                                                                            nS, adv_cols, M);
-      GANTTS_LAUNCH_CHECK("scatter_cols_list_add_kernel(fake)");
+      // loss_d.backward(): D parameter gradients + gradient w.r.t. the (fake) D input (rows M..2M-1 only).  When the
+      // adversarial columns form one window of y_hat_static the last GEMM adds its result straight into g_static
+      // (the scatter of the column gather's backward); otherwise it goes to g_din and a scatter kernel follows.
+      if (adv_window) {
+        float* win = L.g_static + adv_cols.c[0] - M * (int64_t)nS;      // row r of the stacked batch -> g_static[r - M]
+        if ((rc = mlp_bwd_impl(&d, L.g_dout, 1, L.d_out, 1, 2 * M, L.d_tape, L.d_tape_bytes, win, nS, M, pd.gW, pd.gb, 0,
+                               L.mlp_ws, L.mlp_ws_bytes, stream, 1)))
+          return rc;
+      } else {
+        if ((rc = mlp_bwd_impl(&d, L.g_dout, 1, L.d_out, 1, 2 * M, L.d_tape, L.d_tape_bytes, L.g_din, dD, M, pd.gW,
+                               pd.gb, 0, L.mlp_ws, L.mlp_ws_bytes, stream)))
+          return rc;
+        scatter_cols_list_add_kernel<<<blocks_1d(M * nA, 1024), 256, 0, st>>>(L.g_din + M * dD + cond_w, dD, L.g_static,
+                                                                              nS, adv_cols, M);
+        GANTTS_LAUNCH_CHECK("scatter_cols_list_add_kernel(fake)");
+      }
     }
   }
   if (phases & 2) {
     if (has_d) {
       // ---- clip_grad_norm_ + Adagrad on D (train.py:275-276)
-      if ((rc = gantts_grad_sumsq(pd.g, pd.sizes, pd.n, L.scal + S_DSUMSQ, L.red_ws, L.red_ws_bytes, stream))) return rc;
-      if ((rc = gantts_clip_adagrad_step(pd.p, pd.g, pd.s, pd.sizes, pd.n, L.scal + S_DSUMSQ, c->max_norm, c->lr_d,
-                                         c->wd_d, c->eps, stream)))
+      if ((rc = clip_adagrad_model(pd, L.opt_partial, L.scal + S_DSUMSQ, c->max_norm, c->lr_d, c->wd_d, c->eps, st)))
         return rc;
     }
-    // ---- update_generator (train.py:282-320)
-    if ((rc = gantts_masked_sse_fwd(y_hat_static, nS, L.y_static, nS, L.mask, M, nS, L.scal + S_MGE, L.red_ws,
-                                    L.red_ws_bytes, stream)))
-      return rc;
-    if ((rc = gantts_masked_sse_fwd(y_hat, d_out, y, d_out, L.mask, M, d_out, L.scal + S_MSE, L.red_ws,
-                                    L.red_ws_bytes, stream)))
-      return rc;
+    // ---- update_generator (train.py:282-320); the MGE term was evaluated in phase 1
     if (has_adv) {
       // third D forward: updated weights, fresh dropout mask (train.py:307)
       d.seed = gantts_gan_step_seed(seed, 2);
-      if ((rc = gantts_mlp_fwd(&d, L.d_in + M * dD, dD, M, L.d_out, 1, L.d_tape, L.d_tape_bytes, stream))) return rc;
-      if ((rc = gantts_masked_bce_fwd(L.d_out, L.mask, M, 0, L.scal + S_ADV, L.red_ws, L.red_ws_bytes, stream))) return rc;
-      if ((rc = gantts_masked_bce_bwd(L.d_out, L.mask, M, 0, L.scal + S_ADV_SCALE, L.g_dout, stream))) return rc;
-      if ((rc = gantts_mlp_bwd(&d, L.g_dout, 1, L.d_out, 1, M, L.d_tape, L.d_tape_bytes, L.g_din, dD, nullptr,
-                               nullptr, 0, L.mlp_ws, L.mlp_ws_bytes, stream)))
+      if (!cond_w) {
+        Planes din;
+        if ((rc = mlp_tape_input_planes(&d, M, L.d_tape, L.d_tape_bytes, &din))) return rc;
+        ColList none;
+        none.n = 0;
+        gather_planes_kernel<<<blocks_1d(M * nA, 1024), 256, 0, st>>>(y_hat_static, nS, adv_cols, M, nullptr, 0, none, 0,
+                                                                      din.hi, din.lo, din.pitch);
+        GANTTS_LAUNCH_CHECK("gather_planes_kernel(adv)");
+        if ((rc = mlp_fwd_impl(&d, nullptr, 0, M, L.d_out, 1, L.d_tape, L.d_tape_bytes, stream, true))) return rc;
+      } else if ((rc = gantts_mlp_fwd(&d, L.d_in + M * dD, dD, M, L.d_out, 1, L.d_tape, L.d_tape_bytes, stream))) {
         return rc;
-      scatter_cols_list_add_kernel<<<blocks_1d(M * nA, 1024), 256, 0, st>>>(L.g_din + cond_w, dD, L.g_static, nS,
-                                                                            adv_cols, M);
-      GANTTS_LAUNCH_CHECK("scatter_cols_list_add_kernel(adv)");
-    }
-    if (c->mge_w != 0.f) {
-      if ((rc = gantts_masked_sse_bwd(y_hat_static, nS, L.y_static, nS, L.mask, M, nS, L.scal + S_MGE_SCALE,
-                                      L.g_static, nS, 1, stream)))
+      }
+      if ((rc = launch_bce(L.d_out, L.mask, M, 1, 0, 0, L.scal + S_ADV_SCALE, L.g_dout, &L.red[R_ADV], nullptr, st)))
         return rc;
+      if (adv_window) {
+        if ((rc = mlp_bwd_impl(&d, L.g_dout, 1, L.d_out, 1, M, L.d_tape, L.d_tape_bytes, L.g_static + adv_cols.c[0], nS, 0,
+                               nullptr, nullptr, 0, L.mlp_ws, L.mlp_ws_bytes, stream, 1)))
+          return rc;
+      } else {
+        if ((rc = gantts_mlp_bwd(&d, L.g_dout, 1, L.d_out, 1, M, L.d_tape, L.d_tape_bytes, L.g_din, dD, nullptr,
+                                 nullptr, 0, L.mlp_ws, L.mlp_ws_bytes, stream)))
+          return rc;
+        scatter_cols_list_add_kernel<<<blocks_1d(M * nA, 1024), 256, 0, st>>>(L.g_din + cond_w, dD, L.g_static, nS,
+                                                                              adv_cols, M);
+        GANTTS_LAUNCH_CHECK("scatter_cols_list_add_kernel(adv)");
+      }
     }
-    // ---- loss_g.backward(): MLPG backward + generator backward on the summed upstream gradient
-    if ((rc = gantts_mlpg_bwd(L.g_static, (int64_t)c->T * nS, nS, L.g_yhat, (int64_t)c->T * d_out, d_out,
-                              c->mlpg_table, &c->streams, &c->windows, c->B, c->T, 0, stream)))
+    // ---- loss_g.backward(): MSE term (train.py:294) + MLPG backward + generator backward on the summed gradient.
+    // With mse_w != 0 the MSE pass stores its gradient into g_yhat and the MLPG backward accumulates on top of it.
+    if ((rc = launch_sse(y_hat, d_out, y, d_out, L.mask, M, d_out, L.scal + S_MSE_SCALE, c->mse_w != 0.f ? L.g_yhat : nullptr,
+                         d_out, &L.red[R_MSE], st)))
       return rc;
-    if (c->mse_w != 0.f) {
-      if ((rc = gantts_masked_sse_bwd(y_hat, d_out, y, d_out, L.mask, M, d_out, L.scal + S_MSE_SCALE, L.g_yhat,
-                                      d_out, 1, stream)))
-        return rc;
-    }
+    if ((rc = gantts_mlpg_bwd(L.g_static, (int64_t)c->T * nS, nS, L.g_yhat, (int64_t)c->T * d_out, d_out,
+                              c->mlpg_table, &c->streams, &c->windows, c->B, c->T, c->mse_w != 0.f ? 1 : 0, stream)))
+      return rc;
     if ((rc = gantts_mlp_bwd(&g, L.g_yhat, d_out, nullptr, 0, M, L.g_tape, L.g_tape_bytes, nullptr, 0, pg.gW, pg.gb,
                              0, L.mlp_ws, L.mlp_ws_bytes, stream)))
       return rc;
   }
   if (phases & 4) {
     // ---- clip_grad_norm_ + Adagrad on G (train.py:317-318), then the loss scalars
-    if ((rc = gantts_grad_sumsq(pg.g, pg.sizes, pg.n, L.scal + S_GSUMSQ, L.red_ws, L.red_ws_bytes, stream))) return rc;
-    if ((rc = gantts_clip_adagrad_step(pg.p, pg.g, pg.s, pg.sizes, pg.n, L.scal + S_GSUMSQ, c->max_norm, c->lr_g,
-                                       c->wd_g, c->eps, stream)))
+    if ((rc = clip_adagrad_model(pg, L.opt_partial, L.scal + S_GSUMSQ, c->max_norm, c->lr_g, c->wd_g, c->eps, st)))
       return rc;
-    finalize_losses_kernel<<<1, 32, 0, st>>>(L.scal, losses_dev, has_adv ? c->adv_w : 0.f, c->mge_w, c->mse_w,
-                                             has_d ? 1 : 0);
+    if (has_d) cnt.n[R_REAL] = cnt.n[R_FAKE] = bce_blocks(M);
+    if (has_adv) cnt.n[R_ADV] = bce_blocks(M);
+    cnt.n[R_MGE] = sse_blocks(M, nS);
+    cnt.n[R_MSE] = sse_blocks(M, d_out);
+    finalize_losses_kernel<<<1, RED_THREADS, 0, st>>>(L.scal, losses_dev, L.red, cnt, has_adv ? c->adv_w : 0.f, c->mge_w,
+                                                      c->mse_w, has_d ? 1 : 0);
     GANTTS_LAUNCH_CHECK("finalize_losses_kernel");
   }
   return GANTTS_OK;

@@ -508,16 +508,42 @@ extern "C" size_t gantts_mlp_workspace_bytes(const gantts_mlp_t* m, int64_t M) {
   for (int l = 0; l <= m->num_layers; ++l) maxd = m->dims[l] > maxd ? m->dims[l] : maxd;
   for (int l = 0; l < m->num_layers; ++l)       // one partial region per layer: reductions are deferred
     part += mn_partial_bytes(M, m->dims[l + 1], m->dims[l], nullptr, nullptr) + 256;
-  const int nbuf = chain_shape_ok(m) && m->num_layers - 1 > 2 ? m->num_layers - 1 : 2;   // gradient plane buffers
+  const int nbuf = chain_shape_ok(m, CHAIN_BWD_GRAD) && m->num_layers - 1 > 2 ? m->num_layers - 1 : 2;   // gradient plane buffers
   return (size_t)2 * nbuf * plane_bytes(M, maxd) + part + (size_t)MLP_COLSUM_CHUNKS * maxd * sizeof(float) +
          (size_t)GEMV_BLOCKS * (GEMV_MAX_K + 1) * sizeof(float) + 4096;
 }
 
-extern "C" int gantts_mlp_fwd(const gantts_mlp_t* m, const float* x, int64_t x_rs, int64_t M, float* y,
-                              int64_t y_rs, void* tape, size_t tape_bytes, void* stream) {
+// input_ready: the caller has already written the input planes into the tape (mlp_tape_input_planes) -- the fused
+// step gathers the discriminator's input columns straight into planes instead of gathering to fp32 and splitting.
+namespace gantts {
+static int mlp_fwd_impl(const gantts_mlp_t* m, const float* x, int64_t x_rs, int64_t M, float* y, int64_t y_rs, void* tape,
+                        size_t tape_bytes, void* stream, bool input_ready);
+
+static int mlp_tape_input_planes(const gantts_mlp_t* m, int64_t M, void* tape, size_t tape_bytes, Planes* out) {
   int rc = check_mlp(m, M);
   if (rc) return rc;
-  GANTTS_CHECK_ARG(x && y && x_rs >= m->dims[0] && y_rs >= m->dims[m->num_layers], "mlp_fwd: bad pointers/strides");
+  if (!tape || tape_bytes < gantts_mlp_tape_bytes(m, M)) {
+    set_error("mlp_tape_input_planes: tape too small");
+    return GANTTS_E_WORKSPACE;
+  }
+  MlpTape t;
+  carve_tape(m, M, reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(tape) + 255) / 256 * 256), &t);
+  *out = t.H[0];
+  return GANTTS_OK;
+}
+}  // namespace gantts
+
+extern "C" int gantts_mlp_fwd(const gantts_mlp_t* m, const float* x, int64_t x_rs, int64_t M, float* y,
+                              int64_t y_rs, void* tape, size_t tape_bytes, void* stream) {
+  GANTTS_CHECK_ARG(m && x && x_rs >= m->dims[0], "mlp_fwd: bad input pointer/stride");
+  return mlp_fwd_impl(m, x, x_rs, M, y, y_rs, tape, tape_bytes, stream, false);
+}
+
+static int gantts::mlp_fwd_impl(const gantts_mlp_t* m, const float* x, int64_t x_rs, int64_t M, float* y, int64_t y_rs,
+                                void* tape, size_t tape_bytes, void* stream, bool input_ready) {
+  int rc = check_mlp(m, M);
+  if (rc) return rc;
+  GANTTS_CHECK_ARG((x || input_ready) && y && y_rs >= m->dims[m->num_layers], "mlp_fwd: bad pointers/strides");
   size_t need = gantts_mlp_tape_bytes(m, M);
   if (!tape || tape_bytes < need) {
     set_error("mlp_fwd: tape too small (%zu < %zu)", tape_bytes, need);
@@ -527,7 +553,7 @@ extern "C" int gantts_mlp_fwd(const gantts_mlp_t* m, const float* x, int64_t x_r
   MlpTape t;
   carve_tape(m, M, reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(tape) + 255) / 256 * 256), &t);
   const int L = m->num_layers;
-  if ((rc = launch_split(x, x_rs, M, m->dims[0], t.H[0], 0, st))) return rc;
+  if (!input_ready && (rc = launch_split(x, x_rs, M, m->dims[0], t.H[0], 0, st))) return rc;
   {
     WeightSplitList wl;
     wl.n = L;
@@ -550,7 +576,7 @@ extern "C" int gantts_mlp_fwd(const gantts_mlp_t* m, const float* x, int64_t x_r
     split_weights_kernel<<<nb, 256, 0, st>>>(wl);
     GANTTS_LAUNCH_CHECK("split_weights_kernel");
   }
-  if (chain_shape_ok(m)) {
+  if (chain_shape_ok(m, CHAIN_FWD)) {
     // narrow stack with a single output (the discriminator): ONE launch, activations stay on chip between layers
     ChainMaps maps;
     ChainParams cp{};
@@ -567,14 +593,18 @@ extern "C" int gantts_mlp_fwd(const gantts_mlp_t* m, const float* x, int64_t x_r
       cl.n_valid = m->dims[l + 1];
       cl.K = pad64(m->dims[l]);
       cl.bias = m->b[l];
-      cl.out_hi = t.H[l + 1].hi;
-      cl.out_lo = t.H[l + 1].lo;
-      cl.out_pitch = t.H[l + 1].pitch;
+      cl.store_planes = 1;                       // tape: H_{l+1} planes, stored by TMA from the shared-memory tile
+      if ((rc = make_map(&maps.s_hi[l], t.H[l + 1].hi, M, m->dims[l + 1], t.H[l + 1].pitch, TC_BM, 64))) return rc;
+      if ((rc = make_map(&maps.s_lo[l], t.H[l + 1].lo, M, m->dims[l + 1], t.H[l + 1].pitch, TC_BM, 64))) return rc;
       cl.code = t.code[l + 1];
       cl.code_pitch = t.code_pitch[l + 1];
       cl.seed = layer_seed(m->seed, l);
       if ((rc = make_map(&maps.b_hi[l], t.W[l].hi, m->dims[l + 1], m->dims[l], t.W[l].pitch, cl.N / 2, 32))) return rc;
       if ((rc = make_map(&maps.b_lo[l], t.W[l].lo, m->dims[l + 1], m->dims[l], t.W[l].pitch, cl.N / 2, 32))) return rc;
+    }
+    for (int i = L - 1; i < CH_MAX_LAYERS; ++i) {
+      maps.b_hi[i] = maps.b_hi[0]; maps.b_lo[i] = maps.b_lo[0];
+      maps.s_hi[i] = maps.s_hi[0]; maps.s_lo[i] = maps.s_lo[0];
     }
     cp.w_last = m->W[L - 1];
     cp.b_last = m->b[L - 1];
@@ -632,7 +662,7 @@ namespace gantts {
 static int mlp_bwd_impl(const gantts_mlp_t* m, const float* gy, int64_t gy_rs, const float* y, int64_t y_rs, int64_t M,
                         const void* tape, size_t tape_bytes, float* gx, int64_t gx_rs, int64_t gx_row0,
                         float* const* gW, float* const* gb, int accumulate, void* workspace, size_t workspace_bytes,
-                        void* stream);
+                        void* stream, int gx_accumulate = -1);
 }
 
 extern "C" int gantts_mlp_bwd(const gantts_mlp_t* m, const float* gy, int64_t gy_rs, const float* y,
@@ -640,13 +670,16 @@ extern "C" int gantts_mlp_bwd(const gantts_mlp_t* m, const float* gy, int64_t gy
                               int64_t gx_rs, float* const* gW, float* const* gb, int accumulate,
                               void* workspace, size_t workspace_bytes, void* stream) {
   return mlp_bwd_impl(m, gy, gy_rs, y, y_rs, M, tape, tape_bytes, gx, gx_rs, 0, gW, gb, accumulate, workspace,
-                      workspace_bytes, stream);
+                      workspace_bytes, stream, -1);
 }
 
 static int gantts::mlp_bwd_impl(const gantts_mlp_t* m, const float* gy, int64_t gy_rs, const float* y, int64_t y_rs,
                                 int64_t M, const void* tape, size_t tape_bytes, float* gx, int64_t gx_rs,
                                 int64_t gx_row0, float* const* gW, float* const* gb, int accumulate, void* workspace,
-                                size_t workspace_bytes, void* stream) {
+                                size_t workspace_bytes, void* stream, int gx_accumulate) {
+  // gx_accumulate: -1 = like the parameter gradients, 0 = store, 1 = add to what gx holds (gx may be a column window of
+  // a wider matrix with row stride gx_rs: the fused step scatters the input gradient into g_static this way)
+  if (gx_accumulate < 0) gx_accumulate = accumulate;
   int rc = check_mlp(m, M);
   GANTTS_CHECK_ARG(gx_row0 >= 0 && gx_row0 < M, "mlp_bwd: bad gx_row0");
   if (rc) return rc;
@@ -668,8 +701,10 @@ static int gantts::mlp_bwd_impl(const gantts_mlp_t* m, const float* gy, int64_t 
   int maxd = 0;
   for (int l = 0; l <= L; ++l) maxd = m->dims[l] > maxd ? m->dims[l] : maxd;
   char* cur = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 255) / 256 * 256);
-  const bool chain = chain_shape_ok(m);
-  const int nbuf = chain && L - 1 > 2 ? L - 1 : 2;
+  bool any_grad = false;
+  for (int l = 0; l < L; ++l) any_grad |= (gW && gW[l]) || (gb && gb[l]);
+  const bool chain = chain_shape_ok(m, any_grad ? CHAIN_BWD_GRAD : CHAIN_BWD_NOGRAD);
+  const int nbuf = chain_shape_ok(m, CHAIN_BWD_GRAD) && L - 1 > 2 ? L - 1 : 2;
   char* gbuf[GANTTS_MAX_LAYERS];
   for (int i = 0; i < nbuf; ++i) {
     gbuf[i] = cur;
@@ -734,7 +769,6 @@ static int gantts::mlp_bwd_impl(const gantts_mlp_t* m, const float* gy, int64_t 
     cp.head_valid = K1;
     cp.code_head = t.code[Lh];
     cp.code_head_pitch = t.code_pitch[Lh];
-    cp.head_hi = nullptr;                        // written by the GEMV backward when weight gradients are wanted
     for (int i = 0; i < Lh; ++i) {
       const int ml = Lh - 1 - i;                 // MLP layer whose transposed weights this chain layer multiplies by
       ChainLayer& cl = cp.L[i];
@@ -746,19 +780,25 @@ static int gantts::mlp_bwd_impl(const gantts_mlp_t* m, const float* gy, int64_t 
         cl.code = t.code[ml];
         cl.code_pitch = t.code_pitch[ml];
         const bool need_planes = (gW && gW[ml - 1]) || (gb && gb[ml - 1]);
-        cl.out_hi = need_planes ? Gl[ml - 1].hi : nullptr;
-        cl.out_lo = need_planes ? Gl[ml - 1].lo : nullptr;
-        cl.out_pitch = Gl[ml - 1].pitch;
+        cl.store_planes = need_planes ? 1 : 0;
+        if (need_planes) {
+          if ((rc = make_map(&maps.s_hi[i], Gl[ml - 1].hi, M, m->dims[ml], Gl[ml - 1].pitch, TC_BM, 64))) return rc;
+          if ((rc = make_map(&maps.s_lo[i], Gl[ml - 1].lo, M, m->dims[ml], Gl[ml - 1].pitch, TC_BM, 64))) return rc;
+        }
       }
       if ((rc = make_map(&maps.b_hi[i], t.Wt[ml].hi, m->dims[ml], m->dims[ml + 1], t.Wt[ml].pitch, cl.N / 2, 32))) return rc;
       if ((rc = make_map(&maps.b_lo[i], t.Wt[ml].lo, m->dims[ml], m->dims[ml + 1], t.Wt[ml].pitch, cl.N / 2, 32))) return rc;
     }
     maps.a_hi = maps.b_hi[0];                    // unused in the backward kernel
     maps.a_lo = maps.b_lo[0];
+    for (int i = 0; i < CH_MAX_LAYERS; ++i) {
+      if (i >= Lh) { maps.b_hi[i] = maps.b_hi[0]; maps.b_lo[i] = maps.b_lo[0]; }
+      if (i >= Lh || !cp.L[i].store_planes) { maps.s_hi[i] = maps.b_hi[0]; maps.s_lo[i] = maps.b_lo[0]; }
+    }
     cp.C = gx ? gx + gx_row0 * gx_rs : nullptr;
     cp.ldc = gx_rs;
     cp.c_row0 = gx_row0;
-    cp.c_accumulate = accumulate;
+    cp.c_accumulate = gx_accumulate;
     if ((rc = launch_chain<true>(maps, cp, st))) return rc;
     (void)want_w;
     for (int l = Lh - 1; l >= 0; --l) {
@@ -847,7 +887,7 @@ static int gantts::mlp_bwd_impl(const gantts_mlp_t* m, const float* gy, int64_t 
       e.epi = EPI_F32;
       e.C = gx + gx_row0 * gx_rs;
       e.ldc = gx_rs;
-      e.accumulate = accumulate;
+      e.accumulate = gx_accumulate;
       Planes Gs = G;
       Gs.hi += gx_row0 * G.pitch;
       Gs.lo += gx_row0 * G.pitch;

@@ -114,7 +114,7 @@ class FusedGanStep(object):
                                        self.y_hat_static.data_ptr(), self.losses.data_ptr(), self._ws.data_ptr(),
                                        self._ws.numel(), ops._stream()))
 
-    def step(self, x, y, lengths, frames, adv_w=1.0, train=None):
+    def step(self, x, y, lengths, frames=None, adv_w=1.0, train=None):
         """x (B,T,d_in), y (B,T,d_out) contiguous CUDA float32; lengths CUDA int64 (B,); frames = GLOBAL
         number of valid frames (host number; checked against the device-side count when the losses are read,
         see loss_dict).  Returns the device tensor of 12 loss scalars.
@@ -137,16 +137,22 @@ class FusedGanStep(object):
             if self.g.training != self.d.training:
                 raise RuntimeError("FusedGanStep: generator and discriminator disagree on train()/eval()")
             train = self.g.training
-        self._frames_claim = float(frames)
-        inv = 1.0 / float(frames)
+        world = torch.distributed.get_world_size(self.pg) if (torch.distributed.is_available()
+                                                              and torch.distributed.is_initialized()) else 1
+        if frames is None:
+            # single process: the step derives 1 / mask.sum() on the device from `lengths` (no host number to trust)
+            if world > 1:
+                raise RuntimeError("FusedGanStep: data-parallel steps need frames = the GLOBAL number of valid frames")
+            self._frames_claim, inv = None, 0.0
+        else:
+            self._frames_claim = float(frames)
+            inv = 1.0 / float(frames)
         if not train:
             self._call(_lib.STEP_EVAL, x, y, lengths, inv, 0)
             return self.losses
         seed = (self._seed + self._step) & ((1 << 61) - 1)
         self.last_seed = seed
         self._step += 1
-        world = torch.distributed.get_world_size(self.pg) if (torch.distributed.is_available()
-                                                              and torch.distributed.is_initialized()) else 1
         if world == 1:
             self._call(7, x, y, lengths, inv, seed)
         else:

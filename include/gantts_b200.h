@@ -297,7 +297,8 @@ int gantts_sru_bwd(const float* u, const float* x, const float* bias, const floa
  *   1 = prologue, G forward, MLPG, D forward on [real | fake], loss_d backward  -> D gradients ready
  *   2 = D clip+Adagrad, MGE/MSE/ADV losses, third D forward, loss_g backward    -> G gradients ready
  *   4 = G clip+Adagrad, loss scalars
- * inv_frames = 1 / (GLOBAL number of valid frames) (reference normaliser T = mask.sum()).
+ * inv_frames = 1 / (GLOBAL number of valid frames) (reference normaliser T = mask.sum()); a value <= 0 makes the
+ * step derive it on the device from lengths_dev (single-process use).
  * losses_dev[12] = loss_d, loss_fake_d, loss_real_d, loss_mse, loss_mge, loss_adv, loss_g,
  *                  real_correct, fake_correct, local frames, d_grad_norm, g_grad_norm.
  */
