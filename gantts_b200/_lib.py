@@ -14,6 +14,7 @@ MAX_WINDOWS = 4
 MAX_TAPS = 5
 MLPG_HALF_TAPS = 24
 MLPG_NTAPS = 2 * MLPG_HALF_TAPS + 1
+MLPG_TABLE_COLS = 60      # GANTTS_MLPG_TABLE_COLS: FIR taps + banded-Cholesky rows
 
 ENGINE_SIMT = 0
 ENGINE_TC = 1

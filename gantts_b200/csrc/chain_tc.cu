@@ -434,7 +434,10 @@ chain_pair_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
         ptx::tc_fence_after();
         // backward: the A buffer is free once the LAST layer's MMAs are done -> produce the next tile's head first,
         // so that its first MMAs run under this tile's last epilogue
-        if (BWD && last && tile + tile_step < num_tiles) head(tile + tile_step);
+        // (only when this layer does not stage planes through the A buffer itself: otherwise the head follows it)
+        const bool head_early = BWD && last && !to_store && tile + tile_step < num_tiles;
+        const bool head_late = BWD && last && to_store && tile + tile_step < num_tiles;
+        if (head_early) head(tile + tile_step);
         if (to_smem) wait_stores();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256;
         float gemv = 0.f;
@@ -514,6 +517,7 @@ chain_pair_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
           }
         }
         if (to_store) ++st_issued;
+        if (head_late) head(tile + tile_step);
         // accumulator drained
         ptx::tc_fence_before();
         __syncwarp();
@@ -546,16 +550,16 @@ chain_pair_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
 // ---------------------------------------------------------------------------- host side
 // Where the chain kernel replaces the per-layer launches (GANTTS_B200_CHAIN, bit mask): 1 = forward, 2 = backward
 // without weight gradients (the adversarial pass: nothing but the input gradient leaves the chip), 4 = backward with
-// weight gradients (the gradient planes still go to HBM for the weight-gradient GEMMs).  Measured on B200 at cfg2
-// (profiles/r02_chain.md).
+// weight gradients (the gradient planes still go to HBM for the weight-gradient GEMMs).
+// DEFAULT OFF.  Measured on B200 at cfg2 (profiles/r02_chain.md): the kernel is correct (the whole -m gpu suite passes
+// with modes 1|2) but SLOWER in the step than the per-layer launches it replaces (1.345 vs 1.273 ms/step with 1|2,
+// 1.445 with 7; tensor pipe 17 % active): inside one tile the layers are strictly serial -- epilogue of layer l, then
+// MMAs of layer l+1 -- and a 128 x 256 activation tile (128 KB as hi/lo planes) leaves no shared memory for a second
+// tile in flight, whereas the per-layer kernels overlap the epilogue of tile i with the MMAs of tile i+1.
 constexpr int CHAIN_FWD = 1, CHAIN_BWD_NOGRAD = 2, CHAIN_BWD_GRAD = 4;
-static int use_chain() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("GANTTS_B200_CHAIN");
-    v = e ? atoi(e) : (CHAIN_FWD | CHAIN_BWD_NOGRAD);
-  }
-  return v;
+static int use_chain() {          // read on every call (cheap) so that tests can switch it per case
+  const char* e = getenv("GANTTS_B200_CHAIN");
+  return e ? atoi(e) : 0;
 }
 
 static inline int pad64(int v) { return (v + 63) / 64 * 64; }

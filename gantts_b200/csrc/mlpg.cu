@@ -20,6 +20,7 @@ namespace gantts {
 
 constexpr int K_HALF = GANTTS_MLPG_HALF_TAPS;     // 24
 constexpr int NTAPS = 2 * K_HALF + 1;             // 49
+constexpr int TABW = GANTTS_MLPG_TABLE_COLS;      // floats per table row: 49 FIR taps, pad, Cholesky rows at 52 and 56
 constexpr int GROW = 52;                          // taps padded to a float4 multiple
 constexpr int TT = 64;                            // frames per block
 constexpr int TC = 64;                            // columns per block
@@ -78,7 +79,7 @@ mlpg_fwd_kernel(const float* __restrict__ in, int64_t in_bs, int64_t in_ts,
 
   for (int i = threadIdx.x; i < TT * GROW; i += MLPG_THREADS) {
     int r = i / GROW, j = i - r * GROW, t = t0 + r;
-    gs[i] = (t < T && j < NTAPS) ? table[(int64_t)t * NTAPS + j] : 0.f;
+    gs[i] = (t < T && j < NTAPS) ? table[(int64_t)t * TABW + j] : 0.f;
   }
   // Phase 1: b = W^T mu over [t0-K, t0+TT+K) (or the raw input for static streams).  Each thread owns ONE
   // column (stream lookup hoisted) and strides over rows; the non-zero window taps are compacted once per
@@ -187,7 +188,7 @@ mlpg_bwd_kernel(const float* __restrict__ go, int64_t go_bs, int64_t go_ts,
 
   for (int i = threadIdx.x; i < 72 * GROW; i += MLPG_THREADS) {
     int r = i / GROW, j = i - r * GROW, t = t0 - HALO + r;
-    gs[i] = (t >= 0 && t < T && j < NTAPS && r < ZROWS) ? table[(int64_t)t * NTAPS + j] : 0.f;
+    gs[i] = (t >= 0 && t < T && j < NTAPS && r < ZROWS) ? table[(int64_t)t * TABW + j] : 0.f;
   }
   for (int i = threadIdx.x; i < GIN_ROWS * TC; i += MLPG_THREADS) {
     int r = i / TC, c = i - r * TC, t = t0 - HALO - K_HALF + r, oc = c0 + c;
@@ -247,6 +248,199 @@ mlpg_bwd_kernel(const float* __restrict__ go, int64_t go_bs, int64_t go_ts,
       }
     }
   }
+}
+
+
+// ---------------------------------------------------------------------------- substitution kernels (half bandwidth <= 2)
+// y = P^-1 b by banded Cholesky substitution instead of the 49-tap FIR: P = L L^T is pentadiagonal for the hparams
+// windows, so a forward and a backward sweep cost 2 x 3 flops per frame where the FIR costs 49.  Both sweeps are
+// sequential in t; parallelism comes from (batch row, column, time chunk): a chunk of SC frames is solved from a zero
+// state SW frames earlier (forward) / later (backward) -- the influence of the state decays like |r|^n with
+// |r| = sqrt(L2/L0) = 0.389 for these windows (0.389^32 = 8e-14, below fp32 resolution); chunks that touch the ends of
+// the utterance start from the exact boundary state.  One warp = 32 consecutive output columns (lane = column: every
+// load and store is a coalesced row segment), the forward sweep parks z in shared memory for the backward sweep.  The
+// per-column arithmetic depends on T only (chunking), not on which columns share the launch: the reference's bitwise
+// whole-vs-slice property (tests/test_gantts.py:156-159) holds.
+constexpr int SC = 64;                 // frames per chunk
+constexpr int SW = 32;                 // warm-up frames on either side
+constexpr int SOLVE_WARPS = 4;
+constexpr int SOLVE_ZROWS = SC + SW + 4;
+
+struct SolveTaps {
+  float c[GANTTS_MAX_WINDOWS][5];      // coefficient of mu_w[t - k] in b_t, k = -2..2 at index k + 2 (0 where absent)
+  int nw;
+};
+
+__device__ __forceinline__ float4 chol_fwd(const float* __restrict__ table, int t) {
+  return __ldg(reinterpret_cast<const float4*>(table + (int64_t)t * TABW + 52));
+}
+__device__ __forceinline__ float4 chol_bwd(const float* __restrict__ table, int t) {
+  return __ldg(reinterpret_cast<const float4*>(table + (int64_t)t * TABW + 56));
+}
+
+__global__ void __launch_bounds__(32 * SOLVE_WARPS)
+mlpg_solve_fwd_kernel(const float* __restrict__ in, int64_t in_bs, int64_t in_ts, float* __restrict__ out, int64_t out_bs,
+                      int64_t out_ts, const float* __restrict__ table, gantts_streams_t st, SolveTaps taps, int T,
+                      int ncols, int nchunks, int ncg, int64_t nitems) {
+  extern __shared__ __align__(16) float smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t item = (int64_t)blockIdx.x * SOLVE_WARPS + wib;
+  if (item >= nitems) return;
+  float* zs = smem + (size_t)wib * SOLVE_ZROWS * 32;
+  const int cg = (int)(item % ncg), chunk = (int)((item / ncg) % nchunks), b = (int)(item / ((int64_t)ncg * nchunks));
+  const int oc = cg * 32 + lane;
+  ColInfo ci = find_col(st, oc);
+  const bool valid = ci.in_col >= 0 && oc < ncols;
+  const bool dyn = valid && ci.dyn;
+  const float* colp = in + (int64_t)b * in_bs + (valid ? ci.in_col : 0);
+  const int t0 = chunk * SC;
+  const int t1 = t0 + SC < T ? t0 + SC : T;                 // outputs [t0, t1)
+  const int s = t0 - SW > 0 ? t0 - SW : 0;                  // forward sweep start (exact state when s == 0)
+  const int e = t1 + SW < T ? t1 + SW : T;                  // sweeps end (exact state when e == T)
+  // sliding window of mu_w rows t-2 .. t+2 per window
+  float x[GANTTS_MAX_WINDOWS][5];
+#pragma unroll
+  for (int w = 0; w < GANTTS_MAX_WINDOWS; ++w) {
+#pragma unroll
+    for (int q = 0; q < 5; ++q) x[w][q] = 0.f;
+  }
+  auto load_row = [&](int w, int t) -> float {
+    return (valid && t >= 0 && t < T && (dyn || w == 0)) ? __ldg(colp + (int64_t)t * in_ts + (dyn ? w * ci.sd : 0)) : 0.f;
+  };
+#pragma unroll
+  for (int w = 0; w < GANTTS_MAX_WINDOWS; ++w) {
+    if (w < taps.nw) {
+      x[w][2] = load_row(w, s);           // rows s-2, s-1 contribute to b_s through taps of rows outside [0,T) only when
+      x[w][3] = load_row(w, s + 1);       // s == 0 (they are zero); for s > 0 the warm-up absorbs the truncation
+      x[w][4] = load_row(w, s + 2);
+      x[w][1] = load_row(w, s - 1);
+      x[w][0] = load_row(w, s - 2);
+    }
+  }
+  float z1 = 0.f, z2 = 0.f;
+  for (int t = s; t < e; ++t) {
+    float bt = 0.f;
+#pragma unroll
+    for (int w = 0; w < GANTTS_MAX_WINDOWS; ++w) {
+      if (w < taps.nw) {
+#pragma unroll
+        for (int k = -2; k <= 2; ++k) bt = fmaf(taps.c[w][k + 2], x[w][2 - k], bt);      // mu_w[t - k]
+      }
+    }
+    const float4 cf = chol_fwd(table, t);
+    float z = (bt - cf.y * z1 - cf.z * z2) * cf.x;
+    if (!dyn) z = x[0][2];               // static stream: copied through
+    z2 = z1;
+    z1 = z;
+    if (t >= t0) zs[(t - t0) * 32 + lane] = z;
+#pragma unroll
+    for (int w = 0; w < GANTTS_MAX_WINDOWS; ++w) {
+      if (w < taps.nw) {
+        x[w][0] = x[w][1]; x[w][1] = x[w][2]; x[w][2] = x[w][3]; x[w][3] = x[w][4];
+        x[w][4] = load_row(w, t + 3);
+      }
+    }
+  }
+  float y1 = 0.f, y2 = 0.f;
+  float* outp = out + (int64_t)b * out_bs + oc;
+  for (int t = e - 1; t >= t0; --t) {
+    const float4 cb = chol_bwd(table, t);
+    const float4 cf = chol_fwd(table, t);
+    const float zt = zs[(t - t0) * 32 + lane];
+    float y = (zt - cb.x * y1 - cb.y * y2) * cf.x;
+    if (!dyn) y = zt;
+    y2 = y1;
+    y1 = y;
+    if (t < t1 && valid) outp[(int64_t)t * out_ts] = y;
+  }
+}
+
+// Adjoint: z = P^-1 g (same two sweeps on the upstream gradient), gi_w[t] = sum_k coef_w[k+l] z_{t+k}.
+__global__ void __launch_bounds__(32 * SOLVE_WARPS)
+mlpg_solve_bwd_kernel(const float* __restrict__ go, int64_t go_bs, int64_t go_ts, float* __restrict__ gi, int64_t gi_bs,
+                      int64_t gi_ts, const float* __restrict__ table, gantts_streams_t st, SolveTaps taps, int T, int ncols,
+                      int nchunks, int ncg, int64_t nitems, int accumulate) {
+  extern __shared__ __align__(16) float smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t item = (int64_t)blockIdx.x * SOLVE_WARPS + wib;
+  if (item >= nitems) return;
+  float* zs = smem + (size_t)wib * SOLVE_ZROWS * 32;
+  const int cg = (int)(item % ncg), chunk = (int)((item / ncg) % nchunks), b = (int)(item / ((int64_t)ncg * nchunks));
+  const int oc = cg * 32 + lane;
+  ColInfo ci = find_col(st, oc);
+  const bool valid = ci.in_col >= 0 && oc < ncols;
+  const bool dyn = valid && ci.dyn;
+  const float* gop = go + (int64_t)b * go_bs + oc;
+  const int t0 = chunk * SC;
+  const int t1 = t0 + SC < T ? t0 + SC : T;                 // gradient rows [t0, t1) are produced here
+  const int lo = t0 - 2 > 0 ? t0 - 2 : 0;                   // z is needed on [t0-2, t1+2)
+  const int hi = t1 + 2 < T ? t1 + 2 : T;
+  const int s = lo - SW > 0 ? lo - SW : 0;
+  const int e = hi + SW < T ? hi + SW : T;
+  float z1 = 0.f, z2 = 0.f;
+  for (int t = s; t < e; ++t) {
+    const float g = valid ? __ldg(gop + (int64_t)t * go_ts) : 0.f;
+    const float4 cf = chol_fwd(table, t);
+    float z = (g - cf.y * z1 - cf.z * z2) * cf.x;
+    if (!dyn) z = g;
+    z2 = z1;
+    z1 = z;
+    if (t >= lo) zs[(t - lo) * 32 + lane] = z;               // rows lo .. e-1 (<= SC + 4 + SW... bounded by SOLVE_ZROWS + 2)
+  }
+  // backward sweep from e-1 down to lo; window zw[q] = z_{t + q}, q = 0..4, zero outside [0, T)
+  float zw[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  float y1 = 0.f, y2 = 0.f;
+  float* gib = gi + (int64_t)b * gi_bs + (valid ? ci.in_col : 0);
+  for (int t = e - 1; t >= t0 - 2; --t) {
+    float y = 0.f;
+    if (t >= lo) {
+      const float4 cb = chol_bwd(table, t);
+      const float4 cf = chol_fwd(table, t);
+      const float zt = zs[(t - lo) * 32 + lane];
+      y = (zt - cb.x * y1 - cb.y * y2) * cf.x;
+      if (!dyn) y = zt;
+      y2 = y1;
+      y1 = y;
+    }
+    zw[4] = zw[3]; zw[3] = zw[2]; zw[2] = zw[1]; zw[1] = zw[0];
+    zw[0] = (t >= 0 && t < hi) ? y : 0.f;                    // z beyond the needed range only feeds rows we do not emit
+    const int tp = t + 2;                                    // row whose window z_{tp-2..tp+2} is now complete
+    if (valid && tp >= t0 && tp < t1) {
+      float* prow = gib + (int64_t)tp * gi_ts;
+      if (!dyn) {
+        prow[0] = accumulate ? prow[0] + zw[2] : zw[2];
+      } else {
+#pragma unroll
+        for (int w = 0; w < GANTTS_MAX_WINDOWS; ++w) {
+          if (w < taps.nw) {
+            float v = 0.f;
+#pragma unroll
+            for (int k = -2; k <= 2; ++k) v = fmaf(taps.c[w][k + 2], zw[2 + k], v);       // z_{tp + k}
+            float* q = prow + w * ci.sd;
+            *q = accumulate ? *q + v : v;
+          }
+        }
+      }
+    }
+  }
+}
+
+static bool solve_taps(const gantts_windows_t* win, SolveTaps* tp) {
+  int hb = 0;
+  tp->nw = win->n;
+  for (int w = 0; w < GANTTS_MAX_WINDOWS; ++w)
+    for (int q = 0; q < 5; ++q) tp->c[w][q] = 0.f;
+  for (int w = 0; w < win->n; ++w) {
+    if (win->l[w] > 2 || win->u[w] > 2) return false;
+    hb = win->l[w] + win->u[w] > hb ? win->l[w] + win->u[w] : hb;
+    for (int k = -win->l[w]; k <= win->u[w]; ++k) tp->c[w][k + 2] = win->coef[w][k + win->l[w]];
+  }
+  static int use = -1;
+  if (use < 0) {
+    const char* e = getenv("GANTTS_B200_MLPG_SOLVE");
+    use = e ? atoi(e) : 1;
+  }
+  return use && hb <= 2;
 }
 
 static int check_layout(const gantts_streams_t* st, const gantts_windows_t* win, int* ncols) {
@@ -315,6 +509,21 @@ extern "C" int gantts_mlpg_table(const gantts_windows_t* win, int T, float* tabl
       L[(size_t)(i - j) * T + j] = s / d;
     }
   }
+  // Cholesky rows for the substitution kernels (half bandwidth <= 2): forward  z_i = (b_i - f1 z_{i-1} - f2 z_{i-2}) invd,
+  // backward  y_i = (z_i - b1 y_{i+1} - b2 y_{i+2}) invd  with f1 = L[i][i-1], f2 = L[i][i-2], b1 = L[i+1][i], b2 = L[i+2][i]
+  for (int t = 0; t < T; ++t) {
+    float* row = table_host + (size_t)t * TABW;
+    for (int j = NTAPS; j < TABW; ++j) row[j] = 0.f;
+    auto Lat = [&](int i, int j) -> double {      // L[i][j], i >= j
+      const int d = i - j;
+      return (i < T && j >= 0 && d >= 0 && d <= hb) ? L[(size_t)d * T + j] : 0.0;
+    };
+    row[52] = (float)(1.0 / Lat(t, t));
+    row[53] = (float)Lat(t, t - 1);
+    row[54] = (float)Lat(t, t - 2);
+    row[56] = (float)Lat(t + 1, t);
+    row[57] = (float)Lat(t + 2, t);
+  }
   std::vector<double> x(T);
   double worst_tail = 0.0;
   for (int t = 0; t < T; ++t) {
@@ -333,7 +542,7 @@ extern "C" int gantts_mlpg_table(const gantts_windows_t* win, int T, float* tabl
     }
     for (int j = 0; j < NTAPS; ++j) {
       int c = t + j - K_HALF;
-      table_host[(size_t)t * NTAPS + j] = (c >= 0 && c < T) ? (float)x[c] : 0.f;
+      table_host[(size_t)t * TABW + j] = (c >= 0 && c < T) ? (float)x[c] : 0.f;
     }
     double tail = 0.0;
     if (t - K_HALF - 1 >= 0) tail = fabs(x[t - K_HALF - 1]);
@@ -356,6 +565,23 @@ extern "C" int gantts_mlpg_fwd(const float* in, int64_t in_bs, int64_t in_ts, fl
   int rc = check_layout(st, win, &ncols);
   if (rc) return rc;
   GANTTS_CHECK_ARG(in && out && table_dev && B >= 1 && T >= 1, "mlpg_fwd: bad arguments");
+  {
+    SolveTaps tp;
+    if (solve_taps(win, &tp)) {
+      const int nchunks = (T + SC - 1) / SC, ncg = (ncols + 31) / 32;
+      const int64_t nitems = (int64_t)B * nchunks * ncg;
+      const size_t sm = (size_t)SOLVE_WARPS * SOLVE_ZROWS * 32 * sizeof(float);
+      GANTTS_CUDA(cudaFuncSetAttribute(mlpg_solve_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      int in_cols = 0;
+      for (int s = 0; s < st->n; ++s) in_cols += st->sd[s] * (st->dyn[s] ? win->n : 1);
+      prof_begin(PROF_MLPG_FWD, 4.0 * (double)B * T * (in_cols + ncols), as_stream(stream));
+      mlpg_solve_fwd_kernel<<<(unsigned)((nitems + SOLVE_WARPS - 1) / SOLVE_WARPS), 32 * SOLVE_WARPS, sm, as_stream(stream)>>>(
+          in, in_bs, in_ts, out, out_bs, out_ts, table_dev, *st, tp, T, ncols, nchunks, ncg, nitems);
+      prof_end(as_stream(stream));
+      GANTTS_LAUNCH_CHECK("mlpg_solve_fwd_kernel");
+      return GANTTS_OK;
+    }
+  }
   const size_t smem = ((TT + 2 * K_HALF) * TC + TT * GROW) * sizeof(float);
   static bool attr_done_dev[64] = {};
   int dev_id = -1;
@@ -389,6 +615,23 @@ extern "C" int gantts_mlpg_bwd(const float* go, int64_t go_bs, int64_t go_ts, fl
   int rc = check_layout(st, win, &ncols);
   if (rc) return rc;
   GANTTS_CHECK_ARG(go && gi && table_dev && B >= 1 && T >= 1, "mlpg_bwd: bad arguments");
+  {
+    SolveTaps tp;
+    if (solve_taps(win, &tp)) {
+      const int nchunks = (T + SC - 1) / SC, ncg = (ncols + 31) / 32;
+      const int64_t nitems = (int64_t)B * nchunks * ncg;
+      const size_t sm = (size_t)SOLVE_WARPS * SOLVE_ZROWS * 32 * sizeof(float);
+      GANTTS_CUDA(cudaFuncSetAttribute(mlpg_solve_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      int in_cols = 0;
+      for (int s = 0; s < st->n; ++s) in_cols += st->sd[s] * (st->dyn[s] ? win->n : 1);
+      prof_begin(PROF_MLPG_BWD, 4.0 * (double)B * T * (in_cols + ncols), as_stream(stream));
+      mlpg_solve_bwd_kernel<<<(unsigned)((nitems + SOLVE_WARPS - 1) / SOLVE_WARPS), 32 * SOLVE_WARPS, sm, as_stream(stream)>>>(
+          go, go_bs, go_ts, gi, gi_bs, gi_ts, table_dev, *st, tp, T, ncols, nchunks, ncg, nitems, accumulate);
+      prof_end(as_stream(stream));
+      GANTTS_LAUNCH_CHECK("mlpg_solve_bwd_kernel");
+      return GANTTS_OK;
+    }
+  }
   const size_t smem = (GIN_ROWS * TC + 72 * GROW + 72 * TC) * sizeof(float);
   static bool attr_done_dev[64] = {};
   int dev_id = -1;

@@ -79,20 +79,26 @@ def windows_for(num_windows):
     return w
 
 
-def mlpg_table_host(windows, T):
-    """Rows of P^-1 within +-24 taps, float32 (T, 49); host computation inside the C library."""
+def mlpg_table_full_host(windows, T):
+    """The coefficient table the kernels read, float32 (T, GANTTS_MLPG_TABLE_COLS): rows of P^-1 within +-24 taps
+    followed by the rows of the banded Cholesky factor of P; host fp64 computation inside the C library."""
     lib = _lib.load()
     w = _lib.make_windows(windows)
-    tab = np.zeros((int(T), _lib.MLPG_NTAPS), dtype=np.float32)
+    tab = np.zeros((int(T), _lib.MLPG_TABLE_COLS), dtype=np.float32)
     _lib.check(lib.gantts_mlpg_table(ctypes.byref(w), int(T), tab.ctypes.data))
     return tab
+
+
+def mlpg_table_host(windows, T):
+    """Rows of P^-1 within +-24 taps, float32 (T, 49)."""
+    return np.ascontiguousarray(mlpg_table_full_host(windows, T)[:, :_lib.MLPG_NTAPS])
 
 
 def mlpg_table(windows, T, device):
     key = (windows_key(windows), int(T), device.index)
     t = _table_cache.get(key)
     if t is None:
-        t = torch.from_numpy(mlpg_table_host(windows, T)).to(device)
+        t = torch.from_numpy(mlpg_table_full_host(windows, T)).to(device)
         _table_cache[key] = t
     return t
 
@@ -460,7 +466,7 @@ def peek_seeds(n):
 
 def dropout_mask(rows, cols, p, seed, device):
     """The dropout multiplier {0, 1/(1-p)} every engine applies for (seed, rows, cols): float32 (rows, cols).
-    Test hook for injected-mask parity against the oracle (gantts_dropout on a tensor of ones)."""
+    Test hook for injected-mask parity against the CPU checker (gantts_dropout on a tensor of ones)."""
     lib = _lib.load()
     ones = torch.ones(int(rows), int(cols), dtype=torch.float32, device=device)
     out = torch.empty_like(ones)

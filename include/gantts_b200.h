@@ -30,6 +30,9 @@ extern "C" {
 #define GANTTS_MAX_WINDOWS 4
 #define GANTTS_MAX_WINDOW_TAPS 5 /* l, u <= 2 */
 #define GANTTS_MLPG_HALF_TAPS 24 /* FIR half width K: P^-1 decays to 2.6e-10 at lag 24 */
+/* floats per row of the MLPG coefficient table: [0, 2K+1) rows of P^-1 (FIR form), [52, 56) = {1/L_tt, L[t][t-1], L[t][t-2], 0}
+ * and [56, 60) = {L[t+1][t], L[t+2][t], 0, 0}: rows of the banded Cholesky factor of P for the substitution kernels */
+#define GANTTS_MLPG_TABLE_COLS 60
 #define GANTTS_MAX_LAYERS 8
 #define GANTTS_MAX_COLS 256 /* static / adversarial column lists of the fused step */
 
@@ -79,7 +82,7 @@ typedef struct {
  * (K = GANTTS_MLPG_HALF_TAPS), over the PADDED length T for every batch row, exactly like the
  * reference (SURVEY.md 8a note iv).
  *
- * gantts_mlpg_table: HOST function.  Fills table_host[T * (2K+1)] with
+ * gantts_mlpg_table: HOST function.  Fills table_host[T * GANTTS_MLPG_TABLE_COLS] (row stride GANTTS_MLPG_TABLE_COLS) with
  *   table[t][j] = (P^-1)[t, t + j - K]   (0 outside [0,T)), computed in float64 by banded Cholesky,
  * stored as float32.  The caller uploads it once per (windows, T) and passes the device copy below.
  * Returns GANTTS_E_UNSUPPORTED when P^-1 has not decayed below 1e-8 of its diagonal at lag K.
