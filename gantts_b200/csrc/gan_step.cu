@@ -12,9 +12,18 @@
 //     BEFORE the third forward used by the adversarial loss;
 //   * losses are normalised by the number of valid frames, BCE uses log(D + 1e-20) verbatim.
 // Real and fake discriminator batches are stacked into one 2M-row batch (one GEMM per layer).
+#include <nvtx3/nvToolsExt.h>
+
 #include "common.cuh"
 
 namespace gantts {
+
+// NVTX range per phase of the step (header-only NVTX3: a no-op unless a profiler is attached; `ncu --nvtx` and nsys
+// show the phases of one gantts_gan_step call on the timeline).
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 enum ScalarSlot {
   S_REAL = 0,      // [0..2]  real: loss sum, correct count, sum(mask)
@@ -478,6 +487,7 @@ extern "C" int gantts_gan_step(const gantts_gan_step_t* c, int phases, const flo
 
   RedCounts cnt{};
   if (phases & GANTTS_STEP_EVAL) {
+    NvtxRange r_eval("gantts_gan_step/eval");
     // ---- "test" phase of train.py:481-486 (model.eval(), phase != "train" at :273,:315): forwards and losses only
     GANTTS_CHECK_ARG(phases == GANTTS_STEP_EVAL, "gan_step: GANTTS_STEP_EVAL cannot be combined with training phases");
     g.dropout_p = 0.f;
@@ -527,6 +537,7 @@ extern "C" int gantts_gan_step(const gantts_gan_step_t* c, int phases, const flo
   }
 
   if (phases & 1) {
+    NvtxRange r1("gantts_gan_step/phase1: G fwd, MLPG, MGE, D fwd+bwd");
     // ---- prologue: mask, scales, y_static (train.py:528-535)
     if ((rc = gantts_sequence_mask(lengths_dev, L.mask, c->B, c->T, stream))) return rc;
     set_scales_kernel<<<1, 32, 0, st>>>(L.scal, inv_frames, has_adv ? c->adv_w : 0.f, c->mge_w, c->mse_w, 0, lengths_dev, c->B, c->T);
@@ -589,6 +600,7 @@ extern "C" int gantts_gan_step(const gantts_gan_step_t* c, int phases, const flo
     }
   }
   if (phases & 2) {
+    NvtxRange r2("gantts_gan_step/phase2: D step, adv D fwd+bwd, MLPG bwd, G bwd");
     if (has_d) {
       // ---- clip_grad_norm_ + Adagrad on D (train.py:275-276)
       if ((rc = clip_adagrad_model(pd, L.opt_partial, L.scal + S_DSUMSQ, c->max_norm, c->lr_d, c->wd_d, c->eps, st)))
@@ -638,6 +650,7 @@ extern "C" int gantts_gan_step(const gantts_gan_step_t* c, int phases, const flo
       return rc;
   }
   if (phases & 4) {
+    NvtxRange r4("gantts_gan_step/phase4: G step, losses");
     // ---- clip_grad_norm_ + Adagrad on G (train.py:317-318), then the loss scalars
     if ((rc = clip_adagrad_model(pg, L.opt_partial, L.scal + S_GSUMSQ, c->max_norm, c->lr_g, c->wd_g, c->eps, st)))
       return rc;

@@ -44,6 +44,7 @@ struct GemmParams {
   int bn;               // MMA N, multiple of 64, <= 256
   int num_stages;
   uint32_t stage_bytes, b_plane_bytes, tx_bytes;
+  uint32_t bres_bytes;  // pair kernel, BRES: bytes of the resident B operand in front of the stage ring
   int bk;               // reduction elements per smem stage: 64 (SWIZZLE_128B K-major rows) or 32 (SWIZZLE_64B)
   uint32_t a_plane;     // bytes of one A plane tile in a stage
   uint32_t atom_bytes;  // MN-major: bytes of one 64-wide atom ([bk rows][128 B]) = its LBO
@@ -569,7 +570,11 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
 // and the smem stage shrinks to 64 KB (3 stages).  Leader = cluster rank 0: it alone issues the MMAs; its
 // `full` barriers collect the TMA bytes of BOTH CTAs; commits are multicast to both CTAs' barriers; the
 // peer's epilogue warps release the accumulator on the leader's barrier with a remote arrive.
-template <int EPI>
+// BRES = true: the WHOLE B operand of the column tile (N <= 256 rows, K <= 256: the discriminator's weight matrices,
+// 128 KB of hi/lo planes per CTA of the pair) is loaded ONCE and stays in shared memory for every row tile of the
+// persistent CTA; only A streams (32-wide K stages, SWIZZLE_64B): the per-SM operand ingest per unit of MMA work drops
+// from (128 + N/2) to 128 rows, which is what bounds the streaming kernels (profiles/r01_gemm_experiments.md).
+template <int EPI, bool BRES>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                  const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
@@ -577,10 +582,12 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
-  const uint32_t bar_base = base + p.num_stages * p.stage_bytes;
+  const uint32_t ring0 = base + (BRES ? p.bres_bytes : 0u);          // resident B blocks first, then the stage ring
+  const uint32_t bar_base = ring0 + p.num_stages * p.stage_bytes;
   const uint32_t full0 = bar_base, empty0 = bar_base + 8 * TC_MAX_STAGES;
   const uint32_t tfull0 = bar_base + 16 * TC_MAX_STAGES, tempty0 = tfull0 + 16;
   const uint32_t tmem_slot = tempty0 + 16;
+  const uint32_t bfull = tmem_slot + 8;                              // BRES: the resident B operand has landed
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t crank = ptx::cluster_ctarank();
   const bool leader = crank == 0;
@@ -594,6 +601,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant
       ptx::mbar_init(tfull0 + 8 * a, 1);
       ptx::mbar_init(tempty0 + 8 * a, 2 * TC_EPI_WARPS);      // both CTAs' epilogue warps (leader's copy is used)
     }
+    if (BRES) ptx::mbar_init(bfull, 1);
     ptx::fence_barrier_init();
     ptx::prefetch_tensormap(&tmAh);
     ptx::prefetch_tensormap(&tmAl);
@@ -628,6 +636,16 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant
     if (lane == 0) {
       // ------------------------------------------------------------ TMA producer (both CTAs)
       uint32_t s = 0, ph = 0;
+      if (BRES) {
+        // the CTA's half of the B rows, every 64-wide K block, once
+        const int nkb = (int)((p.red + 63) / 64);
+        if (leader) ptx::mbar_expect_tx(bfull, 2u * (uint32_t)nkb * 2u * p.b_plane_bytes);
+        const uint32_t bb = ptx::mapa(bfull, 0);
+        for (int kb = 0; kb < nkb; ++kb) {
+          ptx::tma_load_2d_pair(base + kb * 2 * p.b_plane_bytes, &tmBh, bb, kb * 64, (int)crank * half_bn);
+          ptx::tma_load_2d_pair(base + kb * 2 * p.b_plane_bytes + p.b_plane_bytes, &tmBl, bb, kb * 64, (int)crank * half_bn);
+        }
+      }
       for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
         const int ta = (tile / p.num_b) * 2 + (int)crank, tb = tile % p.num_b;
         const int a0 = ta * TC_BM, b0 = tb * p.bn + (int)crank * half_bn;
@@ -636,12 +654,14 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant
           const uint32_t fb_local = full0 + 8 * s;
           if (leader) ptx::mbar_expect_tx(fb_local, 2 * p.tx_bytes);   // bytes of both CTAs land on this barrier
           const uint32_t fb = ptx::mapa(fb_local, 0);
-          const uint32_t sa_hi = base + s * p.stage_bytes, sa_lo = sa_hi + p.a_plane;
-          const uint32_t sb_hi = sa_lo + p.a_plane, sb_lo = sb_hi + p.b_plane_bytes;
+          const uint32_t sa_hi = ring0 + s * p.stage_bytes, sa_lo = sa_hi + p.a_plane;
           ptx::tma_load_2d_pair(sa_hi, &tmAh, fb, (int32_t)r0, a0);
-          ptx::tma_load_2d_pair(sb_hi, &tmBh, fb, (int32_t)r0, b0);
           ptx::tma_load_2d_pair(sa_lo, &tmAl, fb, (int32_t)r0, a0);
-          ptx::tma_load_2d_pair(sb_lo, &tmBl, fb, (int32_t)r0, b0);
+          if (!BRES) {
+            const uint32_t sb_hi = sa_lo + p.a_plane, sb_lo = sb_hi + p.b_plane_bytes;
+            ptx::tma_load_2d_pair(sb_hi, &tmBh, fb, (int32_t)r0, b0);
+            ptx::tma_load_2d_pair(sb_lo, &tmBl, fb, (int32_t)r0, b0);
+          }
           if (++s == (uint32_t)p.num_stages) { s = 0; ph ^= 1; }
         }
       }
@@ -652,6 +672,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant
       const uint32_t idesc = ptx::make_idesc_bf16(2 * TC_BM, p.bn, 0, 0);
       uint32_t s = 0, ph = 0;
       int it = 0;
+      if (BRES) ptx::mbar_wait(bfull, 0);
       for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++it) {
         const int acc = it & 1;
         const uint32_t aph = (it >> 1) & 1;
@@ -662,17 +683,34 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant
         for (int64_t r0 = 0; r0 < p.red; r0 += p.bk) {
           ptx::mbar_wait(full0 + 8 * s, ph);
           ptx::tc_fence_after();
-          const uint32_t sa_hi = base + s * p.stage_bytes, sa_lo = sa_hi + p.a_plane;
-          const uint32_t sb_hi = sa_lo + p.a_plane, sb_lo = sb_hi + p.b_plane_bytes;
-          for (int k = 0; k < p.bk / 16; ++k) {
-            const uint64_t da_hi = ptx::make_smem_desc(sa_hi + k * 32u, 0u, p.sbo, p.desc_layout);
-            const uint64_t da_lo = ptx::make_smem_desc(sa_lo + k * 32u, 0u, p.sbo, p.desc_layout);
-            const uint64_t db_hi = ptx::make_smem_desc(sb_hi + k * 32u, 0u, p.sbo, p.desc_layout);
-            const uint64_t db_lo = ptx::make_smem_desc(sb_lo + k * 32u, 0u, p.sbo, p.desc_layout);
-            ptx::mma_bf16_ss_pair(d_tmem, da_hi, db_hi, idesc, first);
-            first = 1;
-            ptx::mma_bf16_ss_pair(d_tmem, da_hi, db_lo, idesc, 1);
-            ptx::mma_bf16_ss_pair(d_tmem, da_lo, db_hi, idesc, 1);
+          const uint32_t sa_hi = ring0 + s * p.stage_bytes, sa_lo = sa_hi + p.a_plane;
+          if (BRES) {
+            // A: 32-wide K stage (SWIZZLE_64B); B: resident 64-wide K block kb (SWIZZLE_128B), half (r0/32)&1 of it
+            const uint32_t kb = (uint32_t)(r0 >> 6), hb = (uint32_t)((r0 >> 5) & 1);
+            const uint32_t sb_hi = base + kb * 2 * p.b_plane_bytes + hb * 64u, sb_lo = sb_hi + p.b_plane_bytes;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              const uint64_t da_hi = ptx::make_smem_desc(sa_hi + k * 32u, 0u, 512u, 4u);
+              const uint64_t da_lo = ptx::make_smem_desc(sa_lo + k * 32u, 0u, 512u, 4u);
+              const uint64_t db_hi = ptx::make_smem_desc(sb_hi + k * 32u, 0u, 1024u, 2u);
+              const uint64_t db_lo = ptx::make_smem_desc(sb_lo + k * 32u, 0u, 1024u, 2u);
+              ptx::mma_bf16_ss_pair(d_tmem, da_hi, db_hi, idesc, first);
+              first = 1;
+              ptx::mma_bf16_ss_pair(d_tmem, da_hi, db_lo, idesc, 1);
+              ptx::mma_bf16_ss_pair(d_tmem, da_lo, db_hi, idesc, 1);
+            }
+          } else {
+            const uint32_t sb_hi = sa_lo + p.a_plane, sb_lo = sb_hi + p.b_plane_bytes;
+            for (int k = 0; k < p.bk / 16; ++k) {
+              const uint64_t da_hi = ptx::make_smem_desc(sa_hi + k * 32u, 0u, p.sbo, p.desc_layout);
+              const uint64_t da_lo = ptx::make_smem_desc(sa_lo + k * 32u, 0u, p.sbo, p.desc_layout);
+              const uint64_t db_hi = ptx::make_smem_desc(sb_hi + k * 32u, 0u, p.sbo, p.desc_layout);
+              const uint64_t db_lo = ptx::make_smem_desc(sb_lo + k * 32u, 0u, p.sbo, p.desc_layout);
+              ptx::mma_bf16_ss_pair(d_tmem, da_hi, db_hi, idesc, first);
+              first = 1;
+              ptx::mma_bf16_ss_pair(d_tmem, da_hi, db_lo, idesc, 1);
+              ptx::mma_bf16_ss_pair(d_tmem, da_lo, db_hi, idesc, 1);
+            }
           }
           ptx::mma_commit_pair(empty0 + 8 * s, (uint16_t)0x3);     // frees the stage in both CTAs
           if (++s == (uint32_t)p.num_stages) { s = 0; ph ^= 1; }
@@ -1169,6 +1207,12 @@ static int use_f32_stage() {
   return v;
 }
 
+// B-resident pair kernel for narrow layers (GANTTS_B200_BRES=0 disables); read per call so tests can switch it.
+static int use_bres() {
+  const char* e = getenv("GANTTS_B200_BRES");
+  return e ? atoi(e) : 1;
+}
+
 static int use_pdl() {
   static int v = -1;
   if (v < 0) {
@@ -1227,14 +1271,14 @@ static int launch_kernel(const CUtensorMap& mAh, const CUtensorMap& mAl, const C
   return GANTTS_OK;
 }
 
-template <int EPI>
+template <int EPI, bool BRES = false>
 static int launch_pair_kernel(const CUtensorMap& mAh, const CUtensorMap& mAl, const CUtensorMap& mBh,
                               const CUtensorMap& mBl, const GemmParams& p, cudaStream_t st) {
-  const size_t smem = (size_t)p.num_stages * p.stage_bytes + 1024 + 256 + TC_BIAS_SMEM;
+  const size_t smem = (size_t)(BRES ? p.bres_bytes : 0u) + (size_t)p.num_stages * p.stage_bytes + 1024 + 256 + TC_BIAS_SMEM;
   static bool attr[64] = {};
   const int dev = current_device();
   if (dev < 0 || dev >= 64 || !attr[dev]) {
-    GANTTS_CUDA(cudaFuncSetAttribute(gemm_pair_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    GANTTS_CUDA(cudaFuncSetAttribute(gemm_pair_kernel<EPI, BRES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     if (dev >= 0 && dev < 64) attr[dev] = true;
   }
   const int units = ((p.num_a + 1) / 2) * p.num_b;
@@ -1259,7 +1303,7 @@ static int launch_pair_kernel(const CUtensorMap& mAh, const CUtensorMap& mAl, co
   }
   cfg.attrs = at;
   cfg.numAttrs = na;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_pair_kernel<EPI>, mAh, mAl, mBh, mBl, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_pair_kernel<EPI, BRES>, mAh, mAl, mBh, mBl, p);
   prof_end(st);
   if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(gemm pair)");
   GANTTS_LAUNCH_CHECK("gemm_pair_kernel");
@@ -1363,6 +1407,31 @@ static int launch_gemm_kk(const Planes& A, const Planes& B, const EpiArgs& e, cu
   // bias staged in smem after the barrier block when it fits (padded to whole column tiles)
   p.bias_off = (e.bias && (size_t)p.num_b * p.bn * sizeof(float) <= TC_BIAS_SMEM)
                    ? (uint32_t)p.num_stages * p.stage_bytes + 256u : 0u;
+  // B-resident CTA pairs: one column tile (N <= 256) and K <= 256 -- the discriminator's layers
+  if (use_bres() && p.num_b == 1 && p.red <= 256 && p.num_a >= 4 && p.bn >= 64 && (e.epi != EPI_F32 || p.vec_ok)) {
+    const int nkb = (int)((p.red + 63) / 64);
+    p.bk = 32;
+    p.a_plane = TC_BM * 64u;                                       // 128 rows x 32 bf16, SWIZZLE_64B
+    p.b_plane_bytes = (uint32_t)(p.bn / 2) * 128u;                 // (N/2) rows x 64 bf16, SWIZZLE_128B, per K block
+    p.bres_bytes = (uint32_t)nkb * 2u * p.b_plane_bytes;
+    p.stage_bytes = 2 * p.a_plane;
+    p.tx_bytes = 2 * p.a_plane;
+    p.num_stages = (int)((216 * 1024 - p.bres_bytes) / p.stage_bytes);
+    if (p.num_stages > TC_MAX_STAGES) p.num_stages = TC_MAX_STAGES;
+    p.bias_off = (e.bias && (size_t)p.num_b * p.bn * sizeof(float) <= TC_BIAS_SMEM)
+                     ? p.bres_bytes + (uint32_t)p.num_stages * p.stage_bytes + 256u : 0u;
+    CUtensorMap mAh, mAl, mBh, mBl;
+    int rc;
+    if ((rc = make_map(&mAh, A.hi, A.rows, A.cols, A.pitch, TC_BM, 32))) return rc;
+    if ((rc = make_map(&mAl, A.lo, A.rows, A.cols, A.pitch, TC_BM, 32))) return rc;
+    if ((rc = make_map(&mBh, B.hi, B.rows, B.cols, B.pitch, p.bn / 2, 64))) return rc;
+    if ((rc = make_map(&mBl, B.lo, B.rows, B.cols, B.pitch, p.bn / 2, 64))) return rc;
+    switch (e.epi) {
+      case EPI_F32: return launch_pair_kernel<EPI_F32, true>(mAh, mAl, mBh, mBl, p, st);
+      case EPI_PLANES_FWD: return launch_pair_kernel<EPI_PLANES_FWD, true>(mAh, mAl, mBh, mBl, p, st);
+      case EPI_PLANES_BWD: return launch_pair_kernel<EPI_PLANES_BWD, true>(mAh, mAl, mBh, mBl, p, st);
+    }
+  }
   // GANTTS_B200_CLUSTER=3: CTA-pair MMA (cta_group::2), each CTA holds half of the B tile
   if ((use_cluster() == 3 || (use_cluster() == 0 && p.num_b >= 2)) && p.num_a >= 2) {
     p.b_plane_bytes = ((uint32_t)(p.bn / 2) * rowb + 1023) / 1024 * 1024;

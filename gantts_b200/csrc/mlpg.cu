@@ -258,13 +258,17 @@ mlpg_bwd_kernel(const float* __restrict__ go, int64_t go_bs, int64_t go_ts,
 // state SW frames earlier (forward) / later (backward) -- the influence of the state decays like |r|^n with
 // |r| = sqrt(L2/L0) = 0.389 for these windows (0.389^32 = 8e-14, below fp32 resolution); chunks that touch the ends of
 // the utterance start from the exact boundary state.  One warp = 32 consecutive output columns (lane = column: every
-// load and store is a coalesced row segment), the forward sweep parks z in shared memory for the backward sweep.  The
-// per-column arithmetic depends on T only (chunking), not on which columns share the launch: the reference's bitwise
-// whole-vs-slice property (tests/test_gantts.py:156-159) holds.
-constexpr int SC = 64;                 // frames per chunk
+// load and store is a coalesced row segment).  Each warp works in phases over a shared-memory strip of its chunk:
+//   (1) right-hand side for every frame of the strip -- no recurrence, 8 frames x up to 12 rows of loads in flight;
+//   (2) forward substitution in place;  (3) backward substitution in place (forward kernel: straight to the output);
+//   (4) adjoint only: the window stencil of the solved strip.
+// so the HBM/L2 latency is paid in phase (1) with deep memory-level parallelism and the serial phases touch shared
+// memory only.  The per-column arithmetic depends on T only (chunking), not on which columns share the launch: the
+// reference's bitwise whole-vs-slice property (tests/test_gantts.py:156-159) holds.
+constexpr int SC = 32;                 // frames per chunk
 constexpr int SW = 32;                 // warm-up frames on either side
 constexpr int SOLVE_WARPS = 4;
-constexpr int SOLVE_ZROWS = SC + SW + 4;
+constexpr int SOLVE_ZROWS = SC + 2 * SW + 8;
 
 struct SolveTaps {
   float c[GANTTS_MAX_WINDOWS][5];      // coefficient of mu_w[t - k] in b_t, k = -2..2 at index k + 2 (0 where absent)
@@ -276,6 +280,21 @@ __device__ __forceinline__ float4 chol_fwd(const float* __restrict__ table, int 
 }
 __device__ __forceinline__ float4 chol_bwd(const float* __restrict__ table, int t) {
   return __ldg(reinterpret_cast<const float4*>(table + (int64_t)t * TABW + 56));
+}
+
+// forward substitution over rows [s, s + n) of the strip, in place (static columns are copied through)
+__device__ __forceinline__ void strip_forward(float* zs, int lane, const float* __restrict__ table, int s, int n, bool dyn) {
+  float z1 = 0.f, z2 = 0.f;
+#pragma unroll 8
+  for (int i = 0; i < n; ++i) {
+    const float4 cf = chol_fwd(table, s + i);
+    const float b = zs[i * 32 + lane];
+    float z = (b - cf.y * z1 - cf.z * z2) * cf.x;
+    if (!dyn) z = b;
+    z2 = z1;
+    z1 = z;
+    zs[i * 32 + lane] = z;
+  }
 }
 
 __global__ void __launch_bounds__(32 * SOLVE_WARPS)
@@ -295,58 +314,45 @@ mlpg_solve_fwd_kernel(const float* __restrict__ in, int64_t in_bs, int64_t in_ts
   const float* colp = in + (int64_t)b * in_bs + (valid ? ci.in_col : 0);
   const int t0 = chunk * SC;
   const int t1 = t0 + SC < T ? t0 + SC : T;                 // outputs [t0, t1)
-  const int s = t0 - SW > 0 ? t0 - SW : 0;                  // forward sweep start (exact state when s == 0)
-  const int e = t1 + SW < T ? t1 + SW : T;                  // sweeps end (exact state when e == T)
-  // sliding window of mu_w rows t-2 .. t+2 per window
-  float x[GANTTS_MAX_WINDOWS][5];
-#pragma unroll
-  for (int w = 0; w < GANTTS_MAX_WINDOWS; ++w) {
-#pragma unroll
-    for (int q = 0; q < 5; ++q) x[w][q] = 0.f;
-  }
-  auto load_row = [&](int w, int t) -> float {
-    return (valid && t >= 0 && t < T && (dyn || w == 0)) ? __ldg(colp + (int64_t)t * in_ts + (dyn ? w * ci.sd : 0)) : 0.f;
-  };
-#pragma unroll
-  for (int w = 0; w < GANTTS_MAX_WINDOWS; ++w) {
-    if (w < taps.nw) {
-      x[w][2] = load_row(w, s);           // rows s-2, s-1 contribute to b_s through taps of rows outside [0,T) only when
-      x[w][3] = load_row(w, s + 1);       // s == 0 (they are zero); for s > 0 the warm-up absorbs the truncation
-      x[w][4] = load_row(w, s + 2);
-      x[w][1] = load_row(w, s - 1);
-      x[w][0] = load_row(w, s - 2);
-    }
-  }
-  float z1 = 0.f, z2 = 0.f;
-  for (int t = s; t < e; ++t) {
-    float bt = 0.f;
+  const int s = t0 - SW > 0 ? t0 - SW : 0;                  // strip start (exact state when s == 0)
+  const int e = t1 + SW < T ? t1 + SW : T;                  // strip end (exact state when e == T)
+  const int n = e - s;
+  // (1) b_t = sum_w sum_k coef_w[k+l] mu_w[t - k] for the whole strip, 8 frames per batch
+  for (int i0 = 0; i0 < n; i0 += 8) {
+    float xr[GANTTS_MAX_WINDOWS][12];                       // rows s+i0-2 .. s+i0+9 of every window component
 #pragma unroll
     for (int w = 0; w < GANTTS_MAX_WINDOWS; ++w) {
-      if (w < taps.nw) {
 #pragma unroll
-        for (int k = -2; k <= 2; ++k) bt = fmaf(taps.c[w][k + 2], x[w][2 - k], bt);      // mu_w[t - k]
+      for (int q = 0; q < 12; ++q) {
+        const int t = s + i0 - 2 + q;
+        const bool ok = valid && w < taps.nw && (dyn || w == 0) && t >= 0 && t < T;
+        xr[w][q] = ok ? __ldg(colp + (int64_t)t * in_ts + (dyn ? w * ci.sd : 0)) : 0.f;
       }
     }
-    const float4 cf = chol_fwd(table, t);
-    float z = (bt - cf.y * z1 - cf.z * z2) * cf.x;
-    if (!dyn) z = x[0][2];               // static stream: copied through
-    z2 = z1;
-    z1 = z;
-    if (t >= t0) zs[(t - t0) * 32 + lane] = z;
 #pragma unroll
-    for (int w = 0; w < GANTTS_MAX_WINDOWS; ++w) {
-      if (w < taps.nw) {
-        x[w][0] = x[w][1]; x[w][1] = x[w][2]; x[w][2] = x[w][3]; x[w][3] = x[w][4];
-        x[w][4] = load_row(w, t + 3);
+    for (int u = 0; u < 8; ++u) {
+      float bt = 0.f;
+#pragma unroll
+      for (int w = 0; w < GANTTS_MAX_WINDOWS; ++w) {
+#pragma unroll
+        for (int k = -2; k <= 2; ++k) bt = fmaf(taps.c[w][k + 2], xr[w][u + 2 - k], bt);      // mu_w[t - k]
       }
+      if (!dyn) bt = xr[0][u + 2];
+      if (i0 + u < n) zs[(i0 + u) * 32 + lane] = bt;
     }
   }
+  __syncwarp();
+  // (2) forward substitution
+  strip_forward(zs, lane, table, s, n, dyn);
+  // (3) backward substitution, straight to the output
   float y1 = 0.f, y2 = 0.f;
   float* outp = out + (int64_t)b * out_bs + oc;
-  for (int t = e - 1; t >= t0; --t) {
+#pragma unroll 8
+  for (int i = n - 1; i >= t0 - s; --i) {
+    const int t = s + i;
     const float4 cb = chol_bwd(table, t);
     const float4 cf = chol_fwd(table, t);
-    const float zt = zs[(t - t0) * 32 + lane];
+    const float zt = zs[i * 32 + lane];
     float y = (zt - cb.x * y1 - cb.y * y2) * cf.x;
     if (!dyn) y = zt;
     y2 = y1;
@@ -377,48 +383,52 @@ mlpg_solve_bwd_kernel(const float* __restrict__ go, int64_t go_bs, int64_t go_ts
   const int hi = t1 + 2 < T ? t1 + 2 : T;
   const int s = lo - SW > 0 ? lo - SW : 0;
   const int e = hi + SW < T ? hi + SW : T;
-  float z1 = 0.f, z2 = 0.f;
-  for (int t = s; t < e; ++t) {
-    const float g = valid ? __ldg(gop + (int64_t)t * go_ts) : 0.f;
-    const float4 cf = chol_fwd(table, t);
-    float z = (g - cf.y * z1 - cf.z * z2) * cf.x;
-    if (!dyn) z = g;
-    z2 = z1;
-    z1 = z;
-    if (t >= lo) zs[(t - lo) * 32 + lane] = z;               // rows lo .. e-1 (<= SC + 4 + SW... bounded by SOLVE_ZROWS + 2)
-  }
-  // backward sweep from e-1 down to lo; window zw[q] = z_{t + q}, q = 0..4, zero outside [0, T)
-  float zw[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-  float y1 = 0.f, y2 = 0.f;
-  float* gib = gi + (int64_t)b * gi_bs + (valid ? ci.in_col : 0);
-  for (int t = e - 1; t >= t0 - 2; --t) {
-    float y = 0.f;
-    if (t >= lo) {
+  const int n = e - s;                                      // <= SC + 4 + 2 SW
+  // (1) the strip of the upstream gradient
+#pragma unroll 8
+  for (int i = 0; i < n; ++i) zs[i * 32 + lane] = valid ? __ldg(gop + (int64_t)(s + i) * go_ts) : 0.f;
+  __syncwarp();
+  // (2) forward, (3) backward substitution in place
+  strip_forward(zs, lane, table, s, n, dyn);
+  {
+    float y1 = 0.f, y2 = 0.f;
+#pragma unroll 8
+    for (int i = n - 1; i >= lo - s; --i) {
+      const int t = s + i;
       const float4 cb = chol_bwd(table, t);
       const float4 cf = chol_fwd(table, t);
-      const float zt = zs[(t - lo) * 32 + lane];
-      y = (zt - cb.x * y1 - cb.y * y2) * cf.x;
+      const float zt = zs[i * 32 + lane];
+      float y = (zt - cb.x * y1 - cb.y * y2) * cf.x;
       if (!dyn) y = zt;
       y2 = y1;
       y1 = y;
+      zs[i * 32 + lane] = y;
     }
-    zw[4] = zw[3]; zw[3] = zw[2]; zw[2] = zw[1]; zw[1] = zw[0];
-    zw[0] = (t >= 0 && t < hi) ? y : 0.f;                    // z beyond the needed range only feeds rows we do not emit
-    const int tp = t + 2;                                    // row whose window z_{tp-2..tp+2} is now complete
-    if (valid && tp >= t0 && tp < t1) {
-      float* prow = gib + (int64_t)tp * gi_ts;
-      if (!dyn) {
-        prow[0] = accumulate ? prow[0] + zw[2] : zw[2];
-      } else {
+  }
+  __syncwarp();
+  // (4) gi_w[t] = sum_k coef_w[k+l] z_{t+k} on [t0, t1): z outside [0, T) is zero
+  if (!valid) return;
+  float* gib = gi + (int64_t)b * gi_bs + ci.in_col;
+#pragma unroll 4
+  for (int t = t0; t < t1; ++t) {
+    float zw[5];
 #pragma unroll
-        for (int w = 0; w < GANTTS_MAX_WINDOWS; ++w) {
-          if (w < taps.nw) {
-            float v = 0.f;
+    for (int k = -2; k <= 2; ++k) {
+      const int tt = t + k;
+      zw[k + 2] = (tt >= 0 && tt < T) ? zs[(tt - s) * 32 + lane] : 0.f;
+    }
+    float* prow = gib + (int64_t)t * gi_ts;
+    if (!dyn) {
+      prow[0] = accumulate ? prow[0] + zw[2] : zw[2];
+    } else {
 #pragma unroll
-            for (int k = -2; k <= 2; ++k) v = fmaf(taps.c[w][k + 2], zw[2 + k], v);       // z_{tp + k}
-            float* q = prow + w * ci.sd;
-            *q = accumulate ? *q + v : v;
-          }
+      for (int w = 0; w < GANTTS_MAX_WINDOWS; ++w) {
+        if (w < taps.nw) {
+          float v = 0.f;
+#pragma unroll
+          for (int k = -2; k <= 2; ++k) v = fmaf(taps.c[w][k + 2], zw[2 + k], v);       // z_{t + k}
+          float* q = prow + w * ci.sd;
+          *q = accumulate ? *q + v : v;
         }
       }
     }
