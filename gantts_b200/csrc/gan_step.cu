@@ -162,11 +162,17 @@ bce_fwd_bwd_kernel(const float* __restrict__ Dv, const float* __restrict__ mask,
 
 // MaskedMSELoss forward sums (gantts/seqloss.py:41-43) AND its gradient 2 * scale * (a m - b m) * m in one pass
 // (ga == nullptr: forward only).  The gradient is STORED (not accumulated): this launch initialises the buffer.
+// bmap.n > 0: column d of the target is column bmap.c[d] of `b` (the static features are read straight out of y:
+// get_static_features of multistream.py:56-79 without materialising y_static).
 __global__ void __launch_bounds__(RED_THREADS)
 sse_fwd_bwd_kernel(const float* __restrict__ a, int64_t a_rs, const float* __restrict__ b, int64_t b_rs,
                    const float* __restrict__ mask, int64_t rows, int D, const float* __restrict__ scale,
-                   float* __restrict__ ga, int64_t ga_rs, RedWs* ws) {
+                   float* __restrict__ ga, int64_t ga_rs, RedWs* ws, ColList bmap) {
   __shared__ float sm[RED_NV * 32];
+  __shared__ int sc[GANTTS_MAX_COLS];
+  for (int i = threadIdx.x; i < bmap.n; i += RED_THREADS) sc[i] = bmap.c[i];
+  __syncthreads();
+  const bool mapped = bmap.n > 0;
   float v[RED_NV] = {0.f, 0.f, 0.f, 0.f};
   const float s2 = ga ? 2.f * scale[0] : 0.f;
   const int lane = threadIdx.x & 31;
@@ -178,7 +184,7 @@ sse_fwd_bwd_kernel(const float* __restrict__ a, int64_t a_rs, const float* __res
     const float* br = b + r * b_rs;
 #pragma unroll 4
     for (int d = lane; d < D; d += 32) {
-      const float x = ar[d] * m - br[d] * m;
+      const float x = ar[d] * m - br[mapped ? sc[d] : d] * m;
       v[0] = fmaf(x, x, v[0]);
       if (ga) ga[r * ga_rs + d] = s2 * x * m;
     }
@@ -375,8 +381,12 @@ static int launch_bce(const float* Dv, const float* mask, int64_t M, int halves,
 }
 
 static int launch_sse(const float* a, int64_t a_rs, const float* b, int64_t b_rs, const float* mask, int64_t rows, int D,
-                      const float* scale, float* ga, int64_t ga_rs, RedWs* ws, cudaStream_t st) {
-  sse_fwd_bwd_kernel<<<sse_blocks(rows, D), RED_THREADS, 0, st>>>(a, a_rs, b, b_rs, mask, rows, D, scale, ga, ga_rs, ws);
+                      const float* scale, float* ga, int64_t ga_rs, RedWs* ws, cudaStream_t st,
+                      const ColList* bmap = nullptr) {
+  ColList none;
+  none.n = 0;
+  sse_fwd_bwd_kernel<<<sse_blocks(rows, D), RED_THREADS, 0, st>>>(a, a_rs, b, b_rs, mask, rows, D, scale, ga, ga_rs, ws,
+                                                                 bmap ? *bmap : none);
   GANTTS_LAUNCH_CHECK("sse_fwd_bwd_kernel");
   return GANTTS_OK;
 }
@@ -495,8 +505,10 @@ extern "C" int gantts_gan_step(const gantts_gan_step_t* c, int phases, const flo
     if ((rc = gantts_sequence_mask(lengths_dev, L.mask, c->B, c->T, stream))) return rc;
     set_scales_kernel<<<1, 32, 0, st>>>(L.scal, inv_frames, has_adv ? c->adv_w : 0.f, c->mge_w, c->mse_w, 1, lengths_dev, c->B, c->T);
     GANTTS_LAUNCH_CHECK("set_scales_kernel");
-    gather_cols_list_kernel<<<blocks_1d(M * nS, 1024), 256, 0, st>>>(y, d_out, L.y_static, nS, static_cols, M);
-    GANTTS_LAUNCH_CHECK("gather_cols_list_kernel(y_static)");
+    if (has_d) {      // (the eval path keeps the two-step gather of the discriminator input)
+      gather_cols_list_kernel<<<blocks_1d(M * nS, 1024), 256, 0, st>>>(y, d_out, L.y_static, nS, static_cols, M);
+      GANTTS_LAUNCH_CHECK("gather_cols_list_kernel(y_static)");
+    }
     if ((rc = gantts_mlp_fwd(&g, x, d_in, M, y_hat, d_out, L.g_tape, L.g_tape_bytes, stream))) return rc;
     if ((rc = gantts_mlpg_fwd(y_hat, (int64_t)c->T * d_out, d_out, y_hat_static, (int64_t)c->T * nS, nS,
                               c->mlpg_table, &c->streams, &c->windows, c->B, c->T, stream)))
@@ -524,7 +536,8 @@ extern "C" int gantts_gan_step(const gantts_gan_step_t* c, int phases, const flo
         cnt.n[R_ADV] = bce_blocks(M);
       }
     }
-    if ((rc = launch_sse(y_hat_static, nS, L.y_static, nS, L.mask, M, nS, L.scal + S_MGE_SCALE, nullptr, 0, &L.red[R_MGE], st)))
+    if ((rc = launch_sse(y_hat_static, nS, y, d_out, L.mask, M, nS, L.scal + S_MGE_SCALE, nullptr, 0, &L.red[R_MGE], st,
+                         &static_cols)))
       return rc;
     if ((rc = launch_sse(y_hat, d_out, y, d_out, L.mask, M, d_out, L.scal + S_MSE_SCALE, nullptr, 0, &L.red[R_MSE], st)))
       return rc;
@@ -542,8 +555,10 @@ extern "C" int gantts_gan_step(const gantts_gan_step_t* c, int phases, const flo
     if ((rc = gantts_sequence_mask(lengths_dev, L.mask, c->B, c->T, stream))) return rc;
     set_scales_kernel<<<1, 32, 0, st>>>(L.scal, inv_frames, has_adv ? c->adv_w : 0.f, c->mge_w, c->mse_w, 0, lengths_dev, c->B, c->T);
     GANTTS_LAUNCH_CHECK("set_scales_kernel");
-    gather_cols_list_kernel<<<blocks_1d(M * nS, 1024), 256, 0, st>>>(y, d_out, L.y_static, nS, static_cols, M);
-    GANTTS_LAUNCH_CHECK("gather_cols_list_kernel(y_static)");
+    if (has_d && cond_w) {      // only the conditioned-discriminator fallback still gathers from y_static
+      gather_cols_list_kernel<<<blocks_1d(M * nS, 1024), 256, 0, st>>>(y, d_out, L.y_static, nS, static_cols, M);
+      GANTTS_LAUNCH_CHECK("gather_cols_list_kernel(y_static)");
+    }
     // ---- apply_generator (train.py:336-355): G forward + MLPG
     if ((rc = gantts_mlp_fwd(&g, x, d_in, M, y_hat, d_out, L.g_tape, L.g_tape_bytes, stream))) return rc;
     if ((rc = gantts_mlpg_fwd(y_hat, (int64_t)c->T * d_out, d_out, y_hat_static, (int64_t)c->T * nS, nS,
@@ -551,8 +566,8 @@ extern "C" int gantts_gan_step(const gantts_gan_step_t* c, int phases, const flo
       return rc;
     // MGE loss (train.py:291) and its gradient in one pass; the gradient INITIALISES g_static, the two discriminator
     // passes then accumulate their input gradients on top of it
-    if ((rc = launch_sse(y_hat_static, nS, L.y_static, nS, L.mask, M, nS, L.scal + S_MGE_SCALE, L.g_static, nS,
-                         &L.red[R_MGE], st)))
+    if ((rc = launch_sse(y_hat_static, nS, y, d_out, L.mask, M, nS, L.scal + S_MGE_SCALE, L.g_static, nS,
+                         &L.red[R_MGE], st, &static_cols)))
       return rc;
     if (has_d) {
       // ---- update_discriminator (train.py:245-279): stacked real | fake batch of 2M rows

@@ -44,6 +44,7 @@ struct GemmParams {
   int bn;               // MMA N, multiple of 64, <= 256
   int num_stages;
   uint32_t stage_bytes, b_plane_bytes, tx_bytes;
+  int64_t row0;         // global index of the first output row (dropout keys use global rows when a launch covers a row window)
   uint32_t bres_bytes;  // pair kernel, BRES: bytes of the resident B operand in front of the stage ring
   int bk;               // reduction elements per smem stage: 64 (SWIZZLE_128B K-major rows) or 32 (SWIZZLE_64B)
   uint32_t a_plane;     // bytes of one A plane tile in a stage
@@ -148,7 +149,7 @@ __device__ __forceinline__ void epilogue_f32_staged(const GemmParams& p, const u
       const uint32_t half_n = (uint32_t)(p.cols_b + 1) >> 1;
 #pragma unroll
       for (int j = 0; j < 16; j += 2) {
-        const uint32_t bits = dropout_pair_bits(p.seed, (uint32_t)row, half_n, (uint32_t)(col + j) >> 1);
+        const uint32_t bits = dropout_pair_bits(p.seed, (uint32_t)(row + p.row0), half_n, (uint32_t)(col + j) >> 1);
         v[j] = (bits & 0xffffu) >= p.thresh ? v[j] * p.keep_scale : 0.f;
         v[j + 1] = (bits >> 16) >= p.thresh ? v[j + 1] * p.keep_scale : 0.f;
       }
@@ -207,7 +208,7 @@ __device__ __forceinline__ uint32_t epilogue_chunk16(const GemmParams& p, const 
         const uint32_t half_n = (uint32_t)(p.cols_b + 1) >> 1;
 #pragma unroll
         for (int j = 0; j < 16; j += 2) {
-          const uint32_t bits = dropout_pair_bits(p.seed, (uint32_t)row, half_n, (uint32_t)(col + j) >> 1);
+          const uint32_t bits = dropout_pair_bits(p.seed, (uint32_t)(row + p.row0), half_n, (uint32_t)(col + j) >> 1);
           v[j] = (bits & 0xffffu) >= p.thresh ? v[j] * p.keep_scale : 0.f;
           v[j + 1] = (bits >> 16) >= p.thresh ? v[j + 1] * p.keep_scale : 0.f;
         }
@@ -253,7 +254,7 @@ __device__ __forceinline__ uint32_t epilogue_chunk16(const GemmParams& p, const 
       const uint32_t half_n = (uint32_t)(p.cols_b + 1) >> 1;
 #pragma unroll
       for (int j = 0; j < 16; j += 2) {
-        const uint32_t bits = dropout_pair_bits(p.seed, (uint32_t)row, half_n, (uint32_t)(col + j) >> 1);
+        const uint32_t bits = dropout_pair_bits(p.seed, (uint32_t)(row + p.row0), half_n, (uint32_t)(col + j) >> 1);
         v[j] = (bits & 0xffffu) >= p.thresh ? v[j] * p.keep_scale : 0.f;
         v[j + 1] = (bits >> 16) >= p.thresh ? v[j + 1] * p.keep_scale : 0.f;
       }
@@ -1123,13 +1124,14 @@ static int launch_split(const float* src, int64_t rs, int64_t rows, int cols, co
   return GANTTS_OK;
 }
 
-static int pick_bn(int n) {
-  static int cap = -1;
-  if (cap < 0) {
+static int pick_bn(int n, int cap_override = 0) {
+  static int cap_env = -1;
+  if (cap_env < 0) {
     const char* e = getenv("GANTTS_B200_BN");
-    cap = e ? atoi(e) : 256;
-    if (cap < 64 || cap > 256 || cap % 64) cap = 256;
+    cap_env = e ? atoi(e) : 256;
+    if (cap_env < 64 || cap_env > 256 || cap_env % 64) cap_env = 256;
   }
+  const int cap = cap_override ? cap_override : cap_env;
   int bn = (n + 63) / 64 * 64;
   if (bn <= cap) return bn;
   int tiles = (n + cap - 1) / cap;
@@ -1154,6 +1156,7 @@ struct EpiArgs {
   int act = GANTTS_ACT_NONE;
   float slope = 0.f, p = 0.f;
   uint64_t seed = 0;
+  int64_t row0 = 0;                   // global index of A's first row (row windows of a larger matrix)
 };
 
 static void fill_epilogue(GemmParams& p, const EpiArgs& e) {
@@ -1173,6 +1176,7 @@ static void fill_epilogue(GemmParams& p, const EpiArgs& e) {
   p.keep_scale = e.p > 0.f ? 1.f / (1.f - e.p) : 1.f;
   p.thresh = e.p > 0.f ? (uint32_t)(e.p * 65536.f + 0.5f) : 0u;
   p.seed = e.seed;
+  p.row0 = e.row0;
   static int dbg = -1;
   if (dbg < 0) {
     const char* v = getenv("GANTTS_B200_DBG");
@@ -1207,10 +1211,13 @@ static int use_f32_stage() {
   return v;
 }
 
-// B-resident pair kernel for narrow layers (GANTTS_B200_BRES=0 disables); read per call so tests can switch it.
+// B-resident pair kernel for narrow layers: OPT-IN (GANTTS_B200_BRES=1).  Measured on B200 at cfg2
+// (profiles/r02_gemm_experiments.md): correct, but the discriminator's 256-wide launches did not get faster (34.6 us
+// against 33.5 us per forward launch, step 1.298 against 1.279 ms) -- they are bound by the epilogue and its tape
+// writes, not by the operand ingest the resident weights remove.  Read per call so tests can switch it.
 static int use_bres() {
   const char* e = getenv("GANTTS_B200_BRES");
-  return e ? atoi(e) : 1;
+  return e ? atoi(e) : 0;
 }
 
 static int use_pdl() {
@@ -1376,7 +1383,8 @@ static void maybe_stage_f32(GemmParams& p, const EpiArgs& e, bool mn, uint32_t b
 }
 
 // out[rows_a][cols_b] = epi(A * B^T)   (K-major planes A [rows_a][red], B [cols_b][red]).
-static int launch_gemm_kk(const Planes& A, const Planes& B, const EpiArgs& e, cudaStream_t st) {
+static int launch_gemm_kk_one(const Planes& A, const Planes& B, const EpiArgs& e, cudaStream_t st, int bn_cap = 0,
+                              bool allow_pair = true) {
   GemmParams p{};
   p.rows_a = A.rows;
   p.cols_b = (int)B.rows;
@@ -1392,7 +1400,7 @@ static int launch_gemm_kk(const Planes& A, const Planes& B, const EpiArgs& e, cu
   p.kstep = 32;
   p.desc_layout = p.bk == 64 ? 2u : 4u;
   p.red_chunk = (p.red + p.bk - 1) / p.bk * p.bk;
-  p.bn = pick_bn(p.cols_b);
+  p.bn = pick_bn(p.cols_b, bn_cap);
   p.num_a = (int)((p.rows_a + TC_BM - 1) / TC_BM);
   p.num_b = (p.cols_b + p.bn - 1) / p.bn;
   p.num_z = 1;
@@ -1408,7 +1416,7 @@ static int launch_gemm_kk(const Planes& A, const Planes& B, const EpiArgs& e, cu
   p.bias_off = (e.bias && (size_t)p.num_b * p.bn * sizeof(float) <= TC_BIAS_SMEM)
                    ? (uint32_t)p.num_stages * p.stage_bytes + 256u : 0u;
   // B-resident CTA pairs: one column tile (N <= 256) and K <= 256 -- the discriminator's layers
-  if (use_bres() && p.num_b == 1 && p.red <= 256 && p.num_a >= 4 && p.bn >= 64 && (e.epi != EPI_F32 || p.vec_ok)) {
+  if (allow_pair && use_bres() && p.num_b == 1 && p.red <= 256 && p.num_a >= 4 && p.bn >= 64 && (e.epi != EPI_F32 || p.vec_ok)) {
     const int nkb = (int)((p.red + 63) / 64);
     p.bk = 32;
     p.a_plane = TC_BM * 64u;                                       // 128 rows x 32 bf16, SWIZZLE_64B
@@ -1433,7 +1441,7 @@ static int launch_gemm_kk(const Planes& A, const Planes& B, const EpiArgs& e, cu
     }
   }
   // GANTTS_B200_CLUSTER=3: CTA-pair MMA (cta_group::2), each CTA holds half of the B tile
-  if ((use_cluster() == 3 || (use_cluster() == 0 && p.num_b >= 2)) && p.num_a >= 2) {
+  if (allow_pair && (use_cluster() == 3 || (use_cluster() == 0 && p.num_b >= 2)) && p.num_a >= 2) {
     p.b_plane_bytes = ((uint32_t)(p.bn / 2) * rowb + 1023) / 1024 * 1024;
     p.stage_bytes = 2 * p.a_plane + 2 * p.b_plane_bytes;
     p.tx_bytes = 2 * p.a_plane + 2 * (uint32_t)(p.bn / 2) * rowb;
@@ -1454,7 +1462,7 @@ static int launch_gemm_kk(const Planes& A, const Planes& B, const EpiArgs& e, cu
     }
   }
   // 2-CTA clusters (B tile multicast) when there are at least two row tiles
-  const bool cl2 = use_cluster() == 2 && p.num_a >= 2;
+  const bool cl2 = allow_pair && use_cluster() == 2 && p.num_a >= 2;
   if (!cl2) maybe_stage_f32(p, e, false, 216 * 1024);
   CUtensorMap mAh, mAl, mBh, mBl;
   int rc;
@@ -1476,6 +1484,58 @@ static int launch_gemm_kk(const Planes& A, const Planes& B, const EpiArgs& e, cu
   }
   set_error("gemm_kk: bad epilogue %d", e.epi);
   return GANTTS_E_BADARG;
+}
+
+// Tail balancing (GANTTS_B200_TAIL=0 disables).  The persistent K-major kernels take whole rounds of tiles: 250 pair
+// tiles on 74 CTA pairs are 3.38 rounds of work that cost 4 (the 512-wide generator layers at cfg2), 500 tiles on 148
+// CTAs likewise.  The rows of the incomplete last round are cut off and given to a SECOND launch with narrower column
+// tiles (BN/2 or BN/4, single CTAs) so that they spread over all SMs in half or three quarters of a round.
+static int use_tail() {
+  const char* e = getenv("GANTTS_B200_TAIL");
+  return e ? atoi(e) : 1;
+}
+
+static int launch_gemm_kk(const Planes& A, const Planes& B, const EpiArgs& e, cudaStream_t st) {
+  if (use_tail() && use_cluster() == 0) {
+    const int N = (int)B.rows;
+    const int bn = pick_bn(N);
+    const int num_b = (N + bn - 1) / bn;
+    const int64_t num_a = (A.rows + TC_BM - 1) / TC_BM;
+    const bool pair = num_b >= 2 && num_a >= 2;
+    const int units = pair ? num_sms() / 2 : num_sms();
+    const int unit_rows = pair ? 2 * TC_BM : TC_BM;
+    const int64_t row_tiles = (A.rows + unit_rows - 1) / unit_rows;
+    const int64_t tiles = row_tiles * num_b;
+    const int64_t rounds = tiles / units, rem = tiles % units;
+    if (rounds >= 1 && rem > 0 && bn >= 128 && bn % 128 == 0) {
+      const double frac = (double)rem / units;
+      int best_k = 1;
+      double best = 1.0;
+      for (int k = 2; k <= 4; k *= 2) {
+        if (bn / k < 64) break;
+        const double cost = ceil(k * frac - 1e-9) / k + 0.04;        // + the second launch's fill/drain
+        if (cost < best) { best = cost; best_k = k; }
+      }
+      const int64_t main_row_tiles = rounds * units / num_b;
+      const int64_t main_rows = main_row_tiles * unit_rows;
+      if (best_k > 1 && main_rows > 0 && main_rows < A.rows) {
+        Planes A1 = A, A2 = A;
+        A1.rows = main_rows;
+        A2.rows = A.rows - main_rows;
+        A2.hi += main_rows * A.pitch;
+        A2.lo += main_rows * A.pitch;
+        EpiArgs e2 = e;
+        e2.row0 = e.row0 + main_rows;
+        if (e2.C) e2.C += main_rows * e.ldc;
+        if (e2.out_hi) { e2.out_hi += main_rows * e.out_pitch; e2.out_lo += main_rows * e.out_pitch; }
+        if (e2.code) e2.code += main_rows * e.code_pitch;
+        int rc = launch_gemm_kk_one(A1, B, e, st);
+        if (rc) return rc;
+        return launch_gemm_kk_one(A2, B, e2, st, bn / best_k, false);
+      }
+    }
+  }
+  return launch_gemm_kk_one(A, B, e, st);
 }
 
 // C[n][k] (+)= sum_m A[m][n] * B[m][k]  (MN-major planes A [red][rows_a], B [red][cols_b]);

@@ -582,6 +582,8 @@ extern "C" int gantts_mlpg_fwd(const float* in, int64_t in_bs, int64_t in_ts, fl
       const int64_t nitems = (int64_t)B * nchunks * ncg;
       const size_t sm = (size_t)SOLVE_WARPS * SOLVE_ZROWS * 32 * sizeof(float);
       GANTTS_CUDA(cudaFuncSetAttribute(mlpg_solve_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      // 53 KB per block: the full shared-memory carve-out lets 4 blocks (16 warps) share an SM -- one wave at cfg2
+      GANTTS_CUDA(cudaFuncSetAttribute(mlpg_solve_fwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
       int in_cols = 0;
       for (int s = 0; s < st->n; ++s) in_cols += st->sd[s] * (st->dyn[s] ? win->n : 1);
       prof_begin(PROF_MLPG_FWD, 4.0 * (double)B * T * (in_cols + ncols), as_stream(stream));
@@ -632,6 +634,7 @@ extern "C" int gantts_mlpg_bwd(const float* go, int64_t go_bs, int64_t go_ts, fl
       const int64_t nitems = (int64_t)B * nchunks * ncg;
       const size_t sm = (size_t)SOLVE_WARPS * SOLVE_ZROWS * 32 * sizeof(float);
       GANTTS_CUDA(cudaFuncSetAttribute(mlpg_solve_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      GANTTS_CUDA(cudaFuncSetAttribute(mlpg_solve_bwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
       int in_cols = 0;
       for (int s = 0; s < st->n; ++s) in_cols += st->sd[s] * (st->dyn[s] ? win->n : 1);
       prof_begin(PROF_MLPG_BWD, 4.0 * (double)B * T * (in_cols + ncols), as_stream(stream));
