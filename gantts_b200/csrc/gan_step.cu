@@ -657,11 +657,23 @@ extern "C" int gantts_gan_step(const gantts_gan_step_t* c, int phases, const flo
     if ((rc = launch_sse(y_hat, d_out, y, d_out, L.mask, M, d_out, L.scal + S_MSE_SCALE, c->mse_w != 0.f ? L.g_yhat : nullptr,
                          d_out, &L.red[R_MSE], st)))
       return rc;
-    if ((rc = gantts_mlpg_bwd(L.g_static, (int64_t)c->T * nS, nS, L.g_yhat, (int64_t)c->T * d_out, d_out,
-                              c->mlpg_table, &c->streams, &c->windows, c->B, c->T, c->mse_w != 0.f ? 1 : 0, stream)))
+    // mse_w == 0 (the CLI default, train.py:15): nothing else adds to dL/dy_hat, so the MLPG backward writes the
+    // operand planes of the generator's backward GEMMs directly (no fp32 matrix, no conversion pass)
+    bool direct = false;
+    if (c->mse_w == 0.f) {
+      Planes gp;
+      if ((rc = mlp_bwd_gy_planes(&g, M, L.mlp_ws, L.mlp_ws_bytes, &gp))) return rc;
+      rc = mlpg_bwd_planes(L.g_static, (int64_t)c->T * nS, nS, gp.hi, gp.lo, gp.pitch, c->mlpg_table, &c->streams,
+                           &c->windows, c->B, c->T, stream);
+      if (rc == GANTTS_OK) direct = true;
+      else if (rc != GANTTS_E_UNSUPPORTED) return rc;
+    }
+    if (!direct &&
+        (rc = gantts_mlpg_bwd(L.g_static, (int64_t)c->T * nS, nS, L.g_yhat, (int64_t)c->T * d_out, d_out, c->mlpg_table,
+                              &c->streams, &c->windows, c->B, c->T, c->mse_w != 0.f ? 1 : 0, stream)))
       return rc;
-    if ((rc = gantts_mlp_bwd(&g, L.g_yhat, d_out, nullptr, 0, M, L.g_tape, L.g_tape_bytes, nullptr, 0, pg.gW, pg.gb,
-                             0, L.mlp_ws, L.mlp_ws_bytes, stream)))
+    if ((rc = mlp_bwd_impl(&g, direct ? nullptr : L.g_yhat, d_out, nullptr, 0, M, L.g_tape, L.g_tape_bytes, nullptr, 0, 0,
+                           pg.gW, pg.gb, 0, L.mlp_ws, L.mlp_ws_bytes, stream, -1, direct)))
       return rc;
   }
   if (phases & 4) {

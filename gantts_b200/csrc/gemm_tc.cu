@@ -1486,13 +1486,16 @@ static int launch_gemm_kk_one(const Planes& A, const Planes& B, const EpiArgs& e
   return GANTTS_E_BADARG;
 }
 
-// Tail balancing (GANTTS_B200_TAIL=0 disables).  The persistent K-major kernels take whole rounds of tiles: 250 pair
+// Tail balancing, OPT-IN (GANTTS_B200_TAIL=1).  The persistent K-major kernels take whole rounds of tiles: 250 pair
 // tiles on 74 CTA pairs are 3.38 rounds of work that cost 4 (the 512-wide generator layers at cfg2), 500 tiles on 148
 // CTAs likewise.  The rows of the incomplete last round are cut off and given to a SECOND launch with narrower column
 // tiles (BN/2 or BN/4, single CTAs) so that they spread over all SMs in half or three quarters of a round.
+// Measured on B200 at cfg2 (profiles/r02_gemm_experiments.md): results bitwise identical, step 1.329 ms against
+// 1.243 ms without -- the 16 extra launches (fill, drain, barrier/TMEM set-up) cost more than the quarter round they
+// save, so it stays off.
 static int use_tail() {
   const char* e = getenv("GANTTS_B200_TAIL");
-  return e ? atoi(e) : 1;
+  return e ? atoi(e) : 0;
 }
 
 static int launch_gemm_kk(const Planes& A, const Planes& B, const EpiArgs& e, cudaStream_t st) {

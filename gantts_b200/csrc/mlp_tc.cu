@@ -662,7 +662,22 @@ namespace gantts {
 static int mlp_bwd_impl(const gantts_mlp_t* m, const float* gy, int64_t gy_rs, const float* y, int64_t y_rs, int64_t M,
                         const void* tape, size_t tape_bytes, float* gx, int64_t gx_rs, int64_t gx_row0,
                         float* const* gW, float* const* gb, int accumulate, void* workspace, size_t workspace_bytes,
-                        void* stream, int gx_accumulate = -1);
+                        void* stream, int gx_accumulate = -1, bool gy_planes_ready = false);
+// Where mlp_bwd_impl expects the output-gradient planes when gy_planes_ready (linear output, not the GEMV tail): the
+// producer of gy (the MLPG backward in the fused step) can write them directly instead of an fp32 matrix.
+static int mlp_bwd_gy_planes(const gantts_mlp_t* m, int64_t M, void* workspace, size_t workspace_bytes, Planes* out);
+}
+
+static int gantts::mlp_bwd_gy_planes(const gantts_mlp_t* m, int64_t M, void* workspace, size_t workspace_bytes, Planes* out) {
+  int rc = check_mlp(m, M);
+  if (rc) return rc;
+  if (!workspace || workspace_bytes < gantts_mlp_workspace_bytes(m, M)) {
+    set_error("mlp_bwd_gy_planes: workspace too small");
+    return GANTTS_E_WORKSPACE;
+  }
+  char* cur = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 255) / 256 * 256);   // = gbuf[0] of mlp_bwd_impl
+  *out = carve_planes(cur, M, m->dims[m->num_layers]);
+  return GANTTS_OK;
 }
 
 extern "C" int gantts_mlp_bwd(const gantts_mlp_t* m, const float* gy, int64_t gy_rs, const float* y,
@@ -676,7 +691,7 @@ extern "C" int gantts_mlp_bwd(const gantts_mlp_t* m, const float* gy, int64_t gy
 static int gantts::mlp_bwd_impl(const gantts_mlp_t* m, const float* gy, int64_t gy_rs, const float* y, int64_t y_rs,
                                 int64_t M, const void* tape, size_t tape_bytes, float* gx, int64_t gx_rs,
                                 int64_t gx_row0, float* const* gW, float* const* gb, int accumulate, void* workspace,
-                                size_t workspace_bytes, void* stream, int gx_accumulate) {
+                                size_t workspace_bytes, void* stream, int gx_accumulate, bool gy_planes_ready) {
   // gx_accumulate: -1 = like the parameter gradients, 0 = store, 1 = add to what gx holds (gx may be a column window of
   // a wider matrix with row stride gx_rs: the fused step scatters the input gradient into g_static this way)
   if (gx_accumulate < 0) gx_accumulate = accumulate;
@@ -684,7 +699,9 @@ static int gantts::mlp_bwd_impl(const gantts_mlp_t* m, const float* gy, int64_t 
   GANTTS_CHECK_ARG(gx_row0 >= 0 && gx_row0 < M, "mlp_bwd: bad gx_row0");
   if (rc) return rc;
   const int L = m->num_layers;
-  GANTTS_CHECK_ARG(gy && gy_rs >= m->dims[L], "mlp_bwd: bad gy");
+  GANTTS_CHECK_ARG(gy_planes_ready || (gy && gy_rs >= m->dims[L]), "mlp_bwd: bad gy");
+  GANTTS_CHECK_ARG(!gy_planes_ready || (m->last_act == GANTTS_ACT_NONE && m->dims[L] > 1),
+                   "mlp_bwd: gy planes are only accepted for a linear multi-column output");
   GANTTS_CHECK_ARG(m->last_act != GANTTS_ACT_SIGMOID || y, "mlp_bwd: sigmoid output needs y");
   if (!tape || tape_bytes < gantts_mlp_tape_bytes(m, M)) {
     set_error("mlp_bwd: tape too small");
@@ -846,8 +863,7 @@ static int gantts::mlp_bwd_impl(const gantts_mlp_t* m, const float* gy, int64_t 
       GANTTS_LAUNCH_CHECK("gemv_partial_reduce_kernel");
     }
     l_start = L - 2;
-  } else
-  {
+  } else if (!gy_planes_ready) {
     int64_t total = M * m->dims[L];
     int nb = (int)((total + 1023) / 1024);
     if (nb > num_sms() * 8) nb = num_sms() * 8;

@@ -10,6 +10,7 @@
 // tests/test_gantts.py:156-159 (bitwise whole-vs-slice equality) requires.
 //
 // HBM-bound by design: algorithmic bytes per (b,t) = 4 * (sum of stream widths + output columns).
+#include <cuda_bf16.h>
 #include <math.h>
 
 #include <vector>
@@ -365,7 +366,8 @@ mlpg_solve_fwd_kernel(const float* __restrict__ in, int64_t in_bs, int64_t in_ts
 __global__ void __launch_bounds__(32 * SOLVE_WARPS)
 mlpg_solve_bwd_kernel(const float* __restrict__ go, int64_t go_bs, int64_t go_ts, float* __restrict__ gi, int64_t gi_bs,
                       int64_t gi_ts, const float* __restrict__ table, gantts_streams_t st, SolveTaps taps, int T, int ncols,
-                      int nchunks, int ncg, int64_t nitems, int accumulate) {
+                      int nchunks, int ncg, int64_t nitems, int accumulate, __nv_bfloat16* __restrict__ phi,
+                      __nv_bfloat16* __restrict__ plo, int64_t ppitch) {
   extern __shared__ __align__(16) float smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t item = (int64_t)blockIdx.x * SOLVE_WARPS + wib;
@@ -418,8 +420,16 @@ mlpg_solve_bwd_kernel(const float* __restrict__ go, int64_t go_bs, int64_t go_ts
       zw[k + 2] = (tt >= 0 && tt < T) ? zs[(tt - s) * 32 + lane] : 0.f;
     }
     float* prow = gib + (int64_t)t * gi_ts;
+    // planes output (phi != null): the gradient goes out as the bf16 hi/lo operand planes of the next GEMM, rows = b*T + t
+    const int64_t prow_p = ((int64_t)b * T + t) * ppitch + ci.in_col;
     if (!dyn) {
-      prow[0] = accumulate ? prow[0] + zw[2] : zw[2];
+      if (phi) {
+        const __nv_bfloat16 h = __float2bfloat16_rn(zw[2]);
+        phi[prow_p] = h;
+        plo[prow_p] = __float2bfloat16_rn(zw[2] - __bfloat162float(h));
+      } else {
+        prow[0] = accumulate ? prow[0] + zw[2] : zw[2];
+      }
     } else {
 #pragma unroll
       for (int w = 0; w < GANTTS_MAX_WINDOWS; ++w) {
@@ -427,15 +437,24 @@ mlpg_solve_bwd_kernel(const float* __restrict__ go, int64_t go_bs, int64_t go_ts
           float v = 0.f;
 #pragma unroll
           for (int k = -2; k <= 2; ++k) v = fmaf(taps.c[w][k + 2], zw[2 + k], v);       // z_{t + k}
-          float* q = prow + w * ci.sd;
-          *q = accumulate ? *q + v : v;
+          if (phi) {
+            const __nv_bfloat16 h = __float2bfloat16_rn(v);
+            phi[prow_p + w * ci.sd] = h;
+            plo[prow_p + w * ci.sd] = __float2bfloat16_rn(v - __bfloat162float(h));
+          } else {
+            float* q = prow + w * ci.sd;
+            *q = accumulate ? *q + v : v;
+          }
         }
       }
     }
   }
 }
 
-static bool solve_taps(const gantts_windows_t* win, SolveTaps* tp) {
+// which: 1 = forward, 2 = backward.  GANTTS_B200_MLPG_SOLVE is a bit mask of the directions that use the substitution
+// kernels (default 2: measured on B200 at cfg2 the backward is 35 us against the FIR's 49 us, the forward 50 us against
+// 43 us -- profiles/r02_mlpg.md).
+static bool solve_taps(const gantts_windows_t* win, SolveTaps* tp, int which) {
   int hb = 0;
   tp->nw = win->n;
   for (int w = 0; w < GANTTS_MAX_WINDOWS; ++w)
@@ -445,12 +464,9 @@ static bool solve_taps(const gantts_windows_t* win, SolveTaps* tp) {
     hb = win->l[w] + win->u[w] > hb ? win->l[w] + win->u[w] : hb;
     for (int k = -win->l[w]; k <= win->u[w]; ++k) tp->c[w][k + 2] = win->coef[w][k + win->l[w]];
   }
-  static int use = -1;
-  if (use < 0) {
-    const char* e = getenv("GANTTS_B200_MLPG_SOLVE");
-    use = e ? atoi(e) : 1;
-  }
-  return use && hb <= 2;
+  const char* e = getenv("GANTTS_B200_MLPG_SOLVE");
+  const int use = e ? atoi(e) : 2;
+  return (use & which) && hb <= 2;
 }
 
 static int check_layout(const gantts_streams_t* st, const gantts_windows_t* win, int* ncols) {
@@ -577,7 +593,7 @@ extern "C" int gantts_mlpg_fwd(const float* in, int64_t in_bs, int64_t in_ts, fl
   GANTTS_CHECK_ARG(in && out && table_dev && B >= 1 && T >= 1, "mlpg_fwd: bad arguments");
   {
     SolveTaps tp;
-    if (solve_taps(win, &tp)) {
+    if (solve_taps(win, &tp, 1)) {
       const int nchunks = (T + SC - 1) / SC, ncg = (ncols + 31) / 32;
       const int64_t nitems = (int64_t)B * nchunks * ncg;
       const size_t sm = (size_t)SOLVE_WARPS * SOLVE_ZROWS * 32 * sizeof(float);
@@ -619,6 +635,34 @@ extern "C" int gantts_mlpg_fwd(const float* in, int64_t in_bs, int64_t in_ts, fl
   return GANTTS_OK;
 }
 
+// MLPG backward whose result leaves as bf16 hi/lo operand planes [B*T][pitch] (fused step: the gradient w.r.t. y_hat
+// is consumed by the generator's backward GEMMs only).  Returns GANTTS_E_UNSUPPORTED when the substitution kernel does
+// not apply (the caller then takes the fp32 route).
+namespace gantts {
+static int mlpg_bwd_planes(const float* go, int64_t go_bs, int64_t go_ts, __nv_bfloat16* phi, __nv_bfloat16* plo,
+                           int64_t ppitch, const float* table_dev, const gantts_streams_t* st, const gantts_windows_t* win,
+                           int B, int T, void* stream) {
+  int ncols = 0;
+  int rc = check_layout(st, win, &ncols);
+  if (rc) return rc;
+  SolveTaps tp;
+  if (!solve_taps(win, &tp, 2)) return GANTTS_E_UNSUPPORTED;
+  const int nchunks = (T + SC - 1) / SC, ncg = (ncols + 31) / 32;
+  const int64_t nitems = (int64_t)B * nchunks * ncg;
+  const size_t sm = (size_t)SOLVE_WARPS * SOLVE_ZROWS * 32 * sizeof(float);
+  GANTTS_CUDA(cudaFuncSetAttribute(mlpg_solve_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  GANTTS_CUDA(cudaFuncSetAttribute(mlpg_solve_bwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  int in_cols = 0;
+  for (int s = 0; s < st->n; ++s) in_cols += st->sd[s] * (st->dyn[s] ? win->n : 1);
+  prof_begin(PROF_MLPG_BWD, 4.0 * (double)B * T * (in_cols + ncols), as_stream(stream));
+  mlpg_solve_bwd_kernel<<<(unsigned)((nitems + SOLVE_WARPS - 1) / SOLVE_WARPS), 32 * SOLVE_WARPS, sm, as_stream(stream)>>>(
+      go, go_bs, go_ts, nullptr, 0, 0, table_dev, *st, tp, T, ncols, nchunks, ncg, nitems, 0, phi, plo, ppitch);
+  prof_end(as_stream(stream));
+  GANTTS_LAUNCH_CHECK("mlpg_solve_bwd_kernel(planes)");
+  return GANTTS_OK;
+}
+}  // namespace gantts
+
 extern "C" int gantts_mlpg_bwd(const float* go, int64_t go_bs, int64_t go_ts, float* gi,
                                int64_t gi_bs, int64_t gi_ts, const float* table_dev,
                                const gantts_streams_t* st, const gantts_windows_t* win, int B, int T,
@@ -629,7 +673,7 @@ extern "C" int gantts_mlpg_bwd(const float* go, int64_t go_bs, int64_t go_ts, fl
   GANTTS_CHECK_ARG(go && gi && table_dev && B >= 1 && T >= 1, "mlpg_bwd: bad arguments");
   {
     SolveTaps tp;
-    if (solve_taps(win, &tp)) {
+    if (solve_taps(win, &tp, 2)) {
       const int nchunks = (T + SC - 1) / SC, ncg = (ncols + 31) / 32;
       const int64_t nitems = (int64_t)B * nchunks * ncg;
       const size_t sm = (size_t)SOLVE_WARPS * SOLVE_ZROWS * 32 * sizeof(float);
@@ -639,7 +683,7 @@ extern "C" int gantts_mlpg_bwd(const float* go, int64_t go_bs, int64_t go_ts, fl
       for (int s = 0; s < st->n; ++s) in_cols += st->sd[s] * (st->dyn[s] ? win->n : 1);
       prof_begin(PROF_MLPG_BWD, 4.0 * (double)B * T * (in_cols + ncols), as_stream(stream));
       mlpg_solve_bwd_kernel<<<(unsigned)((nitems + SOLVE_WARPS - 1) / SOLVE_WARPS), 32 * SOLVE_WARPS, sm, as_stream(stream)>>>(
-          go, go_bs, go_ts, gi, gi_bs, gi_ts, table_dev, *st, tp, T, ncols, nchunks, ncg, nitems, accumulate);
+          go, go_bs, go_ts, gi, gi_bs, gi_ts, table_dev, *st, tp, T, ncols, nchunks, ncg, nitems, accumulate, nullptr, nullptr, 0);
       prof_end(as_stream(stream));
       GANTTS_LAUNCH_CHECK("mlpg_solve_bwd_kernel");
       return GANTTS_OK;

@@ -625,3 +625,55 @@ def test_fused_step_with_chain_kernel_matches_default_path(dev, monkeypatch):
     for mode in ("3", "7"):
         for k, v in res["0"].items():
             assert abs(res[mode][k] - v) <= 2e-5 * max(abs(v), 1e-6), (mode, k, res[mode][k], v)
+
+
+# ------------------------------------------------------------------------------ GEMM launch variants
+@pytest.mark.parametrize("env,val", [("GANTTS_B200_TAIL", "1"), ("GANTTS_B200_BRES", "1"), ("GANTTS_B200_F32_STAGE", "0")])
+def test_gemm_launch_variants_are_bitwise_equal(dev, monkeypatch, env, val):
+    """Tail balancing (second launch with narrower column tiles for the incomplete last round), the B-resident pair
+    kernel and the staged fp32 epilogue change HOW a GEMM is tiled, not the order in which an output element
+    accumulates its K products: the default path and each variant must agree bit for bit, forward and backward,
+    dropout included (the second launch keys its dropout masks by global row)."""
+    from gantts_b200 import ops, _lib
+
+    def run():
+        torch.manual_seed(5)
+        outs = []
+        for dims, M, act in (([425, 512, 512, 187], 32000, _lib.ACT_NONE), ([58, 256, 256, 1], 40000, _lib.ACT_SIGMOID)):
+            Ws = [(torch.randn(o, i) / np.sqrt(i)).to(dev).requires_grad_(True) for i, o in zip(dims[:-1], dims[1:])]
+            bs = [(torch.randn(o) * 0.1).to(dev).requires_grad_(True) for o in dims[1:]]
+            x = torch.randn(M, dims[0], device=dev, requires_grad=True)
+            y = ops.mlp_stack(x, Ws, bs, p=0.5, training=True, seed=99, last_act=act)
+            y.backward(torch.ones_like(y))
+            outs += [y.detach(), x.grad] + [w.grad for w in Ws] + [b.grad for b in bs]
+        return outs
+    base = run()
+    monkeypatch.setenv(env, val)
+    if env == "GANTTS_B200_F32_STAGE":
+        pytest.skip("read once per process: exercised by the whole suite under GANTTS_B200_F32_STAGE=0 instead")
+    other = run()
+    for a, b in zip(base, other):
+        assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("mode", ["0", "3"])
+@pytest.mark.parametrize("B,Tn", [(3, 257), (2, 31), (1, 1000), (2, 5)])
+def test_mlpg_both_kernel_families_vs_dense_R(dev, monkeypatch, mode, B, Tn):
+    """multi_stream_mlpg forward and backward with the 49-tap FIR kernels (mode 0) and with the banded-Cholesky
+    substitution kernels (mode 3) against the dense R matmul of the reference path (oracle/nnmnkwii_port), TTS stream
+    layout (three dynamic streams + the static vuv column), lengths that do not divide the time chunks."""
+    import gantts_b200
+    monkeypatch.setenv("GANTTS_B200_MLPG_SOLVE", mode)
+    torch.manual_seed(int(mode) + Tn)
+    x = torch.randn(B, Tn, 187)
+    g = torch.randn(B, Tn, 63)
+    R = torch.from_numpy(nnp.unit_variance_mlpg_matrix(WINDOWS, Tn))
+    xr = x.clone().requires_grad_(True)
+    yr = gp.multi_stream_mlpg(xr, R)
+    yr.backward(g)
+    xd = x.to(dev).requires_grad_(True)
+    yd = gantts_b200.multistream.multi_stream_mlpg(xd, R.to(dev), [180, 3, 1, 3], [True, True, False, True])
+    yd.backward(g.to(dev))
+    assert rel_err(npy(yd), npy(yr)) < 5e-6
+    assert rel_err(npy(xd.grad), npy(xr.grad)) < 5e-6
+    assert torch.equal(yd[:, :, 61].cpu(), x[:, :, 183])          # static stream copied bit-exactly
