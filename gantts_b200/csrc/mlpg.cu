@@ -266,31 +266,39 @@ mlpg_bwd_kernel(const float* __restrict__ go, int64_t go_bs, int64_t go_ts,
 // so the HBM/L2 latency is paid in phase (1) with deep memory-level parallelism and the serial phases touch shared
 // memory only.  The per-column arithmetic depends on T only (chunking), not on which columns share the launch: the
 // reference's bitwise whole-vs-slice property (tests/test_gantts.py:156-159) holds.
-constexpr int SC = 32;                 // frames per chunk
+constexpr int SC = 64;                 // frames per chunk
 constexpr int SW = 32;                 // warm-up frames on either side
 constexpr int SOLVE_WARPS = 4;
-constexpr int SOLVE_ZROWS = SC + 2 * SW + 8;
+constexpr int SOLVE_ZROWS = SC + 2 * SW + 8;                        // strip rows per warp
+constexpr int SOLVE_WARP_FLOATS = SOLVE_ZROWS * 32 + SOLVE_ZROWS * 8;   // strip + the strip's Cholesky rows (2 x float4 per row)
 
 struct SolveTaps {
   float c[GANTTS_MAX_WINDOWS][5];      // coefficient of mu_w[t - k] in b_t, k = -2..2 at index k + 2 (0 where absent)
   int nw;
+  int qlo[GANTTS_MAX_WINDOWS], qhi[GANTTS_MAX_WINDOWS];   // rows q (of the 12-row batch window) any non-zero tap of w touches
 };
 
-__device__ __forceinline__ float4 chol_fwd(const float* __restrict__ table, int t) {
-  return __ldg(reinterpret_cast<const float4*>(table + (int64_t)t * TABW + 52));
-}
-__device__ __forceinline__ float4 chol_bwd(const float* __restrict__ table, int t) {
-  return __ldg(reinterpret_cast<const float4*>(table + (int64_t)t * TABW + 56));
+// Cholesky rows of the strip [s, s+n) into shared memory: cf[i] = {1/L_tt, L[t][t-1], L[t][t-2], -}, cb[i] = {1/L_tt,
+// L[t+1][t], L[t+2][t], -}: one LDS.128 (broadcast) per substitution step instead of two table loads with 64-bit address
+// arithmetic (the first version of these kernels spent 2.7x the expected instructions there).
+__device__ __forceinline__ void strip_coefs(float4* cf, float4* cb, int lane, const float* __restrict__ table, int s, int n) {
+  for (int i = lane; i < n; i += 32) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(table + (int64_t)(s + i) * TABW + 52));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(table + (int64_t)(s + i) * TABW + 56));
+    cf[i] = a;
+    cb[i] = make_float4(a.x, b.x, b.y, 0.f);
+  }
+  __syncwarp();
 }
 
-// forward substitution over rows [s, s + n) of the strip, in place (static columns are copied through)
-__device__ __forceinline__ void strip_forward(float* zs, int lane, const float* __restrict__ table, int s, int n, bool dyn) {
+// forward substitution over rows [0, n) of the strip, in place (static columns are copied through)
+__device__ __forceinline__ void strip_forward(float* zs, const float4* cf, int lane, int n, bool dyn) {
   float z1 = 0.f, z2 = 0.f;
-#pragma unroll 8
+#pragma unroll 4
   for (int i = 0; i < n; ++i) {
-    const float4 cf = chol_fwd(table, s + i);
+    const float4 c = cf[i];
     const float b = zs[i * 32 + lane];
-    float z = (b - cf.y * z1 - cf.z * z2) * cf.x;
+    float z = (b - c.y * z1 - c.z * z2) * c.x;
     if (!dyn) z = b;
     z2 = z1;
     z1 = z;
@@ -306,7 +314,9 @@ mlpg_solve_fwd_kernel(const float* __restrict__ in, int64_t in_bs, int64_t in_ts
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t item = (int64_t)blockIdx.x * SOLVE_WARPS + wib;
   if (item >= nitems) return;
-  float* zs = smem + (size_t)wib * SOLVE_ZROWS * 32;
+  float* zs = smem + (size_t)wib * SOLVE_WARP_FLOATS;
+  float4* cf = reinterpret_cast<float4*>(zs + SOLVE_ZROWS * 32);
+  float4* cb = cf + SOLVE_ZROWS;
   const int cg = (int)(item % ncg), chunk = (int)((item / ncg) % nchunks), b = (int)(item / ((int64_t)ncg * nchunks));
   const int oc = cg * 32 + lane;
   ColInfo ci = find_col(st, oc);
@@ -318,47 +328,61 @@ mlpg_solve_fwd_kernel(const float* __restrict__ in, int64_t in_bs, int64_t in_ts
   const int s = t0 - SW > 0 ? t0 - SW : 0;                  // strip start (exact state when s == 0)
   const int e = t1 + SW < T ? t1 + SW : T;                  // strip end (exact state when e == T)
   const int n = e - s;
-  // (1) b_t = sum_w sum_k coef_w[k+l] mu_w[t - k] for the whole strip, 8 frames per batch
+  strip_coefs(cf, cb, lane, table, s, n);
+  // (1) b_t = sum_w sum_k coef_w[k+l] mu_w[t - k] for the whole strip, 8 frames per batch: only the rows a non-zero tap
+  //     touches are loaded, zero taps are skipped (uniform branches), in-range batches skip the bounds checks
   for (int i0 = 0; i0 < n; i0 += 8) {
-    float xr[GANTTS_MAX_WINDOWS][12];                       // rows s+i0-2 .. s+i0+9 of every window component
+    float bt[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) bt[u] = 0.f;
+    const int r0 = s + i0 - 2;                              // row of batch-window index q = 0
+    const bool interior = r0 >= 0 && r0 + 11 < T;
 #pragma unroll
     for (int w = 0; w < GANTTS_MAX_WINDOWS; ++w) {
+      if (w >= taps.nw || (!dyn && w > 0)) continue;
+      float xr[12];
+      const float* wp = colp + (dyn ? w * ci.sd : 0) + (int64_t)r0 * in_ts;
 #pragma unroll
       for (int q = 0; q < 12; ++q) {
-        const int t = s + i0 - 2 + q;
-        const bool ok = valid && w < taps.nw && (dyn || w == 0) && t >= 0 && t < T;
-        xr[w][q] = ok ? __ldg(colp + (int64_t)t * in_ts + (dyn ? w * ci.sd : 0)) : 0.f;
+        xr[q] = 0.f;
+        if (q >= taps.qlo[w] && q <= taps.qhi[w]) {
+          if (interior) xr[q] = valid ? __ldg(wp + (int64_t)q * in_ts) : 0.f;
+          else if (valid && r0 + q >= 0 && r0 + q < T) xr[q] = __ldg(wp + (int64_t)q * in_ts);
+        }
+      }
+      if (!dyn) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) bt[u] = xr[u + 2];
+      } else {
+#pragma unroll
+        for (int k = -2; k <= 2; ++k) {
+          const float c = taps.c[w][k + 2];
+          if (c != 0.f) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) bt[u] = fmaf(c, xr[u + 2 - k], bt[u]);      // mu_w[t - k]
+          }
+        }
       }
     }
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      float bt = 0.f;
-#pragma unroll
-      for (int w = 0; w < GANTTS_MAX_WINDOWS; ++w) {
-#pragma unroll
-        for (int k = -2; k <= 2; ++k) bt = fmaf(taps.c[w][k + 2], xr[w][u + 2 - k], bt);      // mu_w[t - k]
-      }
-      if (!dyn) bt = xr[0][u + 2];
-      if (i0 + u < n) zs[(i0 + u) * 32 + lane] = bt;
-    }
+    for (int u = 0; u < 8; ++u)
+      if (i0 + u < n) zs[(i0 + u) * 32 + lane] = bt[u];
   }
   __syncwarp();
   // (2) forward substitution
-  strip_forward(zs, lane, table, s, n, dyn);
+  strip_forward(zs, cf, lane, n, dyn);
   // (3) backward substitution, straight to the output
   float y1 = 0.f, y2 = 0.f;
-  float* outp = out + (int64_t)b * out_bs + oc;
-#pragma unroll 8
+  float* outp = out + (int64_t)b * out_bs + oc + (int64_t)s * out_ts;
+#pragma unroll 4
   for (int i = n - 1; i >= t0 - s; --i) {
-    const int t = s + i;
-    const float4 cb = chol_bwd(table, t);
-    const float4 cf = chol_fwd(table, t);
+    const float4 c = cb[i];
     const float zt = zs[i * 32 + lane];
-    float y = (zt - cb.x * y1 - cb.y * y2) * cf.x;
+    float y = (zt - c.y * y1 - c.z * y2) * c.x;
     if (!dyn) y = zt;
     y2 = y1;
     y1 = y;
-    if (t < t1 && valid) outp[(int64_t)t * out_ts] = y;
+    if (s + i < t1 && valid) outp[(int64_t)i * out_ts] = y;
   }
 }
 
@@ -372,13 +396,14 @@ mlpg_solve_bwd_kernel(const float* __restrict__ go, int64_t go_bs, int64_t go_ts
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t item = (int64_t)blockIdx.x * SOLVE_WARPS + wib;
   if (item >= nitems) return;
-  float* zs = smem + (size_t)wib * SOLVE_ZROWS * 32;
+  float* zs = smem + (size_t)wib * SOLVE_WARP_FLOATS;
+  float4* cf = reinterpret_cast<float4*>(zs + SOLVE_ZROWS * 32);
+  float4* cb = cf + SOLVE_ZROWS;
   const int cg = (int)(item % ncg), chunk = (int)((item / ncg) % nchunks), b = (int)(item / ((int64_t)ncg * nchunks));
   const int oc = cg * 32 + lane;
   ColInfo ci = find_col(st, oc);
   const bool valid = ci.in_col >= 0 && oc < ncols;
   const bool dyn = valid && ci.dyn;
-  const float* gop = go + (int64_t)b * go_bs + oc;
   const int t0 = chunk * SC;
   const int t1 = t0 + SC < T ? t0 + SC : T;                 // gradient rows [t0, t1) are produced here
   const int lo = t0 - 2 > 0 ? t0 - 2 : 0;                   // z is needed on [t0-2, t1+2)
@@ -386,21 +411,23 @@ mlpg_solve_bwd_kernel(const float* __restrict__ go, int64_t go_bs, int64_t go_ts
   const int s = lo - SW > 0 ? lo - SW : 0;
   const int e = hi + SW < T ? hi + SW : T;
   const int n = e - s;                                      // <= SC + 4 + 2 SW
+  strip_coefs(cf, cb, lane, table, s, n);
   // (1) the strip of the upstream gradient
+  {
+    const float* gop = go + (int64_t)b * go_bs + oc + (int64_t)s * go_ts;
 #pragma unroll 8
-  for (int i = 0; i < n; ++i) zs[i * 32 + lane] = valid ? __ldg(gop + (int64_t)(s + i) * go_ts) : 0.f;
+    for (int i = 0; i < n; ++i) zs[i * 32 + lane] = valid ? __ldg(gop + (int64_t)i * go_ts) : 0.f;
+  }
   __syncwarp();
   // (2) forward, (3) backward substitution in place
-  strip_forward(zs, lane, table, s, n, dyn);
+  strip_forward(zs, cf, lane, n, dyn);
   {
     float y1 = 0.f, y2 = 0.f;
-#pragma unroll 8
+#pragma unroll 4
     for (int i = n - 1; i >= lo - s; --i) {
-      const int t = s + i;
-      const float4 cb = chol_bwd(table, t);
-      const float4 cf = chol_fwd(table, t);
+      const float4 c = cb[i];
       const float zt = zs[i * 32 + lane];
-      float y = (zt - cb.x * y1 - cb.y * y2) * cf.x;
+      float y = (zt - c.y * y1 - c.z * y2) * c.x;
       if (!dyn) y = zt;
       y2 = y1;
       y1 = y;
@@ -410,8 +437,8 @@ mlpg_solve_bwd_kernel(const float* __restrict__ go, int64_t go_bs, int64_t go_ts
   __syncwarp();
   // (4) gi_w[t] = sum_k coef_w[k+l] z_{t+k} on [t0, t1): z outside [0, T) is zero
   if (!valid) return;
-  float* gib = gi + (int64_t)b * gi_bs + ci.in_col;
-#pragma unroll 4
+  float* gib = gi ? gi + (int64_t)b * gi_bs + ci.in_col : nullptr;
+#pragma unroll 2
   for (int t = t0; t < t1; ++t) {
     float zw[5];
 #pragma unroll
@@ -419,9 +446,9 @@ mlpg_solve_bwd_kernel(const float* __restrict__ go, int64_t go_bs, int64_t go_ts
       const int tt = t + k;
       zw[k + 2] = (tt >= 0 && tt < T) ? zs[(tt - s) * 32 + lane] : 0.f;
     }
-    float* prow = gib + (int64_t)t * gi_ts;
     // planes output (phi != null): the gradient goes out as the bf16 hi/lo operand planes of the next GEMM, rows = b*T + t
     const int64_t prow_p = ((int64_t)b * T + t) * ppitch + ci.in_col;
+    float* prow = gib + (int64_t)t * gi_ts;
     if (!dyn) {
       if (phi) {
         const __nv_bfloat16 h = __float2bfloat16_rn(zw[2]);
@@ -459,10 +486,17 @@ static bool solve_taps(const gantts_windows_t* win, SolveTaps* tp, int which) {
   tp->nw = win->n;
   for (int w = 0; w < GANTTS_MAX_WINDOWS; ++w)
     for (int q = 0; q < 5; ++q) tp->c[w][q] = 0.f;
+  for (int w = 0; w < GANTTS_MAX_WINDOWS; ++w) { tp->qlo[w] = 2; tp->qhi[w] = 9; }
   for (int w = 0; w < win->n; ++w) {
     if (win->l[w] > 2 || win->u[w] > 2) return false;
     hb = win->l[w] + win->u[w] > hb ? win->l[w] + win->u[w] : hb;
-    for (int k = -win->l[w]; k <= win->u[w]; ++k) tp->c[w][k + 2] = win->coef[w][k + win->l[w]];
+    int kmin = 0, kmax = 0;
+    for (int k = -win->l[w]; k <= win->u[w]; ++k) {
+      tp->c[w][k + 2] = win->coef[w][k + win->l[w]];
+      if (tp->c[w][k + 2] != 0.f) { kmin = k < kmin ? k : kmin; kmax = k > kmax ? k : kmax; }
+    }
+    tp->qlo[w] = 2 - kmax;               // row index q = u + 2 - k, u = 0..7
+    tp->qhi[w] = 9 - kmin;
   }
   const char* e = getenv("GANTTS_B200_MLPG_SOLVE");
   const int use = e ? atoi(e) : 2;
@@ -596,7 +630,7 @@ extern "C" int gantts_mlpg_fwd(const float* in, int64_t in_bs, int64_t in_ts, fl
     if (solve_taps(win, &tp, 1)) {
       const int nchunks = (T + SC - 1) / SC, ncg = (ncols + 31) / 32;
       const int64_t nitems = (int64_t)B * nchunks * ncg;
-      const size_t sm = (size_t)SOLVE_WARPS * SOLVE_ZROWS * 32 * sizeof(float);
+      const size_t sm = (size_t)SOLVE_WARPS * SOLVE_WARP_FLOATS * sizeof(float);
       GANTTS_CUDA(cudaFuncSetAttribute(mlpg_solve_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
       // 53 KB per block: the full shared-memory carve-out lets 4 blocks (16 warps) share an SM -- one wave at cfg2
       GANTTS_CUDA(cudaFuncSetAttribute(mlpg_solve_fwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
@@ -649,7 +683,7 @@ static int mlpg_bwd_planes(const float* go, int64_t go_bs, int64_t go_ts, __nv_b
   if (!solve_taps(win, &tp, 2)) return GANTTS_E_UNSUPPORTED;
   const int nchunks = (T + SC - 1) / SC, ncg = (ncols + 31) / 32;
   const int64_t nitems = (int64_t)B * nchunks * ncg;
-  const size_t sm = (size_t)SOLVE_WARPS * SOLVE_ZROWS * 32 * sizeof(float);
+  const size_t sm = (size_t)SOLVE_WARPS * SOLVE_WARP_FLOATS * sizeof(float);
   GANTTS_CUDA(cudaFuncSetAttribute(mlpg_solve_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
   GANTTS_CUDA(cudaFuncSetAttribute(mlpg_solve_bwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   int in_cols = 0;
@@ -676,7 +710,7 @@ extern "C" int gantts_mlpg_bwd(const float* go, int64_t go_bs, int64_t go_ts, fl
     if (solve_taps(win, &tp, 2)) {
       const int nchunks = (T + SC - 1) / SC, ncg = (ncols + 31) / 32;
       const int64_t nitems = (int64_t)B * nchunks * ncg;
-      const size_t sm = (size_t)SOLVE_WARPS * SOLVE_ZROWS * 32 * sizeof(float);
+      const size_t sm = (size_t)SOLVE_WARPS * SOLVE_WARP_FLOATS * sizeof(float);
       GANTTS_CUDA(cudaFuncSetAttribute(mlpg_solve_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
       GANTTS_CUDA(cudaFuncSetAttribute(mlpg_solve_bwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
       int in_cols = 0;
