@@ -504,6 +504,23 @@ def run_b200_arm(args):
     e2e_ms, e2e_repeats = timed_repeats(e2e_loop)
     h2d = sum(t.numel() * 4 for t in host[0])
 
+    # ---------------- N > 1: what the two gradient all-reduces of a step cost by themselves (back to back, no skew to
+    # absorb): the residual the data-parallel step pays over the single-GPU step, reported next to it
+    allreduce = None
+    if world > 1 and path == "fused":
+        gbufs = [trainer.fs.grad_buffer(1).clone(), trainer.fs.grad_buffer(0).clone()]
+
+        def ar_loop(n):
+            for _ in range(n):
+                for b in gbufs:
+                    parallel.allreduce_sum_(b)
+                    b.mul_(1.0 / world)             # keeps the values bounded over the repeats
+
+        ar_loop(5)
+        ar_ms, _ = timed_repeats(ar_loop)
+        allreduce = {"us_per_step_pair": ar_ms * 1e3, "d_bytes": gbufs[0].numel() * 4, "g_bytes": gbufs[1].numel() * 4,
+                     "note": "D + G gradient all-reduce (NCCL) + one scale kernel each, timed alone"}
+
     # ---------------- drop-in path (cfg2, one process): the reference's own per-batch logic -- tests/trainpy_mirror.py =
     # train.py:528-580 with its inline BCE, its .item() calls, clip_grad_norm_ and torch.optim.Adagrad -- on the
     # `gantts` alias package (the B200 modules), dense R on the device as train.py builds it
@@ -605,6 +622,8 @@ def run_b200_arm(args):
             "step_tflops_algorithmic": algorithmic_flops_per_frame(w) * frames_per_step / (ms_per_step * 1e-3) / 1e12 / world,
             "roofline": roofline, "loss_g_last": loss_g,
             "path": "gantts_gan_step (one C call per mini-batch)" if path == "fused" else "GanTrainer (python-orchestrated native ops)"}
+    if allreduce is not None:
+        line["allreduce"] = allreduce
     if dropin is not None:
         line["dropin"] = dropin
     if cb is not None:

@@ -266,29 +266,44 @@ mlpg_bwd_kernel(const float* __restrict__ go, int64_t go_bs, int64_t go_ts,
 // so the HBM/L2 latency is paid in phase (1) with deep memory-level parallelism and the serial phases touch shared
 // memory only.  The per-column arithmetic depends on T only (chunking), not on which columns share the launch: the
 // reference's bitwise whole-vs-slice property (tests/test_gantts.py:156-159) holds.
-constexpr int SC = 64;                 // frames per chunk
-constexpr int SW = 32;                 // warm-up frames on either side
-constexpr int SOLVE_WARPS = 4;
-constexpr int SOLVE_ZROWS = SC + 2 * SW + 8;                        // strip rows per warp
-constexpr int SOLVE_WARP_FLOATS = SOLVE_ZROWS * 32 + SOLVE_ZROWS * 8;   // strip + the strip's Cholesky rows (2 x float4 per row)
+constexpr int SC = 32;                 // frames per chunk
+constexpr int SW = 28;                 // warm-up frames on either side (the recursion forgets at ~0.46 per frame: 4e-10)
+constexpr int SOLVE_WARPS = 4;         // the warps of a block work on the SAME chunk (different batch rows / column groups)
+constexpr int SOLVE_ZROWS = SC + 4 + 2 * SW;                        // strip rows per warp (backward: [t0-2, t1+2) + warm-up)
+constexpr int SOLVE_SMEM_FLOATS = SOLVE_ZROWS * 8 + SOLVE_WARPS * SOLVE_ZROWS * 32;   // Cholesky rows of the chunk + 4 strips
 
 struct SolveTaps {
   float c[GANTTS_MAX_WINDOWS][5];      // coefficient of mu_w[t - k] in b_t, k = -2..2 at index k + 2 (0 where absent)
   int nw;
-  int qlo[GANTTS_MAX_WINDOWS], qhi[GANTTS_MAX_WINDOWS];   // rows q (of the 12-row batch window) any non-zero tap of w touches
+  int std3;                            // the reference's windows: (0,0) | (1,1) with a zero centre tap | (1,1)
 };
 
-// Cholesky rows of the strip [s, s+n) into shared memory: cf[i] = {1/L_tt, L[t][t-1], L[t][t-2], -}, cb[i] = {1/L_tt,
-// L[t+1][t], L[t+2][t], -}: one LDS.128 (broadcast) per substitution step instead of two table loads with 64-bit address
-// arithmetic (the first version of these kernels spent 2.7x the expected instructions there).
-__device__ __forceinline__ void strip_coefs(float4* cf, float4* cb, int lane, const float* __restrict__ table, int s, int n) {
-  for (int i = lane; i < n; i += 32) {
+struct SolveItem {
+  int b, cg, chunk;
+  bool active;
+};
+
+// blocks are laid out chunk-major: ipc = ceil(B * ncg / SOLVE_WARPS) blocks per chunk
+__device__ __forceinline__ SolveItem solve_item(int B, int ncg, int bpc) {
+  SolveItem it;
+  it.chunk = blockIdx.x / bpc;
+  const int local = (blockIdx.x % bpc) * SOLVE_WARPS + (threadIdx.x >> 5);
+  it.active = local < B * ncg;
+  it.b = it.active ? local / ncg : 0;
+  it.cg = it.active ? local % ncg : 0;
+  return it;
+}
+
+// Cholesky rows of the strip [s, s+n) into shared memory, once per block: cf[i] = {1/L_tt, L[t][t-1], L[t][t-2], -},
+// cb[i] = {1/L_tt, L[t+1][t], L[t+2][t], -}: one broadcast LDS.128 per substitution step.
+__device__ __forceinline__ void strip_coefs(float4* cf, float4* cb, const float* __restrict__ table, int s, int n) {
+  for (int i = threadIdx.x; i < n; i += 32 * SOLVE_WARPS) {
     const float4 a = __ldg(reinterpret_cast<const float4*>(table + (int64_t)(s + i) * TABW + 52));
     const float4 b = __ldg(reinterpret_cast<const float4*>(table + (int64_t)(s + i) * TABW + 56));
     cf[i] = a;
     cb[i] = make_float4(a.x, b.x, b.y, 0.f);
   }
-  __syncwarp();
+  __syncthreads();
 }
 
 // forward substitution over rows [0, n) of the strip, in place (static columns are copied through)
@@ -306,61 +321,99 @@ __device__ __forceinline__ void strip_forward(float* zs, const float4* cf, int l
   }
 }
 
-__global__ void __launch_bounds__(32 * SOLVE_WARPS)
-mlpg_solve_fwd_kernel(const float* __restrict__ in, int64_t in_bs, int64_t in_ts, float* __restrict__ out, int64_t out_bs,
-                      int64_t out_ts, const float* __restrict__ table, gantts_streams_t st, SolveTaps taps, int T,
-                      int ncols, int nchunks, int ncg, int64_t nitems) {
+template <bool STD3>
+__global__ void __launch_bounds__(32 * SOLVE_WARPS, 4)
+mlpg_solve_fwd_kernel(const float* __restrict__ in, int64_t in_bs, int in_ts, float* __restrict__ out, int64_t out_bs,
+                      int out_ts, const float* __restrict__ table, gantts_streams_t st, SolveTaps taps, int B, int T,
+                      int ncols, int ncg, int bpc) {
   extern __shared__ __align__(16) float smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int64_t item = (int64_t)blockIdx.x * SOLVE_WARPS + wib;
-  if (item >= nitems) return;
-  float* zs = smem + (size_t)wib * SOLVE_WARP_FLOATS;
-  float4* cf = reinterpret_cast<float4*>(zs + SOLVE_ZROWS * 32);
+  const SolveItem it = solve_item(B, ncg, bpc);
+  float4* cf = reinterpret_cast<float4*>(smem);
   float4* cb = cf + SOLVE_ZROWS;
-  const int cg = (int)(item % ncg), chunk = (int)((item / ncg) % nchunks), b = (int)(item / ((int64_t)ncg * nchunks));
-  const int oc = cg * 32 + lane;
-  ColInfo ci = find_col(st, oc);
-  const bool valid = ci.in_col >= 0 && oc < ncols;
-  const bool dyn = valid && ci.dyn;
-  const float* colp = in + (int64_t)b * in_bs + (valid ? ci.in_col : 0);
-  const int t0 = chunk * SC;
+  float* zs = smem + SOLVE_ZROWS * 8 + (size_t)wib * SOLVE_ZROWS * 32;
+  const int t0 = it.chunk * SC;
   const int t1 = t0 + SC < T ? t0 + SC : T;                 // outputs [t0, t1)
   const int s = t0 - SW > 0 ? t0 - SW : 0;                  // strip start (exact state when s == 0)
   const int e = t1 + SW < T ? t1 + SW : T;                  // strip end (exact state when e == T)
   const int n = e - s;
-  strip_coefs(cf, cb, lane, table, s, n);
-  // (1) b_t = sum_w sum_k coef_w[k+l] mu_w[t - k] for the whole strip, 8 frames per batch: only the rows a non-zero tap
-  //     touches are loaded, zero taps are skipped (uniform branches), in-range batches skip the bounds checks
+  strip_coefs(cf, cb, table, s, n);
+  if (!it.active) return;
+  const int oc = it.cg * 32 + lane;
+  ColInfo ci = find_col(st, oc);
+  const bool valid = ci.in_col >= 0 && oc < ncols;
+  const bool dyn = valid && ci.dyn;
+  // per-lane view of the windows: a static column is "window 0 with coefficient 1", an out-of-range lane reads column 0
+  // of its batch row with all coefficients 0 -- no divergent branches in the gather below
+  const float* colp = in + (int64_t)it.b * in_bs + (valid ? ci.in_col : 0);
+  const int sd = dyn ? ci.sd : 0;
+  // (1) b_t = sum_w sum_k coef_w[k+l] mu_w[t - k] over the strip, 8 frames per batch
   for (int i0 = 0; i0 < n; i0 += 8) {
     float bt[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) bt[u] = 0.f;
-    const int r0 = s + i0 - 2;                              // row of batch-window index q = 0
+    const int r0 = s + i0 - 2;                              // row of batch-window index q = 0 (q = u + 2 - k)
     const bool interior = r0 >= 0 && r0 + 11 < T;
+    if (STD3) {
+      const float c0 = taps.c[0][2];
+      const float c1m = taps.c[1][1], c1p = taps.c[1][3];
+      const float c2m = taps.c[2][1], c2z = taps.c[2][2], c2p = taps.c[2][3];
+      float x0[8], x1[10], x2[10];           // rows t (q = 2..9) of window 0, rows t-1 .. t+1 (q = 1..10) of windows 1, 2
+      if (interior) {
+        const float* p0 = colp + (int64_t)(r0 + 2) * in_ts;
+        const float* p1 = colp + sd + (int64_t)(r0 + 1) * in_ts;
+        const float* p2 = p1 + sd;
 #pragma unroll
-    for (int w = 0; w < GANTTS_MAX_WINDOWS; ++w) {
-      if (w >= taps.nw || (!dyn && w > 0)) continue;
-      float xr[12];
-      const float* wp = colp + (dyn ? w * ci.sd : 0) + (int64_t)r0 * in_ts;
+        for (int q = 0; q < 10; ++q) {
+          x1[q] = __ldg(p1);
+          x2[q] = __ldg(p2);
+          p1 += in_ts;
+          p2 += in_ts;
+        }
 #pragma unroll
-      for (int q = 0; q < 12; ++q) {
-        xr[q] = 0.f;
-        if (q >= taps.qlo[w] && q <= taps.qhi[w]) {
-          if (interior) xr[q] = valid ? __ldg(wp + (int64_t)q * in_ts) : 0.f;
-          else if (valid && r0 + q >= 0 && r0 + q < T) xr[q] = __ldg(wp + (int64_t)q * in_ts);
+        for (int u = 0; u < 8; ++u) {
+          x0[u] = __ldg(p0);
+          p0 += in_ts;
+        }
+      } else {                               // first / last batches of a sequence: rows outside [0, T) read as zero
+#pragma unroll
+        for (int q = 0; q < 10; ++q) {
+          const int r = r0 + 1 + q;
+          const int rc = r < 0 ? 0 : (r >= T ? T - 1 : r);
+          const float* pr = colp + (int64_t)rc * in_ts;
+          const float a1 = __ldg(pr + sd), a2 = __ldg(pr + 2 * sd), a0 = __ldg(pr);
+          x1[q] = r == rc ? a1 : 0.f;
+          x2[q] = r == rc ? a2 : 0.f;
+          if (q >= 1 && q <= 8) x0[q - 1] = r == rc ? a0 : 0.f;
         }
       }
-      if (!dyn) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) bt[u] = xr[u + 2];
-      } else {
+      for (int u = 0; u < 8; ++u) {
+        // k = -1 -> row t+1 (x[u+2]), k = +1 -> row t-1 (x[u])
+        float v = c0 * x0[u];
+        v = fmaf(c1m, x1[u + 2], v);
+        v = fmaf(c1p, x1[u], v);
+        v = fmaf(c2m, x2[u + 2], v);
+        v = fmaf(c2z, x2[u + 1], v);
+        v = fmaf(c2p, x2[u], v);
+        bt[u] = dyn ? v : (valid ? x0[u] : 0.f);
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) bt[u] = 0.f;
+#pragma unroll
+      for (int w = 0; w < GANTTS_MAX_WINDOWS; ++w) {
+        if (w >= taps.nw) continue;
+        float xr[12];
+        const float* wp = colp + w * sd + (int64_t)r0 * in_ts;
+#pragma unroll
+        for (int q = 0; q < 12; ++q) {
+          const int r = r0 + q;
+          xr[q] = (valid && (dyn || w == 0) && r >= 0 && r < T) ? __ldg(wp + (int64_t)q * in_ts) : 0.f;
+        }
 #pragma unroll
         for (int k = -2; k <= 2; ++k) {
-          const float c = taps.c[w][k + 2];
-          if (c != 0.f) {
+          const float c = dyn ? taps.c[w][k + 2] : ((w == 0 && k == 0) ? 1.f : 0.f);
 #pragma unroll
-            for (int u = 0; u < 8; ++u) bt[u] = fmaf(c, xr[u + 2 - k], bt[u]);      // mu_w[t - k]
-          }
+          for (int u = 0; u < 8; ++u) bt[u] = fmaf(c, xr[u + 2 - k], bt[u]);      // mu_w[t - k]
         }
       }
     }
@@ -371,52 +424,63 @@ mlpg_solve_fwd_kernel(const float* __restrict__ in, int64_t in_bs, int64_t in_ts
   __syncwarp();
   // (2) forward substitution
   strip_forward(zs, cf, lane, n, dyn);
-  // (3) backward substitution, straight to the output
+  // (3) backward substitution: warm-up rows [t1, e) silently, then [t0, t1) straight to the output
   float y1 = 0.f, y2 = 0.f;
-  float* outp = out + (int64_t)b * out_bs + oc + (int64_t)s * out_ts;
 #pragma unroll 4
-  for (int i = n - 1; i >= t0 - s; --i) {
+  for (int i = n - 1; i >= t1 - s; --i) {
+    const float4 c = cb[i];
+    const float y = (zs[i * 32 + lane] - c.y * y1 - c.z * y2) * c.x;
+    y2 = y1;
+    y1 = y;
+  }
+  float* outp = out + (int64_t)it.b * out_bs + (valid ? oc : 0) + (int64_t)(t1 - 1) * out_ts;
+#pragma unroll 4
+  for (int i = t1 - s - 1; i >= t0 - s; --i) {
     const float4 c = cb[i];
     const float zt = zs[i * 32 + lane];
     float y = (zt - c.y * y1 - c.z * y2) * c.x;
     if (!dyn) y = zt;
     y2 = y1;
     y1 = y;
-    if (s + i < t1 && valid) outp[(int64_t)i * out_ts] = y;
+    if (valid) *outp = y;
+    outp -= out_ts;
   }
 }
 
 // Adjoint: z = P^-1 g (same two sweeps on the upstream gradient), gi_w[t] = sum_k coef_w[k+l] z_{t+k}.
-__global__ void __launch_bounds__(32 * SOLVE_WARPS)
-mlpg_solve_bwd_kernel(const float* __restrict__ go, int64_t go_bs, int64_t go_ts, float* __restrict__ gi, int64_t gi_bs,
-                      int64_t gi_ts, const float* __restrict__ table, gantts_streams_t st, SolveTaps taps, int T, int ncols,
-                      int nchunks, int ncg, int64_t nitems, int accumulate, __nv_bfloat16* __restrict__ phi,
-                      __nv_bfloat16* __restrict__ plo, int64_t ppitch) {
+template <bool STD3>
+__global__ void __launch_bounds__(32 * SOLVE_WARPS, 4)
+mlpg_solve_bwd_kernel(const float* __restrict__ go, int64_t go_bs, int go_ts, float* __restrict__ gi, int64_t gi_bs,
+                      int gi_ts, const float* __restrict__ table, gantts_streams_t st, SolveTaps taps, int B, int T, int ncols,
+                      int ncg, int bpc, int accumulate, __nv_bfloat16* __restrict__ phi, __nv_bfloat16* __restrict__ plo,
+                      int ppitch) {
   extern __shared__ __align__(16) float smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int64_t item = (int64_t)blockIdx.x * SOLVE_WARPS + wib;
-  if (item >= nitems) return;
-  float* zs = smem + (size_t)wib * SOLVE_WARP_FLOATS;
-  float4* cf = reinterpret_cast<float4*>(zs + SOLVE_ZROWS * 32);
+  const SolveItem it = solve_item(B, ncg, bpc);
+  float4* cf = reinterpret_cast<float4*>(smem);
   float4* cb = cf + SOLVE_ZROWS;
-  const int cg = (int)(item % ncg), chunk = (int)((item / ncg) % nchunks), b = (int)(item / ((int64_t)ncg * nchunks));
-  const int oc = cg * 32 + lane;
-  ColInfo ci = find_col(st, oc);
-  const bool valid = ci.in_col >= 0 && oc < ncols;
-  const bool dyn = valid && ci.dyn;
-  const int t0 = chunk * SC;
+  float* zs = smem + SOLVE_ZROWS * 8 + (size_t)wib * SOLVE_ZROWS * 32;
+  const int t0 = it.chunk * SC;
   const int t1 = t0 + SC < T ? t0 + SC : T;                 // gradient rows [t0, t1) are produced here
   const int lo = t0 - 2 > 0 ? t0 - 2 : 0;                   // z is needed on [t0-2, t1+2)
   const int hi = t1 + 2 < T ? t1 + 2 : T;
   const int s = lo - SW > 0 ? lo - SW : 0;
   const int e = hi + SW < T ? hi + SW : T;
   const int n = e - s;                                      // <= SC + 4 + 2 SW
-  strip_coefs(cf, cb, lane, table, s, n);
+  strip_coefs(cf, cb, table, s, n);
+  if (!it.active) return;
+  const int oc = it.cg * 32 + lane;
+  ColInfo ci = find_col(st, oc);
+  const bool valid = ci.in_col >= 0 && oc < ncols;
+  const bool dyn = valid && ci.dyn;
   // (1) the strip of the upstream gradient
   {
-    const float* gop = go + (int64_t)b * go_bs + oc + (int64_t)s * go_ts;
+    const float* gop = go + (int64_t)it.b * go_bs + (valid ? oc : 0) + (int64_t)s * go_ts;
 #pragma unroll 8
-    for (int i = 0; i < n; ++i) zs[i * 32 + lane] = valid ? __ldg(gop + (int64_t)i * go_ts) : 0.f;
+    for (int i = 0; i < n; ++i) {
+      zs[i * 32 + lane] = valid ? __ldg(gop) : 0.f;
+      gop += go_ts;
+    }
   }
   __syncwarp();
   // (2) forward, (3) backward substitution in place
@@ -437,7 +501,49 @@ mlpg_solve_bwd_kernel(const float* __restrict__ go, int64_t go_bs, int64_t go_ts
   __syncwarp();
   // (4) gi_w[t] = sum_k coef_w[k+l] z_{t+k} on [t0, t1): z outside [0, T) is zero
   if (!valid) return;
-  float* gib = gi ? gi + (int64_t)b * gi_bs + ci.in_col : nullptr;
+  if (STD3) {
+    const float c0 = dyn ? taps.c[0][2] : 1.f;
+    const float c1m = taps.c[1][1], c1p = taps.c[1][3];
+    const float c2m = taps.c[2][1], c2z = taps.c[2][2], c2p = taps.c[2][3];
+    const int sd = dyn ? ci.sd : 0;
+    float zm = t0 - 1 >= 0 ? zs[(t0 - 1 - s) * 32 + lane] : 0.f;
+    float zc = zs[(t0 - s) * 32 + lane];
+    // planes output (phi != null): the gradient goes out as the bf16 hi/lo operand planes of the next GEMM, rows = b*T + t
+    int64_t po = ((int64_t)it.b * T + t0) * ppitch + ci.in_col;
+    float* gp = gi ? gi + (int64_t)it.b * gi_bs + ci.in_col + (int64_t)t0 * gi_ts : nullptr;
+#pragma unroll 2
+    for (int t = t0; t < t1; ++t) {
+      const float zp = t + 1 < T ? zs[(t + 1 - s) * 32 + lane] : 0.f;
+      // coefficient index k + 2 multiplies z_{t + k}
+      const float v0 = c0 * zc;
+      const float v1 = fmaf(c1p, zp, c1m * zm);
+      const float v2 = fmaf(c2p, zp, fmaf(c2z, zc, c2m * zm));
+      if (phi) {
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(v0);
+        phi[po] = h0;
+        plo[po] = __float2bfloat16_rn(v0 - __bfloat162float(h0));
+        if (dyn) {
+          const __nv_bfloat16 h1 = __float2bfloat16_rn(v1), h2 = __float2bfloat16_rn(v2);
+          phi[po + sd] = h1;
+          plo[po + sd] = __float2bfloat16_rn(v1 - __bfloat162float(h1));
+          phi[po + 2 * sd] = h2;
+          plo[po + 2 * sd] = __float2bfloat16_rn(v2 - __bfloat162float(h2));
+        }
+        po += ppitch;
+      } else {
+        gp[0] = accumulate ? gp[0] + v0 : v0;
+        if (dyn) {
+          gp[sd] = accumulate ? gp[sd] + v1 : v1;
+          gp[2 * sd] = accumulate ? gp[2 * sd] + v2 : v2;
+        }
+        gp += gi_ts;
+      }
+      zm = zc;
+      zc = zp;
+    }
+    return;
+  }
+  float* gib = gi ? gi + (int64_t)it.b * gi_bs + ci.in_col : nullptr;
 #pragma unroll 2
   for (int t = t0; t < t1; ++t) {
     float zw[5];
@@ -446,8 +552,7 @@ mlpg_solve_bwd_kernel(const float* __restrict__ go, int64_t go_bs, int64_t go_ts
       const int tt = t + k;
       zw[k + 2] = (tt >= 0 && tt < T) ? zs[(tt - s) * 32 + lane] : 0.f;
     }
-    // planes output (phi != null): the gradient goes out as the bf16 hi/lo operand planes of the next GEMM, rows = b*T + t
-    const int64_t prow_p = ((int64_t)b * T + t) * ppitch + ci.in_col;
+    const int64_t prow_p = ((int64_t)it.b * T + t) * ppitch + ci.in_col;
     float* prow = gib + (int64_t)t * gi_ts;
     if (!dyn) {
       if (phi) {
@@ -478,6 +583,20 @@ mlpg_solve_bwd_kernel(const float* __restrict__ go, int64_t go_bs, int64_t go_ts
   }
 }
 
+struct SolveGrid {
+  int ncg, bpc;
+  unsigned blocks;
+  size_t smem;
+};
+static SolveGrid solve_grid(int B, int T, int ncols) {
+  SolveGrid g;
+  g.ncg = (ncols + 31) / 32;
+  g.bpc = (B * g.ncg + SOLVE_WARPS - 1) / SOLVE_WARPS;
+  g.blocks = (unsigned)(((T + SC - 1) / SC) * g.bpc);
+  g.smem = (size_t)SOLVE_SMEM_FLOATS * sizeof(float);
+  return g;
+}
+
 // which: 1 = forward, 2 = backward.  GANTTS_B200_MLPG_SOLVE is a bit mask of the directions that use the substitution
 // kernels (default 2: measured on B200 at cfg2 the backward is 35 us against the FIR's 49 us, the forward 50 us against
 // 43 us -- profiles/r02_mlpg.md).
@@ -486,22 +605,25 @@ static bool solve_taps(const gantts_windows_t* win, SolveTaps* tp, int which) {
   tp->nw = win->n;
   for (int w = 0; w < GANTTS_MAX_WINDOWS; ++w)
     for (int q = 0; q < 5; ++q) tp->c[w][q] = 0.f;
-  for (int w = 0; w < GANTTS_MAX_WINDOWS; ++w) { tp->qlo[w] = 2; tp->qhi[w] = 9; }
   for (int w = 0; w < win->n; ++w) {
     if (win->l[w] > 2 || win->u[w] > 2) return false;
     hb = win->l[w] + win->u[w] > hb ? win->l[w] + win->u[w] : hb;
-    int kmin = 0, kmax = 0;
-    for (int k = -win->l[w]; k <= win->u[w]; ++k) {
-      tp->c[w][k + 2] = win->coef[w][k + win->l[w]];
-      if (tp->c[w][k + 2] != 0.f) { kmin = k < kmin ? k : kmin; kmax = k > kmax ? k : kmax; }
-    }
-    tp->qlo[w] = 2 - kmax;               // row index q = u + 2 - k, u = 0..7
-    tp->qhi[w] = 9 - kmin;
+    for (int k = -win->l[w]; k <= win->u[w]; ++k) tp->c[w][k + 2] = win->coef[w][k + win->l[w]];
   }
+  // the sparsity pattern of the reference's windows (hparams.py: [1], [-0.5, 0, 0.5], [1, -2, 1]); any coefficients
+  bool std3 = win->n == 3;
+  for (int w = 0; w < 3 && std3; ++w) {
+    std3 = tp->c[w][0] == 0.f && tp->c[w][4] == 0.f;
+    if (w == 0) std3 = std3 && tp->c[0][1] == 0.f && tp->c[0][3] == 0.f;
+    if (w == 1) std3 = std3 && tp->c[1][2] == 0.f;
+  }
+  tp->std3 = std3 ? 1 : 0;
   const char* e = getenv("GANTTS_B200_MLPG_SOLVE");
   const int use = e ? atoi(e) : 2;
   return (use & which) && hb <= 2;
 }
+
+static bool fits_i32(int64_t v) { return v >= 0 && v < ((int64_t)1 << 31); }
 
 static int check_layout(const gantts_streams_t* st, const gantts_windows_t* win, int* ncols) {
   GANTTS_CHECK_ARG(st && win, "mlpg: null stream/window table");
@@ -627,18 +749,17 @@ extern "C" int gantts_mlpg_fwd(const float* in, int64_t in_bs, int64_t in_ts, fl
   GANTTS_CHECK_ARG(in && out && table_dev && B >= 1 && T >= 1, "mlpg_fwd: bad arguments");
   {
     SolveTaps tp;
-    if (solve_taps(win, &tp, 1)) {
-      const int nchunks = (T + SC - 1) / SC, ncg = (ncols + 31) / 32;
-      const int64_t nitems = (int64_t)B * nchunks * ncg;
-      const size_t sm = (size_t)SOLVE_WARPS * SOLVE_WARP_FLOATS * sizeof(float);
-      GANTTS_CUDA(cudaFuncSetAttribute(mlpg_solve_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-      // 53 KB per block: the full shared-memory carve-out lets 4 blocks (16 warps) share an SM -- one wave at cfg2
-      GANTTS_CUDA(cudaFuncSetAttribute(mlpg_solve_fwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    if (solve_taps(win, &tp, 1) && fits_i32((int64_t)T * in_ts) && fits_i32((int64_t)T * out_ts)) {
+      const SolveGrid g = solve_grid(B, T, ncols);
+      auto fn = tp.std3 ? mlpg_solve_fwd_kernel<true> : mlpg_solve_fwd_kernel<false>;
+      GANTTS_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+      // 50 KB per block: the full shared-memory carve-out lets 4 blocks (16 warps) share an SM
+      GANTTS_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
       int in_cols = 0;
       for (int s = 0; s < st->n; ++s) in_cols += st->sd[s] * (st->dyn[s] ? win->n : 1);
       prof_begin(PROF_MLPG_FWD, 4.0 * (double)B * T * (in_cols + ncols), as_stream(stream));
-      mlpg_solve_fwd_kernel<<<(unsigned)((nitems + SOLVE_WARPS - 1) / SOLVE_WARPS), 32 * SOLVE_WARPS, sm, as_stream(stream)>>>(
-          in, in_bs, in_ts, out, out_bs, out_ts, table_dev, *st, tp, T, ncols, nchunks, ncg, nitems);
+      fn<<<g.blocks, 32 * SOLVE_WARPS, g.smem, as_stream(stream)>>>(in, in_bs, (int)in_ts, out, out_bs, (int)out_ts, table_dev, *st,
+                                                                  tp, B, T, ncols, g.ncg, g.bpc);
       prof_end(as_stream(stream));
       GANTTS_LAUNCH_CHECK("mlpg_solve_fwd_kernel");
       return GANTTS_OK;
@@ -680,17 +801,16 @@ static int mlpg_bwd_planes(const float* go, int64_t go_bs, int64_t go_ts, __nv_b
   int rc = check_layout(st, win, &ncols);
   if (rc) return rc;
   SolveTaps tp;
-  if (!solve_taps(win, &tp, 2)) return GANTTS_E_UNSUPPORTED;
-  const int nchunks = (T + SC - 1) / SC, ncg = (ncols + 31) / 32;
-  const int64_t nitems = (int64_t)B * nchunks * ncg;
-  const size_t sm = (size_t)SOLVE_WARPS * SOLVE_WARP_FLOATS * sizeof(float);
-  GANTTS_CUDA(cudaFuncSetAttribute(mlpg_solve_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-  GANTTS_CUDA(cudaFuncSetAttribute(mlpg_solve_bwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  if (!solve_taps(win, &tp, 2) || !fits_i32((int64_t)T * go_ts) || !fits_i32((int64_t)B * T * ppitch)) return GANTTS_E_UNSUPPORTED;
+  const SolveGrid g = solve_grid(B, T, ncols);
+  auto fn = tp.std3 ? mlpg_solve_bwd_kernel<true> : mlpg_solve_bwd_kernel<false>;
+  GANTTS_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+  GANTTS_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   int in_cols = 0;
   for (int s = 0; s < st->n; ++s) in_cols += st->sd[s] * (st->dyn[s] ? win->n : 1);
   prof_begin(PROF_MLPG_BWD, 4.0 * (double)B * T * (in_cols + ncols), as_stream(stream));
-  mlpg_solve_bwd_kernel<<<(unsigned)((nitems + SOLVE_WARPS - 1) / SOLVE_WARPS), 32 * SOLVE_WARPS, sm, as_stream(stream)>>>(
-      go, go_bs, go_ts, nullptr, 0, 0, table_dev, *st, tp, T, ncols, nchunks, ncg, nitems, 0, phi, plo, ppitch);
+  fn<<<g.blocks, 32 * SOLVE_WARPS, g.smem, as_stream(stream)>>>(go, go_bs, (int)go_ts, nullptr, 0, 0, table_dev, *st, tp, B, T, ncols,
+                                                              g.ncg, g.bpc, 0, phi, plo, (int)ppitch);
   prof_end(as_stream(stream));
   GANTTS_LAUNCH_CHECK("mlpg_solve_bwd_kernel(planes)");
   return GANTTS_OK;
@@ -707,17 +827,16 @@ extern "C" int gantts_mlpg_bwd(const float* go, int64_t go_bs, int64_t go_ts, fl
   GANTTS_CHECK_ARG(go && gi && table_dev && B >= 1 && T >= 1, "mlpg_bwd: bad arguments");
   {
     SolveTaps tp;
-    if (solve_taps(win, &tp, 2)) {
-      const int nchunks = (T + SC - 1) / SC, ncg = (ncols + 31) / 32;
-      const int64_t nitems = (int64_t)B * nchunks * ncg;
-      const size_t sm = (size_t)SOLVE_WARPS * SOLVE_WARP_FLOATS * sizeof(float);
-      GANTTS_CUDA(cudaFuncSetAttribute(mlpg_solve_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-      GANTTS_CUDA(cudaFuncSetAttribute(mlpg_solve_bwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    if (solve_taps(win, &tp, 2) && fits_i32((int64_t)T * go_ts) && fits_i32((int64_t)T * gi_ts)) {
+      const SolveGrid g = solve_grid(B, T, ncols);
+      auto fn = tp.std3 ? mlpg_solve_bwd_kernel<true> : mlpg_solve_bwd_kernel<false>;
+      GANTTS_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+      GANTTS_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
       int in_cols = 0;
       for (int s = 0; s < st->n; ++s) in_cols += st->sd[s] * (st->dyn[s] ? win->n : 1);
       prof_begin(PROF_MLPG_BWD, 4.0 * (double)B * T * (in_cols + ncols), as_stream(stream));
-      mlpg_solve_bwd_kernel<<<(unsigned)((nitems + SOLVE_WARPS - 1) / SOLVE_WARPS), 32 * SOLVE_WARPS, sm, as_stream(stream)>>>(
-          go, go_bs, go_ts, gi, gi_bs, gi_ts, table_dev, *st, tp, T, ncols, nchunks, ncg, nitems, accumulate, nullptr, nullptr, 0);
+      fn<<<g.blocks, 32 * SOLVE_WARPS, g.smem, as_stream(stream)>>>(go, go_bs, (int)go_ts, gi, gi_bs, (int)gi_ts, table_dev, *st, tp, B, T,
+                                                                  ncols, g.ncg, g.bpc, accumulate, nullptr, nullptr, 0);
       prof_end(as_stream(stream));
       GANTTS_LAUNCH_CHECK("mlpg_solve_bwd_kernel");
       return GANTTS_OK;
