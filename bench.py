@@ -446,6 +446,14 @@ def run_b200_arm(args):
     for i in range(args.warmup):
         trainer.step(*resident[i % NUM_BATCHES])
     barrier()
+    if os.environ.get("GANTTS_B200_CUDA_PROFILE_STEPS"):
+        # profiler window (ncu --profile-from-start off): exactly N steps after the warm-up, so that a launch list or
+        # a --set full capture holds whole steps in launch order.  Numbers printed by such a run are never bench values.
+        torch.cuda.profiler.start()
+        for i in range(int(os.environ["GANTTS_B200_CUDA_PROFILE_STEPS"])):
+            trainer.step(*resident[i % NUM_BATCHES])
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -461,6 +469,13 @@ def run_b200_arm(args):
     clocks = sampler.stop() if rank == 0 else None
     value = frames_per_step / (ms_per_step * 1e-3)
     loss_g = float(last["out"]["loss_g"])
+    # host time to ENQUEUE a step (8 steps stay well inside the driver's launch queue, so the CPU never waits for the
+    # GPU): while it is below ms_per_step the GPU is never starved and a CUDA graph of the step would not change `value`
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    resident_loop(8)
+    host_enqueue_ms = (time.perf_counter() - t0) / 8 * 1e3
+    torch.cuda.synchronize()
     # ---------------- roofline pass: K steps again with CUDA events around every GEMM / chain / MLPG / LSTM launch
     # (kept out of the region `value` is timed on: the event records sit between consecutive kernels)
     lib.gantts_profile_enable(1)
@@ -618,6 +633,7 @@ def run_b200_arm(args):
                     "how": "pinned host x,y -> double-buffered cudaMemcpyAsync on a copy stream -> one step through the "
                            "public API (%s) -> 4 loss scalars D2H; copies inside the timed region" % path},
             "gpu_launches": int(round(launches * args.steps)), "gpu_launches_per_step": launches,
+            "host_enqueue_ms_per_step": host_enqueue_ms,
             "algorithmic_gflop_per_step": algorithmic_flops_per_frame(w) * w["B"] * w["T"] / 1e9,
             "step_tflops_algorithmic": algorithmic_flops_per_frame(w) * frames_per_step / (ms_per_step * 1e-3) / 1e12 / world,
             "roofline": roofline, "loss_g_last": loss_g,

@@ -619,7 +619,7 @@ static bool solve_taps(const gantts_windows_t* win, SolveTaps* tp, int which) {
   }
   tp->std3 = std3 ? 1 : 0;
   const char* e = getenv("GANTTS_B200_MLPG_SOLVE");
-  const int use = e ? atoi(e) : 2;
+  const int use = e ? atoi(e) : 3;
   return (use & which) && hb <= 2;
 }
 
