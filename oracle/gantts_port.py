@@ -417,3 +417,54 @@ def sru_layer_forward(x, W, b, bidirectional=False, use_tanh=False, use_relu=Tru
             hs[t] = r * gc + (1 - r) * xp
         outs.append(torch.stack(hs, 0))
     return torch.cat(outs, -1)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Logging metrics of the step (reference train.py:358-432): inv_scale :358-381, split_streams :384-397,
+# compute_distortions :399-432.  numpy float64; `hp` needs .name and, for "acoustic", .windows / .stream_sizes /
+# .has_dynamic_features, for "vc" .order.  nnmnkwii.preprocessing.inv_scale(x, m, s) = x * s + m.
+def inv_scale_streams(mgc, lf0, vuv, bap, Y_mean, Y_std, hp):
+    nw = len(hp.windows)
+    mgc_dim, lf0_dim, vuv_dim, bap_dim = hp.stream_sizes                     # static + dynamic domain (:360)
+    lf0_0 = mgc_dim
+    vuv_0 = lf0_0 + lf0_dim
+    bap_0 = vuv_0 + vuv_dim
+    mgc = mgc * Y_std[:mgc_dim // nw] + Y_mean[:mgc_dim // nw]               # :368
+    lf0 = lf0 * Y_std[lf0_0:lf0_0 + lf0_dim // nw] + Y_mean[lf0_0:lf0_0 + lf0_dim // nw]
+    bap = bap * Y_std[bap_0:bap_0 + bap_dim // nw] + Y_mean[bap_0:bap_0 + bap_dim // nw]
+    vuv = vuv * Y_std[vuv_0] + Y_mean[vuv_0]
+    return mgc, lf0, (vuv > 0.5).astype(np.int64), bap                       # :376-379
+
+
+def split_streams_np(y_static, Y_mean, Y_std, hp):
+    from . import nnmnkwii_port  # noqa: F401  (same package: the metrics live next to the MLPG port)
+    sizes = get_static_stream_sizes(hp.stream_sizes, hp.has_dynamic_features, len(hp.windows))   # :386
+    a = np.cumsum([0] + list(sizes))
+    y = np.asarray(y_static, dtype=np.float64)
+    return inv_scale_streams(y[:, :, a[0]:a[1]], y[:, :, a[1]:a[2]], y[:, :, a[2]], y[:, :, a[3]:], Y_mean, Y_std, hp)
+
+
+def compute_distortions(y_static, y_hat_static, Y_mean, Y_std, lengths, hp):
+    from . import nnmnkwii_port as M
+    Y_mean, Y_std = np.asarray(Y_mean, dtype=np.float64), np.asarray(Y_std, dtype=np.float64)
+    if hp.name == "acoustic":                                                 # :400-417
+        mgc, lf0, vuv, bap = split_streams_np(y_static, Y_mean, Y_std, hp)
+        mgc_h, lf0_h, vuv_h, bap_h = split_streams_np(y_hat_static, Y_mean, Y_std, hp)
+        try:
+            f0_mse = M.lf0_mean_squared_error(lf0, vuv, lf0_h, vuv_h, lengths=lengths, linear_domain=True)
+        except ZeroDivisionError:
+            f0_mse = float("nan")
+        return {"mcd": M.melcd(mgc[:, :, 1:], mgc_h[:, :, 1:], lengths=lengths),
+                "bap_mcd": M.melcd(bap, bap_h, lengths=lengths) / 10.0,
+                "f0_rmse": float(np.sqrt(f0_mse)),
+                "vuv_err": M.vuv_error(vuv, vuv_h, lengths=lengths)}
+    if hp.name == "duration":                                                 # :418-422
+        a = np.asarray(y_static, dtype=np.float64) * Y_std + Y_mean
+        b = np.asarray(y_hat_static, dtype=np.float64) * Y_std + Y_mean
+        return {"dur_rmse": float(np.sqrt(M.mean_squared_error(a, b, lengths=lengths)))}
+    if hp.name == "vc":                                                       # :423-428
+        d = hp.order
+        a = np.asarray(y_static, dtype=np.float64) * Y_std[:d] + Y_mean[:d]
+        b = np.asarray(y_hat_static, dtype=np.float64) * Y_std[:d] + Y_mean[:d]
+        return {"mcd": M.melcd(a, b, lengths=lengths)}
+    raise AssertionError("unknown hp.name %r" % (hp.name,))

@@ -174,3 +174,48 @@ def mlpg(mean_frames, variance_frames, windows):
             b += W.T @ (tau * mu[:, w * sd + d])
         out[:, d] = np.linalg.solve(P, b)
     return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# nnmnkwii.metrics (un-vendored; published definitions, parity unpinned against the package itself) -- the checker of
+# the device-side distortions kernel (csrc/metrics.cu).  Written over a flat valid-frame selection, independently of the
+# product's numpy shim (compat/nnmnkwii/metrics.py loops per utterance), so the two do not share code.
+def _valid_frames(a, lengths):
+    """(B, T, D) or (B, T) -> (n_valid_frames, D) float64 rows of the frames t < lengths[b]."""
+    a = np.asarray(a, dtype=np.float64)
+    if a.ndim == 2:
+        a = a[:, :, None]
+    B, T = a.shape[:2]
+    lengths = [T] * B if lengths is None else [int(v) for v in lengths]
+    keep = np.arange(T)[None, :] < np.asarray(lengths)[:, None]
+    return a[keep]
+
+
+def melcd(X, Y, lengths=None):
+    """10 / ln(10) * sqrt(2) * mean over valid frames of the Euclidean distance (dB)."""
+    d = _valid_frames(X, lengths) - _valid_frames(Y, lengths)
+    return float(10.0 / np.log(10.0) * np.sqrt(2.0) * np.mean(np.sqrt(np.sum(d * d, axis=1))))
+
+
+def mean_squared_error(X, Y, lengths=None):
+    """sum of squared differences over valid frames / number of valid FRAMES."""
+    d = _valid_frames(X, lengths) - _valid_frames(Y, lengths)
+    return float(np.sum(d * d) / d.shape[0])
+
+
+def lf0_mean_squared_error(src_f0, src_vuv, tgt_f0, tgt_vuv, lengths=None, linear_domain=False):
+    """MSE of (log-)F0 over valid frames voiced in both; ZeroDivisionError when there is none."""
+    sf, tf = _valid_frames(src_f0, lengths), _valid_frames(tgt_f0, lengths)
+    both = (_valid_frames(src_vuv, lengths)[:, 0] + _valid_frames(tgt_vuv, lengths)[:, 0]) >= 2
+    if linear_domain:
+        sf, tf = np.exp(sf), np.exp(tf)
+    n = int(np.count_nonzero(both))
+    if n == 0:
+        raise ZeroDivisionError("no frame voiced in both source and target")
+    d = sf[both] - tf[both]
+    return float(np.sum(d * d) / n)
+
+
+def vuv_error(src_vuv, tgt_vuv, lengths=None):
+    a, b = _valid_frames(src_vuv, lengths), _valid_frames(tgt_vuv, lengths)
+    return float(np.count_nonzero(a != b) / a.shape[0])

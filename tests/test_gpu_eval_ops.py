@@ -24,38 +24,11 @@ def dev():
     return torch.device("cuda:0")
 
 
-def _np_metrics():
-    """The numpy shim of nnmnkwii.metrics (compat/), used here as the CPU oracle of the device kernel."""
-    import importlib.util
-    spec = importlib.util.spec_from_file_location("_np_metrics", os.path.join(ROOT, "compat", "nnmnkwii", "metrics.py"))
-    m = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(m)
-    return m
-
-
 def _reference_compute_distortions(y, yh, Ym, Ys, lengths, hp):
-    """train.py:358-432 restated on numpy (split_streams + inv_scale + metrics)."""
-    M = _np_metrics()
-    nw = len(hp.windows)
-    mgc_dim, lf0_dim, vuv_dim, bap_dim = hp.stream_sizes
-    s = [d // nw if dyn else d for d, dyn in zip(hp.stream_sizes, hp.has_dynamic_features)]
-    lf0_i, vuv_i, bap_i = mgc_dim, mgc_dim + lf0_dim, mgc_dim + lf0_dim + vuv_dim
-
-    def split(a):
-        mgc, lf0 = a[:, :, :s[0]], a[:, :, s[0]:s[0] + s[1]]
-        vuv, bap = a[:, :, s[0] + s[1]], a[:, :, s[0] + s[1] + s[2]:]
-        mgc = mgc * Ys[:mgc_dim // nw] + Ym[:mgc_dim // nw]
-        lf0 = lf0 * Ys[lf0_i:lf0_i + lf0_dim // nw] + Ym[lf0_i:lf0_i + lf0_dim // nw]
-        bap = bap * Ys[bap_i:bap_i + bap_dim // nw] + Ym[bap_i:bap_i + bap_dim // nw]
-        vuv = (vuv * Ys[vuv_i] + Ym[vuv_i] > 0.5).astype(np.int64)
-        return mgc, lf0, vuv, bap
-
-    mgc, lf0, vuv, bap = split(y)
-    mgc_h, lf0_h, vuv_h, bap_h = split(yh)
-    return {"mcd": M.melcd(mgc[:, :, 1:], mgc_h[:, :, 1:], lengths=lengths),
-            "bap_mcd": M.melcd(bap, bap_h, lengths=lengths) / 10.0,
-            "f0_rmse": math.sqrt(M.lf0_mean_squared_error(lf0, vuv, lf0_h, vuv_h, lengths=lengths, linear_domain=True)),
-            "vuv_err": M.vuv_error(vuv, vuv_h, lengths=lengths)}
+    """reference train.py:358-432 as restated in oracle/ (gantts_port.compute_distortions over nnmnkwii_port's metrics --
+    the checker shares no code with the product's numpy shim compat/nnmnkwii/metrics.py)."""
+    from oracle import gantts_port as gp
+    return gp.compute_distortions(y, yh, Ym, Ys, lengths, hp)
 
 
 @pytest.mark.parametrize("B,T", [(3, 50), (32, 1000)])
@@ -82,7 +55,7 @@ def test_compute_distortions_acoustic(dev, B, T):
 
 def test_compute_distortions_vc_and_duration(dev):
     from gantts_b200 import metrics
-    M = _np_metrics()
+    from oracle import gantts_port as gp
     rng = np.random.RandomState(4)
     B, T = 4, 70
     lengths = [70, 66, 41, 40]
@@ -91,13 +64,13 @@ def test_compute_distortions_vc_and_duration(dev):
     Ym, Ys = rng.randn(177), 0.5 + rng.rand(177)
     hp = types.SimpleNamespace(name="vc", order=59)
     got = metrics.compute_distortions(torch.from_numpy(y).to(dev), torch.from_numpy(yh).to(dev), Ym, Ys, lengths, hp)
-    want = M.melcd(y * Ys[:59] + Ym[:59], yh * Ys[:59] + Ym[:59], lengths=lengths)
+    want = gp.compute_distortions(y, yh, Ym, Ys, lengths, hp)["mcd"]
     assert abs(got["mcd"] - want) <= 2e-5 * want
     hp = types.SimpleNamespace(name="duration")
     y5, yh5 = y[:, :, :5], yh[:, :, :5]
     got = metrics.compute_distortions(torch.from_numpy(y5).to(dev), torch.from_numpy(yh5).to(dev), Ym[:5], Ys[:5],
                                       lengths, hp)
-    want = math.sqrt(M.mean_squared_error(y5 * Ys[:5] + Ym[:5], yh5 * Ys[:5] + Ym[:5], lengths=lengths))
+    want = gp.compute_distortions(y5, yh5, Ym[:5], Ys[:5], lengths, hp)["dur_rmse"]
     assert abs(got["dur_rmse"] - want) <= 2e-5 * want
 
 

@@ -218,3 +218,51 @@ def test_variance_mlpg_restatement_reduces_to_R():
     v = np.ones(3 * sd)
     v[[0, sd, 2 * sd]] = 7.0
     np.testing.assert_allclose(nnp.mlpg(mu, v, WINDOWS), nnp.mlpg(mu, np.ones(3 * sd), WINDOWS), atol=1e-9)
+
+
+def test_metrics_restatement_hand_values_and_agrees_with_the_shim():
+    """oracle/nnmnkwii_port metrics (the checker of csrc/metrics.cu) against hand-computed values, and against the product's
+    separately written numpy shim (compat/nnmnkwii/metrics.py): two restatements of the published nnmnkwii definitions
+    (package not vendored: parity unpinned) that share no code."""
+    import importlib.util
+    import os
+    import types
+    from oracle import nnmnkwii_port as M
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("_shim_metrics", os.path.join(root, "compat", "nnmnkwii", "metrics.py"))
+    shim = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(shim)
+    rs = np.random.RandomState(1)
+    X, Y = rs.randn(2, 5, 4), rs.randn(2, 5, 4)
+    lens = [5, 3]
+    exp = 10 / np.log(10) * np.sqrt(2) * (np.sqrt(((X[0] - Y[0]) ** 2).sum(-1)).sum() +
+                                          np.sqrt(((X[1, :3] - Y[1, :3]) ** 2).sum(-1)).sum()) / 8
+    assert abs(M.melcd(X, Y, lens) - exp) < 1e-9
+    assert abs(M.mean_squared_error(X, Y, lens) - (((X[0] - Y[0]) ** 2).sum() + ((X[1, :3] - Y[1, :3]) ** 2).sum()) / 8) < 1e-12
+    v1 = np.array([[1, 1, 0, 1, 1], [1, 0, 1, 1, 1]], float)
+    v2 = np.array([[1, 0, 0, 1, 1], [1, 1, 1, 0, 0]], float)
+    assert M.vuv_error(v1, v2, lens) == 2 / 8
+    f1, f2 = rs.rand(2, 5, 1), rs.rand(2, 5, 1)
+    both = [(0, 0), (0, 3), (0, 4), (1, 0), (1, 2)]
+    exp = sum((f1[b, t, 0] - f2[b, t, 0]) ** 2 for b, t in both) / len(both)
+    assert abs(M.lf0_mean_squared_error(f1, v1, f2, v2, lens) - exp) < 1e-12
+    with pytest.raises(ZeroDivisionError):
+        M.lf0_mean_squared_error(f1, v1 * 0, f2, v2, lens)
+    for fn in ("melcd", "mean_squared_error"):
+        assert abs(getattr(M, fn)(X, Y, lens) - getattr(shim, fn)(X, Y, lens)) < 1e-12
+    assert abs(M.lf0_mean_squared_error(f1, v1, f2, v2, lens, linear_domain=True) -
+               shim.lf0_mean_squared_error(f1, v1, f2, v2, lens, linear_domain=True)) < 1e-12
+    # train.py:399-432 on top of them: acoustic split + inverse scaling
+    from oracle import gantts_port as gp
+    from conftest import WINDOWS
+    hp = types.SimpleNamespace(name="acoustic", windows=WINDOWS, stream_sizes=[180, 3, 1, 3],
+                               has_dynamic_features=[True, True, False, True])
+    y = rs.randn(2, 6, 63)
+    yh = y + 0.1 * rs.randn(2, 6, 63)
+    Ym, Ys = rs.randn(187) * 0.1, 0.5 + rs.rand(187)
+    Ym[183], Ys[183] = 0.5, 0.5
+    d = gp.compute_distortions(y, yh, Ym, Ys, [6, 4], hp)
+    mgc = y[:, :, 1:60] * Ys[1:60] + Ym[1:60]
+    mgc_h = yh[:, :, 1:60] * Ys[1:60] + Ym[1:60]
+    assert abs(d["mcd"] - M.melcd(mgc, mgc_h, [6, 4])) < 1e-12
+    assert set(d) == {"mcd", "bap_mcd", "f0_rmse", "vuv_err"}

@@ -14,6 +14,10 @@ timeout 600 python bench.py --workload cfg3 --no-cpu-baseline > gpurun_out/bench
 timeout 600 python bench.py --workload cfg5 --no-cpu-baseline > gpurun_out/bench_${TAG}_cfg5.json 2>> gpurun_out/bench_${TAG}.err
 export GANTTS_B200_CUDA_PROFILE_STEPS=1
 timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_${TAG}.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-dropin > gpurun_out/ncu_list_${TAG}.log 2>&1
-timeout 1200 ncu --profile-from-start off --set full --clock-control none --import-source on -o gpurun_out/prof_step_${TAG} -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-dropin > gpurun_out/ncu_full_${TAG}.log 2>&1
+timeout 1200 ncu --profile-from-start off --set full --clock-control none -o gpurun_out/prof_step_${TAG} -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-dropin > gpurun_out/ncu_full_${TAG}.log 2>&1
 unset GANTTS_B200_CUDA_PROFILE_STEPS
+# gpurun copies back at most 64 MiB: keep the raw-page CSV of the capture, drop the report itself when it is large
+ncu -i gpurun_out/prof_step_${TAG}.ncu-rep --page raw --csv > gpurun_out/step_full_${TAG}.csv 2>/dev/null
+if [ $(du -sm gpurun_out | cut -f1) -gt 55 ]; then rm -f gpurun_out/prof_step_${TAG}.ncu-rep; fi
+du -sm gpurun_out
 ls -la gpurun_out | grep ${TAG}

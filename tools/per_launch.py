@@ -53,9 +53,13 @@ def short(name):
 
 def full_metrics():
     rep = os.path.join(GO, "prof_step_%s.ncu-rep" % TAG)
-    if not os.path.exists(rep):
+    raw = os.path.join(GO, "step_full_%s.csv" % TAG)
+    if os.path.exists(raw):
+        out = open(raw).read()
+    elif os.path.exists(rep):
+        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    else:
         return None
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     if len(rows) < 3:
         return None
