@@ -458,12 +458,14 @@ chain_pair_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
 #pragma unroll
             for (int e = 0; e < 16; ++e) v[e] = fmaxf(v[e], v[e] * p.slope);
             if (p.thresh && !(p.dbg & 2u)) {
-              const uint32_t half_n = (uint32_t)(L.n_valid + 1) >> 1;
+              const uint32_t quarter_n = (uint32_t)(L.n_valid + 3) >> 2, limit = drop_limit(p.thresh);
 #pragma unroll
-              for (int e = 0; e < 16; e += 2) {
-                const uint32_t bits = dropout_pair_bits(L.seed, (uint32_t)row, half_n, (uint32_t)(col + e) >> 1);
-                v[e] = (bits & 0xffffu) >= p.thresh ? v[e] * p.keep_scale : 0.f;
-                v[e + 1] = (bits >> 16) >= p.thresh ? v[e + 1] * p.keep_scale : 0.f;
+              for (int e = 0; e < 16; e += 4) {
+                const DropBits d = dropout_quad_bits(L.seed, (uint32_t)row, quarter_n, (uint32_t)(col + e) >> 2);
+                v[e] = (d.a << 16) > limit ? v[e] * p.keep_scale : 0.f;
+                v[e + 1] = d.a > limit ? v[e + 1] * p.keep_scale : 0.f;
+                v[e + 2] = (d.b << 16) > limit ? v[e + 2] * p.keep_scale : 0.f;
+                v[e + 3] = d.b > limit ? v[e + 3] * p.keep_scale : 0.f;
               }
             }
             if (L.n_valid < L.N) {

@@ -70,20 +70,35 @@ __device__ __forceinline__ void block_sum(float (&v)[NV], float* smem) {
   }
 }
 
-// Counter-based keep decision for dropout: one 32-bit hash per PAIR of adjacent columns
-// (key = row * ceil(N/2) + col/2, 32-bit wrap-around arithmetic), 16-bit threshold per element:
-// keep iff field >= thresh, thresh = round(p * 65536).  Both GEMM engines use exactly this
-// function, so they produce identical masks.  Not torch's Philox stream (hard part 4).
-__device__ __forceinline__ uint32_t dropout_pair_bits(uint64_t seed, uint32_t row, uint32_t half_n,
-                                                      uint32_t pair_col) {
-  uint32_t x = (row * half_n + pair_col) * 0x9E3779B1u + static_cast<uint32_t>(seed);
+// Counter-based keep decision for dropout: one 32-bit mixing chain per FOUR adjacent columns
+// (key = row * ceil(N/4) + col/4, 32-bit wrap-around arithmetic) gives word a (columns 4q, 4q+1) and, by one more
+// multiply-xorshift round, word b (columns 4q+2, 4q+3); 16-bit field per element, low field = even column:
+// keep iff field >= thresh, thresh = round(p * 65536).  Every engine (tcgen05 epilogues, chain kernel, SIMT GEMM,
+// LSTM inter-layer dropout, gantts_dropout) uses exactly this function, so they produce identical masks.
+// Not torch's Philox stream (hard part 4).  (Round 1 hashed once per column PAIR: the epilogues are
+// issue-bound and the hash was ~16 % of their instructions -- profiles/r02_gemm_experiments.md.)
+struct DropBits {
+  uint32_t a, b;
+};
+__device__ __forceinline__ DropBits dropout_quad_bits(uint64_t seed, uint32_t row, uint32_t quarter_n, uint32_t quad) {
+  uint32_t x = (row * quarter_n + quad) * 0x9E3779B1u + static_cast<uint32_t>(seed);
   x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
-  return x ^ static_cast<uint32_t>(seed >> 32);
+  uint32_t y = x * 0x9E3779B1u;
+  y ^= y >> 15;
+  const uint32_t s = static_cast<uint32_t>(seed >> 32);
+  DropBits r;
+  r.a = x ^ s;
+  r.b = y ^ s;
+  return r;
 }
+// keep iff field >= thresh  <=>  word > drop_limit(thresh) for the HIGH field of `word`, (word << 16) > the same limit
+// for the LOW field (thresh in [1, 65536]; 65536 = p 1.0 keeps nothing): one compare per element without extracting it.
+__device__ __forceinline__ uint32_t drop_limit(uint32_t thresh) { return ((thresh - 1u) << 16) | 0xffffu; }
 __device__ __forceinline__ bool dropout_keep(uint64_t seed, uint32_t row, uint32_t n_cols, uint32_t col,
                                              uint32_t thresh) {
-  uint32_t bits = dropout_pair_bits(seed, row, (n_cols + 1) >> 1, col >> 1);
-  uint32_t f = (col & 1) ? (bits >> 16) : (bits & 0xffffu);
+  const DropBits q = dropout_quad_bits(seed, row, (n_cols + 3) >> 2, col >> 2);
+  const uint32_t w = (col & 2) ? q.b : q.a;
+  const uint32_t f = (col & 1) ? (w >> 16) : (w & 0xffffu);
   return f >= thresh;
 }
 

@@ -117,6 +117,21 @@ __device__ __forceinline__ void store_planes16(const float* v, __nv_bfloat16* hi
   }
 }
 
+// Dropout of the 16 values of one row at columns [col, col+16), col % 16 == 0: v = keep ? v * scale : 0
+// (common.cuh: one hash chain per four columns, one unsigned compare per element).
+__device__ __forceinline__ void dropout16(float (&v)[16], uint64_t seed, uint32_t row, int n_cols, int col, uint32_t thresh,
+                                          float scale) {
+  const uint32_t quarter_n = (uint32_t)(n_cols + 3) >> 2, limit = drop_limit(thresh);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const DropBits d = dropout_quad_bits(seed, row, quarter_n, ((uint32_t)col >> 2) + q);
+    v[4 * q] = (d.a << 16) > limit ? v[4 * q] * scale : 0.f;
+    v[4 * q + 1] = d.a > limit ? v[4 * q + 1] * scale : 0.f;
+    v[4 * q + 2] = (d.b << 16) > limit ? v[4 * q + 2] * scale : 0.f;
+    v[4 * q + 3] = d.b > limit ? v[4 * q + 3] * scale : 0.f;
+  }
+}
+
 // EPI_F32 for outputs whose row stride is not a multiple of 4 floats (y_hat: ld 187, the discriminator input
 // gradient: ld 58, weight-gradient partials of 425- and 58-wide layers).  Straight from registers a thread can
 // only issue 16 scalar stores per chunk and a warp store touches 32 rows = 32 sectors (the 512->187 layer takes
@@ -145,15 +160,7 @@ __device__ __forceinline__ void epilogue_f32_staged(const GemmParams& p, const u
   if (p.act == GANTTS_ACT_LEAKY_DROPOUT) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], v[j] * p.slope);
-    if (p.thresh) {
-      const uint32_t half_n = (uint32_t)(p.cols_b + 1) >> 1;
-#pragma unroll
-      for (int j = 0; j < 16; j += 2) {
-        const uint32_t bits = dropout_pair_bits(p.seed, (uint32_t)(row + p.row0), half_n, (uint32_t)(col + j) >> 1);
-        v[j] = (bits & 0xffffu) >= p.thresh ? v[j] * p.keep_scale : 0.f;
-        v[j + 1] = (bits >> 16) >= p.thresh ? v[j + 1] * p.keep_scale : 0.f;
-      }
-    }
+    if (p.thresh) dropout16(v, p.seed, (uint32_t)(row + p.row0), p.cols_b, col, p.thresh, p.keep_scale);
   } else if (p.act == GANTTS_ACT_SIGMOID) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = 1.f / (1.f + expf(-v[j]));
@@ -166,15 +173,21 @@ __device__ __forceinline__ void epilogue_f32_staged(const GemmParams& p, const u
   float* cbase = p.C + (int64_t)z * p.c_zstride;
   const int j = lane & 15, hr = lane >> 4;
   const bool col_ok = col + j < p.cols_b;
+  float* q0 = cbase + (row0 + hr) * p.ldc + col + j;
+  // accumulate (the discriminator's input gradient added into its window of g_static): all 16 loads are issued before
+  // the first store -- interleaved `*q = *q + val` serialises 16 load -> store round trips per warp (the compiler must
+  // assume the store aliases the next load): 31.6 us per launch against a 6 us HBM floor (profiles/r02_gemm_per_launch.md)
+  float old[16];
+  if (p.accumulate) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      old[i] = (col_ok && row0 + 2 * i + hr < p.rows_a) ? __ldcg(q0 + (int64_t)(2 * i) * p.ldc) : 0.f;
+  }
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     const int rr = 2 * i + hr;
     const float val = scr[rr * 16 + 4 * ((j >> 2) ^ ((rr >> 1) & 3)) + (j & 3)];
-    const int64_t grow = row0 + rr;
-    if (col_ok && grow < p.rows_a) {
-      float* q = cbase + grow * p.ldc + col + j;
-      *q = p.accumulate ? *q + val : val;
-    }
+    if (col_ok && row0 + rr < p.rows_a) q0[(int64_t)(2 * i) * p.ldc] = p.accumulate ? old[i] + val : val;
   }
   __syncwarp();
 }
@@ -204,15 +217,7 @@ __device__ __forceinline__ uint32_t epilogue_chunk16(const GemmParams& p, const 
     if (p.act == GANTTS_ACT_LEAKY_DROPOUT) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], v[j] * p.slope);
-      if (p.thresh) {
-        const uint32_t half_n = (uint32_t)(p.cols_b + 1) >> 1;
-#pragma unroll
-        for (int j = 0; j < 16; j += 2) {
-          const uint32_t bits = dropout_pair_bits(p.seed, (uint32_t)(row + p.row0), half_n, (uint32_t)(col + j) >> 1);
-          v[j] = (bits & 0xffffu) >= p.thresh ? v[j] * p.keep_scale : 0.f;
-          v[j + 1] = (bits >> 16) >= p.thresh ? v[j + 1] * p.keep_scale : 0.f;
-        }
-      }
+      if (p.thresh) dropout16(v, p.seed, (uint32_t)(row + p.row0), p.cols_b, col, p.thresh, p.keep_scale);
     } else if (p.act == GANTTS_ACT_SIGMOID) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] = 1.f / (1.f + expf(-v[j]));
@@ -248,34 +253,41 @@ __device__ __forceinline__ uint32_t epilogue_chunk16(const GemmParams& p, const 
       for (int j = 0; j < 16; ++j)
         if (col + j < p.cols_b) v[j] += __ldg(p.bias + col + j);
     }
+    // LeakyReLU as compare + select (torch's x > 0 ? x : x * slope), dropout keep as one unsigned compare per element
+    // (common.cuh); the 2-bit derivative code (bit 0: derivative 0, bit 1: negative side) is OR-ed in under the very
+    // predicates those compares produce: 2 instructions per element where `v == 0` / `v < 0` tests on the result cost 6
+    // (the epilogue is issue-bound: profiles/r02_gemm_experiments.md).  With dropout on, bit 0 = "dropped"; a kept element
+    // whose pre-activation is exactly 0 decodes as the positive side (measure zero).  Without dropout bit 0 = (v == 0).
+    if (p.thresh) {
+      const uint32_t quarter_n = (uint32_t)(p.cols_b + 3) >> 2, limit = drop_limit(p.thresh);
+      const uint32_t grow = (uint32_t)(row + p.row0);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], v[j] * p.slope);
-    if (p.thresh && !(p.dbg & 2)) {
-      const uint32_t half_n = (uint32_t)(p.cols_b + 1) >> 1;
+      for (int q = 0; q < 4; ++q) {
+        const DropBits d = dropout_quad_bits(p.seed, grow, quarter_n, ((uint32_t)col >> 2) + q);
 #pragma unroll
-      for (int j = 0; j < 16; j += 2) {
-        const uint32_t bits = dropout_pair_bits(p.seed, (uint32_t)(row + p.row0), half_n, (uint32_t)(col + j) >> 1);
-        v[j] = (bits & 0xffffu) >= p.thresh ? v[j] * p.keep_scale : 0.f;
-        v[j + 1] = (bits >> 16) >= p.thresh ? v[j + 1] * p.keep_scale : 0.f;
+        for (int e = 0; e < 4; ++e) {
+          const int j = 4 * q + e;
+          const uint32_t w = e < 2 ? d.a : d.b;
+          const bool keep = ((e & 1) ? w : (w << 16)) > limit;
+          const bool neg = v[j] < 0.f;
+          const float a = neg ? v[j] * p.slope : v[j];
+          v[j] = keep ? a * p.keep_scale : 0.f;
+          if (!keep) code |= 1u << (2 * j);
+          if (neg) code |= 2u << (2 * j);
+        }
       }
-    }
-    if (!(p.dbg & 4)) {
+    } else {
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
+        const bool neg = v[j] < 0.f;
+        v[j] = neg ? v[j] * p.slope : v[j];
         if (v[j] == 0.f) code |= 1u << (2 * j);
-        if (v[j] < 0.f) code |= 2u << (2 * j);
+        if (neg) code |= 2u << (2 * j);
       }
     }
     __nv_bfloat16* oh = p.out_hi + row * p.out_pitch + col;
     __nv_bfloat16* ol = p.out_lo + row * p.out_pitch + col;
-    if (p.dbg & 1) {
-      float acc = 0.f;
-#pragma unroll
-      for (int j = 0; j < 16; ++j) acc += v[j];
-      if (acc == 123.456f) oh[0] = __float2bfloat16_rn(acc);
-    } else {
-      store_planes16(v, oh, ol, col, p.out_pitch);
-    }
+    store_planes16(v, oh, ol, col, p.out_pitch);
   } else {  // EPI_PLANES_BWD: gz = g * act'(h), derivative class from the saved 2-bit code
     const float dpos = p.keep_scale, dneg = p.slope * p.keep_scale;
     const float dzero = p.thresh ? 0.f : p.slope;
