@@ -177,17 +177,21 @@ __device__ __forceinline__ void epilogue_f32_staged(const GemmParams& p, const u
   // accumulate (the discriminator's input gradient added into its window of g_static): all 16 loads are issued before
   // the first store -- interleaved `*q = *q + val` serialises 16 load -> store round trips per warp (the compiler must
   // assume the store aliases the next load): 31.6 us per launch against a 6 us HBM floor (profiles/r02_gemm_per_launch.md)
-  float old[16];
-  if (p.accumulate) {
+  // (two halves of 8: 16 live loads on top of the tile cost spills under the 96-register cap)
 #pragma unroll
-    for (int i = 0; i < 16; ++i)
-      old[i] = (col_ok && row0 + 2 * i + hr < p.rows_a) ? __ldcg(q0 + (int64_t)(2 * i) * p.ldc) : 0.f;
-  }
+  for (int h = 0; h < 2; ++h) {
+    float old[8];
+    if (p.accumulate) {
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const int rr = 2 * i + hr;
-    const float val = scr[rr * 16 + 4 * ((j >> 2) ^ ((rr >> 1) & 3)) + (j & 3)];
-    if (col_ok && row0 + rr < p.rows_a) q0[(int64_t)(2 * i) * p.ldc] = p.accumulate ? old[i] + val : val;
+      for (int i = 0; i < 8; ++i)
+        old[i] = (col_ok && row0 + 2 * (8 * h + i) + hr < p.rows_a) ? __ldcg(q0 + (int64_t)(2 * (8 * h + i)) * p.ldc) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int rr = 2 * (8 * h + i) + hr;
+      const float val = scr[rr * 16 + 4 * ((j >> 2) ^ ((rr >> 1) & 3)) + (j & 3)];
+      if (col_ok && row0 + rr < p.rows_a) q0[(int64_t)(2 * (8 * h + i)) * p.ldc] = p.accumulate ? old[i] + val : val;
+    }
   }
   __syncwarp();
 }
@@ -521,30 +525,54 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
       ptx::mbar_wait(tfull0 + 8 * acc, aph);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256;
-      uint32_t code_out[4];
-#pragma unroll
-      for (int ci = 0; ci < 2; ++ci) {
-        const int c = cbeg + 32 * ci;
-        code_out[2 * ci] = code_out[2 * ci + 1] = 0u;
-        if (c < cend && !(p.dbg & 8)) {
-          uint32_t r0[16], r1[16];
-          const bool two = c + 32 <= cend;
-          ptx::tmem_ld16(taddr + c, r0);
-          if (two) ptx::tmem_ld16(taddr + c + 16, r1);
+      // The warp's span is up to four 16-column chunks.  The TMEM load of chunk k+1 is in flight while chunk k goes
+      // through the element-wise epilogue (two register sets, alternating; tcgen05.wait::ld before the set is read):
+      // with load -> wait -> compute about two of the four warps of a scheduler sat on the TMEM load at any time
+      // (ncu: long scoreboard 1.9 per issue, issue slots 50 % busy on the discriminator's forward launches).
+      uint32_t code_out[4] = {0u, 0u, 0u, 0u};
+      const int nck = (p.dbg & 8) ? 0 : (cend - cbeg) >> 4;
+      // (a macro, not a lambda: k must stay a literal so that codes[] / code_out[] live in registers)
+#define run_chunk(r, k)                                                                                          \
+  do {                                                                                                           \
+    const int c = cbeg + 16 * (k);                                                                               \
+    if (EPI == EPI_F32 && stage_scr != nullptr) { /* whole warp takes part; rows beyond rows_a masked at the store */ \
+      if (col0 + c < p.cols_b) epilogue_f32_staged(p, r, row - lane, lane, col0 + c, z, bias_s, stage_scr);      \
+    } else if (row_ok && col0 + c < p.cols_b) {                                                                  \
+      code_out[k] = epilogue_chunk16<EPI>(p, r, row, col0 + c, z, bias_s, codes[k]);                             \
+    }                                                                                                            \
+  } while (0)
+      if (EPI == EPI_F32) {
+        // fp32 outputs: one chunk at a time (the staged store path needs the registers a second set would take:
+        // 196 bytes of spills under the 96-register cap of a 576-thread block)
+        uint32_t ra[16];
+        if (nck > 0) { ptx::tmem_ld16(taddr + cbeg, ra); ptx::tmem_ld_wait(); run_chunk(ra, 0); }
+        if (nck > 1) { ptx::tmem_ld16(taddr + cbeg + 16, ra); ptx::tmem_ld_wait(); run_chunk(ra, 1); }
+        if (nck > 2) { ptx::tmem_ld16(taddr + cbeg + 32, ra); ptx::tmem_ld_wait(); run_chunk(ra, 2); }
+        if (nck > 3) { ptx::tmem_ld16(taddr + cbeg + 48, ra); ptx::tmem_ld_wait(); run_chunk(ra, 3); }
+      } else {
+        uint32_t ra[16], rb[16];
+        if (nck > 0) {
+          ptx::tmem_ld16(taddr + cbeg, ra);
           ptx::tmem_ld_wait();
-          if (EPI == EPI_F32 && stage_scr != nullptr) {
-            // whole warp takes part (rows beyond rows_a are masked at the store)
-            if (col0 + c < p.cols_b) epilogue_f32_staged(p, r0, row - lane, lane, col0 + c, z, bias_s, stage_scr);
-            if (two && col0 + c + 16 < p.cols_b)
-              epilogue_f32_staged(p, r1, row - lane, lane, col0 + c + 16, z, bias_s, stage_scr);
-          } else if (row_ok) {
-            if (col0 + c < p.cols_b)
-              code_out[2 * ci] = epilogue_chunk16<EPI>(p, r0, row, col0 + c, z, bias_s, codes[2 * ci]);
-            if (two && col0 + c + 16 < p.cols_b)
-              code_out[2 * ci + 1] = epilogue_chunk16<EPI>(p, r1, row, col0 + c + 16, z, bias_s, codes[2 * ci + 1]);
-          }
+          if (nck > 1) ptx::tmem_ld16(taddr + cbeg + 16, rb);
+          run_chunk(ra, 0);
+        }
+        if (nck > 1) {
+          ptx::tmem_ld_wait();
+          if (nck > 2) ptx::tmem_ld16(taddr + cbeg + 32, ra);
+          run_chunk(rb, 1);
+        }
+        if (nck > 2) {
+          ptx::tmem_ld_wait();
+          if (nck > 3) ptx::tmem_ld16(taddr + cbeg + 48, rb);
+          run_chunk(ra, 2);
+        }
+        if (nck > 3) {
+          ptx::tmem_ld_wait();
+          run_chunk(rb, 3);
         }
       }
+#undef run_chunk
       if (EPI == EPI_PLANES_FWD && p.code != nullptr && row_ok) {
         uint32_t* cp = p.code + row * p.code_pitch + ((col0 + cbeg) >> 4);
         if (cw == 64 && (p.code_pitch & 3) == 0) {
@@ -773,25 +801,46 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant
       ptx::mbar_wait(tfull0 + 8 * acc, aph);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256;
-      uint32_t code_out[4];
-#pragma unroll
-      for (int ci = 0; ci < 2; ++ci) {
-        const int c = cbeg + 32 * ci;
-        code_out[2 * ci] = code_out[2 * ci + 1] = 0u;
-        if (c < cend) {
-          uint32_t r0[16], r1[16];
-          const bool two = c + 32 <= cend;
-          ptx::tmem_ld16(taddr + c, r0);
-          if (two) ptx::tmem_ld16(taddr + c + 16, r1);
+      // TMEM load of chunk k+1 in flight under the epilogue of chunk k (see gemm_bf16x3_kernel)
+      uint32_t code_out[4] = {0u, 0u, 0u, 0u};
+      const int nck = (cend - cbeg) >> 4;
+#define run_chunk(r, k)                                                                                          \
+  do {                                                                                                           \
+    const int c = cbeg + 16 * (k);                                                                               \
+    if (row_ok && col0 + c < p.cols_b) code_out[k] = epilogue_chunk16<EPI>(p, r, row, col0 + c, 0, bias_s, codes[k]); \
+  } while (0)
+      if (EPI == EPI_F32) {
+        // fp32 outputs: one chunk at a time (the staged store path needs the registers a second set would take:
+        // 196 bytes of spills under the 96-register cap of a 576-thread block)
+        uint32_t ra[16];
+        if (nck > 0) { ptx::tmem_ld16(taddr + cbeg, ra); ptx::tmem_ld_wait(); run_chunk(ra, 0); }
+        if (nck > 1) { ptx::tmem_ld16(taddr + cbeg + 16, ra); ptx::tmem_ld_wait(); run_chunk(ra, 1); }
+        if (nck > 2) { ptx::tmem_ld16(taddr + cbeg + 32, ra); ptx::tmem_ld_wait(); run_chunk(ra, 2); }
+        if (nck > 3) { ptx::tmem_ld16(taddr + cbeg + 48, ra); ptx::tmem_ld_wait(); run_chunk(ra, 3); }
+      } else {
+        uint32_t ra[16], rb[16];
+        if (nck > 0) {
+          ptx::tmem_ld16(taddr + cbeg, ra);
           ptx::tmem_ld_wait();
-          if (row_ok) {
-            if (col0 + c < p.cols_b)
-              code_out[2 * ci] = epilogue_chunk16<EPI>(p, r0, row, col0 + c, 0, bias_s, codes[2 * ci]);
-            if (two && col0 + c + 16 < p.cols_b)
-              code_out[2 * ci + 1] = epilogue_chunk16<EPI>(p, r1, row, col0 + c + 16, 0, bias_s, codes[2 * ci + 1]);
-          }
+          if (nck > 1) ptx::tmem_ld16(taddr + cbeg + 16, rb);
+          run_chunk(ra, 0);
+        }
+        if (nck > 1) {
+          ptx::tmem_ld_wait();
+          if (nck > 2) ptx::tmem_ld16(taddr + cbeg + 32, ra);
+          run_chunk(rb, 1);
+        }
+        if (nck > 2) {
+          ptx::tmem_ld_wait();
+          if (nck > 3) ptx::tmem_ld16(taddr + cbeg + 48, rb);
+          run_chunk(ra, 2);
+        }
+        if (nck > 3) {
+          ptx::tmem_ld_wait();
+          run_chunk(rb, 3);
         }
       }
+#undef run_chunk
       if (EPI == EPI_PLANES_FWD && p.code != nullptr && row_ok) {
         uint32_t* cp = p.code + row * p.code_pitch + ((col0 + cbeg) >> 4);
         if (cw == 64 && (p.code_pitch & 3) == 0) {
@@ -1588,32 +1637,66 @@ struct ReduceList {
   int64_t off[REDUCE_MAX_JOBS + 1];
 };
 
-__global__ void multi_reduce_kernel(ReduceList rl, int accumulate) {
+// out[j][e] = sum_z partial[j][z][e] for a list of (partial, out) pairs: the split-K reduction of a model's weight
+// gradients in one launch.  A block covers 32 float4 columns; its 8 warps take the splits z = w, w+8, ... (all loads of a
+// warp independent and in flight together), the per-warp sums meet in shared memory and are added in warp order -- a fixed
+// summation order, so the result is deterministic.  (The first version walked the splits sequentially per thread: 24 us for
+// 42 MB of L2-resident partials at cfg2, 3.8 % issue utilisation -- profiles/r02_launches.md.)
+constexpr int MR_WARPS = 8;
+__global__ void __launch_bounds__(32 * MR_WARPS) multi_reduce_kernel(ReduceList rl, int accumulate) {
+  __shared__ float4 part_s[MR_WARPS][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t total4 = rl.off[rl.n];                        // in units of 4 elements
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4;
-       i += (int64_t)gridDim.x * blockDim.x) {
+  for (int64_t base = (int64_t)blockIdx.x * 32; base < total4; base += (int64_t)gridDim.x * 32) {
+    const int64_t i = base + lane;
     int j = 0;
-    while (j + 1 < rl.n && i >= rl.off[j + 1]) ++j;
-    const int64_t e = (i - rl.off[j]) * 4, n = rl.len[j];
-    const float* part = rl.partial[j];
-    float* out = rl.out[j];
-    if (e + 3 < n && (n & 3) == 0) {
-      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    int64_t e = 0, n = 0;
+    bool vec = false;
+    if (i < total4) {
+      while (j + 1 < rl.n && i >= rl.off[j + 1]) ++j;
+      e = (i - rl.off[j]) * 4;
+      n = rl.len[j];
+      vec = e + 3 < n && (n & 3) == 0;
+      const float* part = rl.partial[j];
+      const int splits = rl.splits[j];
+      if (vec) {
 #pragma unroll 4
-      for (int z = 0; z < rl.splits[j]; ++z) {
-        const float4 v = *reinterpret_cast<const float4*>(part + (int64_t)z * n + e);
-        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-      }
-      float4* o = reinterpret_cast<float4*>(out + e);
-      if (accumulate) { const float4 c = *o; s.x += c.x; s.y += c.y; s.z += c.z; s.w += c.w; }
-      *o = s;
-    } else {
-      for (int64_t q = e; q < e + 4 && q < n; ++q) {
-        float s = 0.f;
-        for (int z = 0; z < rl.splits[j]; ++z) s += part[(int64_t)z * n + q];
-        out[q] = accumulate ? out[q] + s : s;
+        for (int z = w; z < splits; z += MR_WARPS) {
+          const float4 v = __ldcg(reinterpret_cast<const float4*>(part + (int64_t)z * n + e));
+          s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+      } else {
+        for (int z = w; z < splits; z += MR_WARPS) {
+          const float* pz = part + (int64_t)z * n + e;
+          if (e < n) s.x += pz[0];
+          if (e + 1 < n) s.y += pz[1];
+          if (e + 2 < n) s.z += pz[2];
+          if (e + 3 < n) s.w += pz[3];
+        }
       }
     }
+    part_s[w][lane] = s;
+    __syncthreads();
+    if (w == 0 && i < total4) {
+      float4 t = part_s[0][lane];
+#pragma unroll
+      for (int k = 1; k < MR_WARPS; ++k) {
+        const float4 v = part_s[k][lane];
+        t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+      }
+      float* out = rl.out[j];
+      if (vec) {
+        float4* o = reinterpret_cast<float4*>(out + e);
+        if (accumulate) { const float4 c = *o; t.x += c.x; t.y += c.y; t.z += c.z; t.w += c.w; }
+        *o = t;
+      } else {
+        const float tv[4] = {t.x, t.y, t.z, t.w};
+        for (int q = 0; q < 4; ++q)
+          if (e + q < n) out[e + q] = accumulate ? out[e + q] + tv[q] : tv[q];
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -1621,9 +1704,9 @@ static int flush_reduce(ReduceList& rl, int accumulate, cudaStream_t st) {
   if (rl.n == 0) return GANTTS_OK;
   rl.off[0] = 0;
   for (int j = 0; j < rl.n; ++j) rl.off[j + 1] = rl.off[j] + (rl.len[j] + 3) / 4;
-  int nb = (int)((rl.off[rl.n] + 255) / 256);
-  if (nb > num_sms() * 8) nb = num_sms() * 8;
-  multi_reduce_kernel<<<nb, 256, 0, st>>>(rl, accumulate);
+  int64_t nb = (rl.off[rl.n] + 31) / 32;
+  if (nb > (int64_t)num_sms() * 16) nb = (int64_t)num_sms() * 16;
+  multi_reduce_kernel<<<(unsigned)nb, 32 * MR_WARPS, 0, st>>>(rl, accumulate);
   GANTTS_LAUNCH_CHECK("multi_reduce_kernel");
   rl.n = 0;
   return GANTTS_OK;
