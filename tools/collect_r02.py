@@ -41,7 +41,8 @@ def top_kernel():
     tot, n, us = 0.0, 0, 0.0
     for r in rows[2:]:
         nm = r[i_name]
-        kmaj = ("gemm_pair_kernel" in nm or "gemm_bf16x3_kernel<(bool)0" in nm or "gemm_bf16x3_kernel<false" in nm)
+        kmaj = ("gemm_pair_kernel" in nm or "gemm_bf16x3_kernel<(bool)0" in nm or "gemm_bf16x3_kernel<false" in nm or
+                "gemm_bf16x3_kernel<0," in nm)
         if not kmaj:
             continue
         tot += float(r[i_rd].replace(",", "")) * scale.get(u[i_rd], 1.0) + float(r[i_wr].replace(",", "")) * scale.get(u[i_wr], 1.0)
