@@ -430,14 +430,27 @@ def run_b200_arm(args):
         per, total = [], 0.0
         while True:
             barrier()
+            t_host = time.perf_counter()
             e0.record()
             loop(args.steps)
             e1.record()
+            t_host = time.perf_counter() - t_host
             barrier()
-            ms = max_over_ranks(e0.elapsed_time(e1))
+            local_ms = e0.elapsed_time(e1)
+            ms = max_over_ranks(local_ms)
+            if os.environ.get("GANTTS_B200_BENCH_TRACE"):
+                sys.stderr.write("[trace] rank %d repeat %d: device %.3f ms/step (max over ranks %.3f), host enqueue %.3f ms/step\n"
+                                 % (rank, len(per), local_ms / args.steps, ms / args.steps, t_host / args.steps * 1e3))
+                sys.stderr.flush()
             per.append(ms / args.steps)
             total += ms
-            if (len(per) >= 3 and total >= MIN_TIMED_SECONDS * 1e3) or len(per) >= MAX_REPEATS:
+            enough = len(per) >= 3 and total >= MIN_TIMED_SECONDS * 1e3
+            # a transient on the box (one 2-GPU run of round 2 saw repeats of 1.2, 8 and 16 ms/step, none of the following
+            # runs did): while the repeats disagree by more than 30 %, keep measuring (bounded) so the median is not
+            # decided by three samples
+            if enough and max(per) > 1.3 * min(per) and len(per) < 11 and total < 8e3:
+                enough = False
+            if enough or len(per) >= MAX_REPEATS:
                 break
         return float(np.median(per)), per
 
@@ -627,7 +640,8 @@ def run_b200_arm(args):
             "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 (GEMMs: bf16x3 split on tcgen05, fp32 accumulate)" if args.engine == "tc" else "f32",
             "data": "synthetic", "config": workload_config(w, args.engine, args), "clocks": clocks,
-            "timed_repeats": {"n": len(repeats), "ms_per_step_min": min(repeats), "ms_per_step_max": max(repeats)},
+            "timed_repeats": {"n": len(repeats), "ms_per_step_min": min(repeats), "ms_per_step_max": max(repeats),
+                              "ms_per_step_all": [round(v, 4) for v in repeats]},
             "e2e": {"value": frames_per_step / (e2e_ms * 1e-3), "unit": "frames/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16, "repeats": len(e2e_repeats),
                     "how": "pinned host x,y -> double-buffered cudaMemcpyAsync on a copy stream -> one step through the "
