@@ -141,6 +141,37 @@ def test_gan_trainer_cfg2_full_size_train_mode_injected_masks(dev):
     assert max(errs.values()) < 1e-4, errs
 
 
+@pytest.mark.parametrize("mse_w,mge_w", [(0.0, 1.0), (1.0, 0.0)])
+def test_fused_step_without_discriminator(dev, mse_w, mge_w):
+    """BASELINE configs[3] (TTS acoustic MLP + MGE loss, no adversarial term) and the MSE-only objective of configs[0] on the
+    fused entry point: w_d = 0 -- no discriminator forward/backward/update, loss_g = mse_w MSE + mge_w MGE -- train mode with
+    the injected generator mask, against the oracle; the discriminator's weights must come out untouched."""
+    from gantts_b200 import step as gstep, fused, ops, _lib
+    lib = _lib.load()
+    B, T, p = 4, 250, 0.5
+    M = B * T
+    mg, md, state = cfg2_models(p, dev)
+    d_before = [q.detach().clone() for q in md.parameters()]
+    lens = ragged_lengths(B, T, 21)
+    x, y = make_batch(B, T, 425, 187, lens, 123)
+    fs = fused.FusedGanStep(mg, md, gstep.TTS_ACOUSTIC, B, T, w_d=0.0, mse_w=mse_w, mge_w=mge_w, seed=99)
+    fs.step(x.to(dev), y.to(dev), torch.LongTensor(lens).to(dev), frames=sum(lens))
+    got = fs.loss_dict()
+    masks = {"g": [m.cpu() for m in ops.mlp_dropout_masks(M, [512] * 3, p, lib.gantts_gan_step_seed(fs.last_seed, 0), dev)]}
+    R = torch.from_numpy(nnp.unit_variance_mlpg_matrix(WINDOWS, T))
+    ref, yh_ref, ys_ref = gp.gan_step_mlp(state, x, y, lens, R, TTS_HP, w_d=0.0, mse_w=mse_w, mge_w=mge_w, dropout_g=p,
+                                          dropout_d=p, training=True, masks=masks)
+    errs = loss_errors(got, ref, ("loss_mge", "loss_mse", "loss_g", "g_grad_norm"))
+    errs["y_hat"] = rel_err(npy(fs.y_hat), yh_ref.numpy())
+    errs["y_hat_static"] = rel_err(npy(fs.y_hat_static), ys_ref.numpy())
+    assert max(errs.values()) < 1e-4, errs
+    assert got["loss_d"] == 0.0 and got["loss_adv"] == 0.0 and got["frames"] == float(sum(lens))
+    for a, b in zip(d_before, md.parameters()):
+        assert torch.equal(a, b.detach())
+    dW = np.abs(npy(mg.layers[1].weight) - state.g[1][0].detach().numpy())
+    assert np.median(dW) < 1e-6 and dW.max() <= 0.0201
+
+
 def test_cfg1_highway_step_full_size(dev):
     """BASELINE cfg1: In2OutHighwayNet(177 -> 177, static 59, 3 x 512, dropout 0.5), B=8 x T=200, no discriminator
     (w_d = 0), MSE + MGE, train mode with injected masks; two consecutive steps incl. post-step weights."""

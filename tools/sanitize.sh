@@ -19,3 +19,14 @@ run() {   # tool, selection, seconds
 run memcheck "$MEM" ${SAN_SECONDS:-420}
 run racecheck "$RACE" ${SAN_SECONDS:-420}
 run initcheck "$MEM" ${SAN_SECONDS:-420}
+# second tier (the first tier takes ~6 s per tool): the tcgen05 GEMM / fused-step path at golden sizes, the SRU scan, the
+# MLPG substitution kernels at several lengths, the LSTM backward -- memcheck only (racecheck does not model the async proxy
+# / mbarrier hand-offs of the TMA + tcgen05 kernels)
+MEM2='test_gan_step_golden or test_fused_gan_step_small_vs_oracle or test_mlp_model_golden or test_sru_layer_vs_port or test_mlpg_sizes_vs_f64_banded or (test_lstm_fwd_bwd_vs_torch_cpu) or test_mlp_stack_sigmoid_single_output'
+run2() {
+  timeout $2 compute-sanitizer --tool memcheck --error-exitcode 7 --print-limit 20 \
+      python -m pytest tests/test_gpu_parity.py -m gpu -q -x --timeout $2 -k "$1" > gpurun_out/sanitize_memcheck2.log 2>&1
+  echo "== memcheck tier 2 exit=$? (124 = time limit)" | tee -a gpurun_out/sanitize_summary.log
+  grep -E "ERROR SUMMARY|passed|failed|Invalid __" gpurun_out/sanitize_memcheck2.log | tail -6 | tee -a gpurun_out/sanitize_summary.log
+}
+if [ "${SAN_TIER2:-1}" = "1" ]; then run2 "$MEM2" ${SAN_SECONDS2:-600}; fi
