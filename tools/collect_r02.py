@@ -74,6 +74,14 @@ def scaling(b):
             lines.append("| %d | %.4f | %.2f M | %.2f (%.0f %%) | %.3f | %s | %s_bench%s.json |" % (
                 n, d["ms_per_step"], d["value"] / 1e6, d["value"] / base["value"], 100.0 * d["value"] / base["value"] / n,
                 d["e2e"]["ms_per_step"], ("%.0f" % ar["us_per_step_pair"]) if ar else "-", TAG, k))
+    c5, c5n = last_json(os.path.join(GO, "bench_%s_cfg5.json" % TAG)), last_json(os.path.join(GO, "bench_%s_cfg5_n8.json" % TAG))
+    if c5 and c5n:
+        json.dump(c5n, open(os.path.join(OUT, "%s_bench_cfg5_n8.json" % TAG), "w"), indent=1)
+        lines += ["", "cfg5 (BASELINE configs[4]: TTS acoustic LSTMRNN + GAN + MGE, B=64 x T=1500 per GPU, `GanTrainer`, gradient all-reduce of "
+                  "the 17 M-parameter generator and the discriminator per step): 1 GPU %.1f ms/step = %.1f k frames/s (%s_bench_cfg5.json); "
+                  "**8 GPUs %.1f ms/step = %.2f M frames/s = %.2fx (%.0f %%)** (%s_bench_cfg5_n8.json)." % (
+                      c5["ms_per_step"], c5["value"] / 1e3, TAG, c5n["ms_per_step"], c5n["value"] / 1e6, c5n["value"] / c5["value"],
+                      100.0 * c5n["value"] / c5["value"] / 8, TAG)]
     open(os.path.join(OUT, "%s_scaling.md" % TAG), "w").write("\n".join(lines) + "\n")
 
 
