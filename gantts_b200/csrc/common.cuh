@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/gantts_b200.h"
@@ -43,6 +44,40 @@ void prof_begin(int kind, double work, cudaStream_t st);   // work: algorithmic 
 void prof_end(cudaStream_t st);
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// Programmatic dependent launch for the small streaming kernels of the fused step (the tcgen05 GEMMs already use it):
+// a kernel launched through GANTTS_PDL_LAUNCH may become resident while its predecessor in the stream is still in its last
+// wave; pdl_entry() at the top of the kernel (a) lets ITS successor do the same and (b) blocks until every prerequisite
+// grid has completed and its writes are visible -- nothing the predecessor produced is touched before that.  Without the
+// launch attribute (plain <<<>>> launches, the modular ops) both instructions are no-ops.  GANTTS_B200_PDL=0 disables.
+__device__ __forceinline__ void pdl_entry() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+inline int pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GANTTS_B200_PDL");
+    v = e ? atoi(e) : 1;
+  }
+  return v;
+}
+template <typename... KA, typename... A>
+static inline void pdl_launch(void (*kern)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, static_cast<KA>(args)...);       // errors surface through GANTTS_LAUNCH_CHECK
+}
+#define GANTTS_PDL_LAUNCH(kern, grid, block, smem, st, ...) \
+  ::gantts::pdl_launch(kern, dim3(grid), dim3(block), (size_t)(smem), st, __VA_ARGS__)
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -63,6 +63,7 @@ __global__ void gather_cols_list_kernel(const float* __restrict__ in, int64_t in
 __global__ void gather_planes_kernel(const float* __restrict__ a, int64_t a_rs, ColList ca, int64_t rows_a,
                                      const float* __restrict__ b, int64_t b_rs, ColList cb, int64_t rows_b,
                                      __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int64_t pitch) {
+  pdl_entry();
   __shared__ int sa[GANTTS_MAX_COLS], sb[GANTTS_MAX_COLS];
   for (int i = threadIdx.x; i < ca.n; i += blockDim.x) sa[i] = ca.c[i];
   for (int i = threadIdx.x; i < cb.n; i += blockDim.x) sb[i] = cb.c[i];
@@ -102,6 +103,7 @@ __global__ void scatter_cols_list_add_kernel(const float* __restrict__ go, int64
 // single-process use; a data-parallel caller passes 1 / (GLOBAL number of valid frames).
 __global__ void set_scales_kernel(float* scal, float inv_frames, float adv_w, float mge_w, float mse_w,
                                   int zero_norms, const int64_t* __restrict__ lengths, int B, int T) {
+  pdl_entry();
   if (threadIdx.x == 0) {
     if (zero_norms) scal[S_DSUMSQ] = scal[S_GSUMSQ] = 0.f;
     if (!(inv_frames > 0.f)) {
@@ -135,6 +137,7 @@ struct RedCounts {
 __global__ void __launch_bounds__(RED_THREADS)
 bce_fwd_bwd_kernel(const float* __restrict__ Dv, const float* __restrict__ mask, int64_t M, int kind0, int kind1,
                    int nbh, const float* __restrict__ scale, float* __restrict__ gD, RedWs* ws0, RedWs* ws1) {
+  pdl_entry();
   __shared__ float sm[RED_NV * 32];
   const int half = blockIdx.x >= nbh ? 1 : 0;
   const int kind = half ? kind1 : kind0;
@@ -168,6 +171,7 @@ __global__ void __launch_bounds__(RED_THREADS)
 sse_fwd_bwd_kernel(const float* __restrict__ a, int64_t a_rs, const float* __restrict__ b, int64_t b_rs,
                    const float* __restrict__ mask, int64_t rows, int D, const float* __restrict__ scale,
                    float* __restrict__ ga, int64_t ga_rs, RedWs* ws, ColList bmap) {
+  pdl_entry();
   __shared__ float sm[RED_NV * 32];
   __shared__ int sc[GANTTS_MAX_COLS];
   for (int i = threadIdx.x; i < bmap.n; i += RED_THREADS) sc[i] = bmap.c[i];
@@ -202,6 +206,7 @@ sse_fwd_bwd_kernel(const float* __restrict__ a, int64_t a_rs, const float* __res
 __global__ void __launch_bounds__(OPT_THREADS)
 clip_adagrad_partials_kernel(TensorList tl, const float* __restrict__ partial, int npartial, float* __restrict__ sumsq_out,
                              float max_norm, float lr, float wd, float eps) {
+  pdl_entry();
   __shared__ float sm[32];
   __shared__ float total_s;
   float v[1] = {0.f};
@@ -235,6 +240,7 @@ clip_adagrad_partials_kernel(TensorList tl, const float* __restrict__ partial, i
 __global__ void __launch_bounds__(RED_THREADS)
 finalize_losses_kernel(const float* scal, float* losses, const RedWs* red, RedCounts cnt, float adv_w, float mge_w,
                        float mse_w, int has_d) {
+  pdl_entry();
   __shared__ float sm[RED_NV * 32];
   __shared__ float tot[R_COUNT][RED_NV];
   for (int sl = 0; sl < R_COUNT; ++sl) {
@@ -375,7 +381,7 @@ static inline int sse_blocks(int64_t rows, int D) { return grid_for(rows * D, RE
 static int launch_bce(const float* Dv, const float* mask, int64_t M, int halves, int kind0, int kind1, const float* scale,
                       float* gD, RedWs* ws0, RedWs* ws1, cudaStream_t st) {
   const int nbh = bce_blocks(M);
-  bce_fwd_bwd_kernel<<<nbh * halves, RED_THREADS, 0, st>>>(Dv, mask, M, kind0, kind1, nbh, scale, gD, ws0, ws1);
+  GANTTS_PDL_LAUNCH((bce_fwd_bwd_kernel), nbh * halves, RED_THREADS, 0, st, Dv, mask, M, kind0, kind1, nbh, scale, gD, ws0, ws1);
   GANTTS_LAUNCH_CHECK("bce_fwd_bwd_kernel");
   return GANTTS_OK;
 }
@@ -385,7 +391,7 @@ static int launch_sse(const float* a, int64_t a_rs, const float* b, int64_t b_rs
                       const ColList* bmap = nullptr) {
   ColList none;
   none.n = 0;
-  sse_fwd_bwd_kernel<<<sse_blocks(rows, D), RED_THREADS, 0, st>>>(a, a_rs, b, b_rs, mask, rows, D, scale, ga, ga_rs, ws,
+  GANTTS_PDL_LAUNCH((sse_fwd_bwd_kernel), sse_blocks(rows, D), RED_THREADS, 0, st, a, a_rs, b, b_rs, mask, rows, D, scale, ga, ga_rs, ws,
                                                                  bmap ? *bmap : none);
   GANTTS_LAUNCH_CHECK("sse_fwd_bwd_kernel");
   return GANTTS_OK;
@@ -398,9 +404,9 @@ static int clip_adagrad_model(const ParamList& pl, float* partial, float* sumsq_
   int rc = fill(tl, pl.p, pl.g, pl.s, nullptr, pl.sizes, 0, pl.n);
   if (rc) return rc;
   const int nb = blocks_for(tl.off[tl.n], OPT_MAX_BLOCKS);
-  sumsq_partial_kernel<<<nb, OPT_THREADS, 0, st>>>(tl, partial);
+  GANTTS_PDL_LAUNCH((sumsq_partial_kernel), nb, OPT_THREADS, 0, st, tl, partial);
   GANTTS_LAUNCH_CHECK("sumsq_partial_kernel");
-  clip_adagrad_partials_kernel<<<nb, OPT_THREADS, 0, st>>>(tl, partial, nb, sumsq_out, max_norm, lr, wd, eps);
+  GANTTS_PDL_LAUNCH((clip_adagrad_partials_kernel), nb, OPT_THREADS, 0, st, tl, partial, nb, sumsq_out, max_norm, lr, wd, eps);
   GANTTS_LAUNCH_CHECK("clip_adagrad_partials_kernel");
   return GANTTS_OK;
 }
@@ -503,7 +509,7 @@ extern "C" int gantts_gan_step(const gantts_gan_step_t* c, int phases, const flo
     g.dropout_p = 0.f;
     d.dropout_p = 0.f;
     if ((rc = gantts_sequence_mask(lengths_dev, L.mask, c->B, c->T, stream))) return rc;
-    set_scales_kernel<<<1, 32, 0, st>>>(L.scal, inv_frames, has_adv ? c->adv_w : 0.f, c->mge_w, c->mse_w, 1, lengths_dev, c->B, c->T);
+    GANTTS_PDL_LAUNCH((set_scales_kernel), 1, 32, 0, st, L.scal, inv_frames, has_adv ? c->adv_w : 0.f, c->mge_w, c->mse_w, 1, lengths_dev, c->B, c->T);
     GANTTS_LAUNCH_CHECK("set_scales_kernel");
     if (has_d) {      // (the eval path keeps the two-step gather of the discriminator input)
       gather_cols_list_kernel<<<blocks_1d(M * nS, 1024), 256, 0, st>>>(y, d_out, L.y_static, nS, static_cols, M);
@@ -543,7 +549,7 @@ extern "C" int gantts_gan_step(const gantts_gan_step_t* c, int phases, const flo
       return rc;
     cnt.n[R_MGE] = sse_blocks(M, nS);
     cnt.n[R_MSE] = sse_blocks(M, d_out);
-    finalize_losses_kernel<<<1, RED_THREADS, 0, st>>>(L.scal, losses_dev, L.red, cnt, has_adv ? c->adv_w : 0.f, c->mge_w,
+    GANTTS_PDL_LAUNCH((finalize_losses_kernel), 1, RED_THREADS, 0, st, L.scal, losses_dev, L.red, cnt, has_adv ? c->adv_w : 0.f, c->mge_w,
                                                       c->mse_w, has_d ? 1 : 0);
     GANTTS_LAUNCH_CHECK("finalize_losses_kernel");
     return GANTTS_OK;
@@ -553,7 +559,7 @@ extern "C" int gantts_gan_step(const gantts_gan_step_t* c, int phases, const flo
     NvtxRange r1("gantts_gan_step/phase1: G fwd, MLPG, MGE, D fwd+bwd");
     // ---- prologue: mask, scales, y_static (train.py:528-535)
     if ((rc = gantts_sequence_mask(lengths_dev, L.mask, c->B, c->T, stream))) return rc;
-    set_scales_kernel<<<1, 32, 0, st>>>(L.scal, inv_frames, has_adv ? c->adv_w : 0.f, c->mge_w, c->mse_w, 0, lengths_dev, c->B, c->T);
+    GANTTS_PDL_LAUNCH((set_scales_kernel), 1, 32, 0, st, L.scal, inv_frames, has_adv ? c->adv_w : 0.f, c->mge_w, c->mse_w, 0, lengths_dev, c->B, c->T);
     GANTTS_LAUNCH_CHECK("set_scales_kernel");
     if (has_d && cond_w) {      // only the conditioned-discriminator fallback still gathers from y_static
       gather_cols_list_kernel<<<blocks_1d(M * nS, 1024), 256, 0, st>>>(y, d_out, L.y_static, nS, static_cols, M);
@@ -576,7 +582,7 @@ extern "C" int gantts_gan_step(const gantts_gan_step_t* c, int phases, const flo
         // selected columns of y (real) and y_hat_static (fake) straight into the discriminator's input planes
         Planes din;
         if ((rc = mlp_tape_input_planes(&d, 2 * M, L.d_tape, L.d_tape_bytes, &din))) return rc;
-        gather_planes_kernel<<<blocks_1d(2 * M * nA, 1024), 256, 0, st>>>(y, d_out, real_cols, M, y_hat_static, nS,
+        GANTTS_PDL_LAUNCH((gather_planes_kernel), blocks_1d(2 * M * nA, 1024), 256, 0, st, y, d_out, real_cols, M, y_hat_static, nS,
                                                                           adv_cols, M, din.hi, din.lo, din.pitch);
         GANTTS_LAUNCH_CHECK("gather_planes_kernel(real|fake)");
         if ((rc = mlp_fwd_impl(&d, nullptr, 0, 2 * M, L.d_out, 1, L.d_tape, L.d_tape_bytes, stream, true))) return rc;
@@ -630,7 +636,7 @@ extern "C" int gantts_gan_step(const gantts_gan_step_t* c, int phases, const flo
         if ((rc = mlp_tape_input_planes(&d, M, L.d_tape, L.d_tape_bytes, &din))) return rc;
         ColList none;
         none.n = 0;
-        gather_planes_kernel<<<blocks_1d(M * nA, 1024), 256, 0, st>>>(y_hat_static, nS, adv_cols, M, nullptr, 0, none, 0,
+        GANTTS_PDL_LAUNCH((gather_planes_kernel), blocks_1d(M * nA, 1024), 256, 0, st, y_hat_static, nS, adv_cols, M, nullptr, 0, none, 0,
                                                                       din.hi, din.lo, din.pitch);
         GANTTS_LAUNCH_CHECK("gather_planes_kernel(adv)");
         if ((rc = mlp_fwd_impl(&d, nullptr, 0, M, L.d_out, 1, L.d_tape, L.d_tape_bytes, stream, true))) return rc;
@@ -685,7 +691,7 @@ extern "C" int gantts_gan_step(const gantts_gan_step_t* c, int phases, const flo
     if (has_adv) cnt.n[R_ADV] = bce_blocks(M);
     cnt.n[R_MGE] = sse_blocks(M, nS);
     cnt.n[R_MSE] = sse_blocks(M, d_out);
-    finalize_losses_kernel<<<1, RED_THREADS, 0, st>>>(L.scal, losses_dev, L.red, cnt, has_adv ? c->adv_w : 0.f, c->mge_w,
+    GANTTS_PDL_LAUNCH((finalize_losses_kernel), 1, RED_THREADS, 0, st, L.scal, losses_dev, L.red, cnt, has_adv ? c->adv_w : 0.f, c->mge_w,
                                                       c->mse_w, has_d ? 1 : 0);
     GANTTS_LAUNCH_CHECK("finalize_losses_kernel");
   }

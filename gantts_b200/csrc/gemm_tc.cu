@@ -1060,6 +1060,7 @@ gemm_pair_mn_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
 __global__ void split_planes_kernel(const float* __restrict__ src, int64_t rs, int64_t rows, int cols,
                                     __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
                                     int64_t pitch, int transpose) {
+  pdl_entry();
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -1180,7 +1181,7 @@ static int launch_split(const float* src, int64_t rs, int64_t rows, int cols, co
   int nb = (int)((total + 1023) / 1024);
   if (nb > num_sms() * 8) nb = num_sms() * 8;
   if (nb < 1) nb = 1;
-  split_planes_kernel<<<nb, 256, 0, st>>>(src, rs, rows, cols, pl.hi, pl.lo, pl.pitch, transpose);
+  GANTTS_PDL_LAUNCH((split_planes_kernel), nb, 256, 0, st, src, rs, rows, cols, pl.hi, pl.lo, pl.pitch, transpose);
   GANTTS_LAUNCH_CHECK("split_planes_kernel");
   return GANTTS_OK;
 }
@@ -1644,6 +1645,7 @@ struct ReduceList {
 // 42 MB of L2-resident partials at cfg2, 3.8 % issue utilisation -- profiles/r02_launches.md.)
 constexpr int MR_WARPS = 8;
 __global__ void __launch_bounds__(32 * MR_WARPS) multi_reduce_kernel(ReduceList rl, int accumulate) {
+  pdl_entry();
   __shared__ float4 part_s[MR_WARPS][32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t total4 = rl.off[rl.n];                        // in units of 4 elements
@@ -1706,7 +1708,7 @@ static int flush_reduce(ReduceList& rl, int accumulate, cudaStream_t st) {
   for (int j = 0; j < rl.n; ++j) rl.off[j + 1] = rl.off[j] + (rl.len[j] + 3) / 4;
   int64_t nb = (rl.off[rl.n] + 31) / 32;
   if (nb > (int64_t)num_sms() * 16) nb = (int64_t)num_sms() * 16;
-  multi_reduce_kernel<<<(unsigned)nb, 32 * MR_WARPS, 0, st>>>(rl, accumulate);
+  GANTTS_PDL_LAUNCH((multi_reduce_kernel), (unsigned)nb, 32 * MR_WARPS, 0, st, rl, accumulate);
   GANTTS_LAUNCH_CHECK("multi_reduce_kernel");
   rl.n = 0;
   return GANTTS_OK;

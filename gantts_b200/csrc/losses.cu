@@ -16,6 +16,7 @@ struct RedWs {
 
 __global__ void sequence_mask_kernel(const int64_t* __restrict__ lengths, float* __restrict__ mask,
                                      int B, int T) {
+  pdl_entry();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)B * T) return;
   int b = (int)(i / T), t = (int)(i - (int64_t)b * T);
@@ -153,7 +154,7 @@ using namespace gantts;
 extern "C" int gantts_sequence_mask(const int64_t* lengths_dev, float* mask, int B, int T, void* stream) {
   GANTTS_CHECK_ARG(lengths_dev && mask && B >= 1 && T >= 1, "sequence_mask: bad arguments");
   int64_t n = (int64_t)B * T;
-  sequence_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(lengths_dev, mask, B, T);
+  GANTTS_PDL_LAUNCH((sequence_mask_kernel), (unsigned)((n + 255) / 256), 256, 0, as_stream(stream), lengths_dev, mask, B, T);
   GANTTS_LAUNCH_CHECK("sequence_mask_kernel");
   return GANTTS_OK;
 }

@@ -98,6 +98,7 @@ struct WeightSplitList {
 // written with coalesced 64-byte row segments (a per-element kernel scattered 2-byte stores into the
 // transposed planes: 11 us per launch for 3.4 MB of generator weights).  off[] counts tiles per layer.
 __global__ void __launch_bounds__(256) split_weights_kernel(WeightSplitList wl) {
+  pdl_entry();
   __shared__ uint16_t th[32][34], tl[32][34];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   for (int64_t tile = blockIdx.x; tile < wl.off[wl.n]; tile += gridDim.x) {
@@ -256,6 +257,7 @@ __global__ void __launch_bounds__(GEMV_THREADS)
 gemv_fwd_vec_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, int64_t pitch,
                     const float* __restrict__ w, const float* __restrict__ b, float* __restrict__ y, int64_t y_rs,
                     int64_t M, int K, int sigmoid) {
+  pdl_entry();
   const int lane = threadIdx.x & 31;
   float wr[NCH][8];
 #pragma unroll
@@ -317,6 +319,7 @@ gemv_bwd_vec_kernel(const float* __restrict__ gy, int64_t gy_rs, const float* __
                     __nv_bfloat16* __restrict__ ghi, __nv_bfloat16* __restrict__ glo, int64_t gpitch,
                     float* __restrict__ partial, int64_t M, int K, int sigmoid, float dpos, float dneg, float dzero,
                     int want_gw) {
+  pdl_entry();
   __shared__ float gws[GEMV_THREADS / 32][GEMV_MAX_K + 1];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   float wr[NCH][8], gw[NCH][8];
@@ -412,6 +415,7 @@ gemv_bwd_vec_kernel(const float* __restrict__ gy, int64_t gy_rs, const float* __
 __global__ void __launch_bounds__(256)
 gemv_partial_reduce_kernel(const float* __restrict__ partial, int blocks, int K, float* __restrict__ out_w,
                            float* __restrict__ out_b, int accumulate) {
+  pdl_entry();
   __shared__ float sm[8][33];
   const int cl = threadIdx.x & 31, rg = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
@@ -573,7 +577,7 @@ static int gantts::mlp_fwd_impl(const gantts_mlp_t* m, const float* x, int64_t x
     int nb = (int)wl.off[L];
     if (nb > num_sms() * 8) nb = num_sms() * 8;
     if (nb < 1) nb = 1;
-    split_weights_kernel<<<nb, 256, 0, st>>>(wl);
+    GANTTS_PDL_LAUNCH((split_weights_kernel), nb, 256, 0, st, wl);
     GANTTS_LAUNCH_CHECK("split_weights_kernel");
   }
   if (chain_shape_ok(m, CHAIN_FWD)) {
@@ -632,7 +636,7 @@ static int gantts::mlp_fwd_impl(const gantts_mlp_t* m, const float* x, int64_t x
         // single-output last layer: GEMV + sigmoid, one warp per row
         const int Kl = m->dims[l], sg = m->last_act == GANTTS_ACT_SIGMOID;
         if (Kl % 8 == 0 && Kl <= 256)
-          gemv_fwd_vec_kernel<1, 4><<<2 * GEMV_BLOCKS, GEMV_THREADS, 0, st>>>(t.H[l].hi, t.H[l].lo, t.H[l].pitch, m->W[l],
+          GANTTS_PDL_LAUNCH((gemv_fwd_vec_kernel<1, 4>), 2 * GEMV_BLOCKS, GEMV_THREADS, 0, st, t.H[l].hi, t.H[l].lo, t.H[l].pitch, m->W[l],
                                                                           m->b[l], y, y_rs, M, Kl, sg);
         else if (Kl % 8 == 0 && Kl <= 512)
           gemv_fwd_vec_kernel<2, 2><<<2 * GEMV_BLOCKS, GEMV_THREADS, 0, st>>>(t.H[l].hi, t.H[l].lo, t.H[l].pitch, m->W[l],
@@ -759,13 +763,13 @@ static int gantts::mlp_bwd_impl(const gantts_mlp_t* m, const float* gy, int64_t 
       Gl[Lh - 1].hi, Gl[Lh - 1].lo, Gl[Lh - 1].pitch, gemv_part0, M, K1, m->last_act == GANTTS_ACT_SIGMOID ? 1 : 0, ks, \
       m->slope * ks, m->dropout_p > 0.f ? 0.f : m->slope, want_last ? 1 : 0
       if (K1 % 8 == 0 && K1 <= 256)
-        gemv_bwd_vec_kernel<1, 4><<<GEMV_BLOCKS, GEMV_THREADS, 0, st>>>(GANTTS_GEMV_BWD_ARGS2);
+        GANTTS_PDL_LAUNCH((gemv_bwd_vec_kernel<1, 4>), GEMV_BLOCKS, GEMV_THREADS, 0, st, GANTTS_GEMV_BWD_ARGS2);
       else
         gemv_bwd_kernel<<<GEMV_BLOCKS, GEMV_THREADS, 0, st>>>(GANTTS_GEMV_BWD_ARGS2);
 #undef GANTTS_GEMV_BWD_ARGS2
       GANTTS_LAUNCH_CHECK("gemv_bwd_kernel");
       if (want_last) {
-        gemv_partial_reduce_kernel<<<(K1 + 1 + 31) / 32, 256, 0, st>>>(gemv_part0, GEMV_BLOCKS, K1,
+        GANTTS_PDL_LAUNCH((gemv_partial_reduce_kernel), (K1 + 1 + 31) / 32, 256, 0, st, gemv_part0, GEMV_BLOCKS, K1,
                                                                       gW ? gW[L - 1] : nullptr,
                                                                       gb ? gb[L - 1] : nullptr, accumulate);
         GANTTS_LAUNCH_CHECK("gemv_partial_reduce_kernel");
@@ -846,7 +850,7 @@ static int gantts::mlp_bwd_impl(const gantts_mlp_t* m, const float* gy, int64_t 
       m->W[L - 1], G.hi, G.lo, G.pitch, gemv_part, M, K1, m->last_act == GANTTS_ACT_SIGMOID ? 1 : 0, ks,        \
       m->slope * ks, m->dropout_p > 0.f ? 0.f : m->slope, want
     if (K1 % 8 == 0 && K1 <= 256)
-      gemv_bwd_vec_kernel<1, 4><<<GEMV_BLOCKS, GEMV_THREADS, 0, st>>>(GANTTS_GEMV_BWD_ARGS);
+      GANTTS_PDL_LAUNCH((gemv_bwd_vec_kernel<1, 4>), GEMV_BLOCKS, GEMV_THREADS, 0, st, GANTTS_GEMV_BWD_ARGS);
     else if (K1 % 8 == 0 && K1 <= 512)
       gemv_bwd_vec_kernel<2, 2><<<GEMV_BLOCKS, GEMV_THREADS, 0, st>>>(GANTTS_GEMV_BWD_ARGS);
     else if (K1 % 8 == 0)
@@ -857,7 +861,7 @@ static int gantts::mlp_bwd_impl(const gantts_mlp_t* m, const float* gy, int64_t 
     GANTTS_LAUNCH_CHECK("gemv_bwd_kernel");
     if (want) {
       // partial rows are [K1 weights | 1 bias]: one column-parallel reduction for both
-      gemv_partial_reduce_kernel<<<(K1 + 1 + 31) / 32, 256, 0, st>>>(gemv_part, GEMV_BLOCKS, K1,
+      GANTTS_PDL_LAUNCH((gemv_partial_reduce_kernel), (K1 + 1 + 31) / 32, 256, 0, st, gemv_part, GEMV_BLOCKS, K1,
                                                                     gW ? gW[L - 1] : nullptr,
                                                                     gb ? gb[L - 1] : nullptr, accumulate);
       GANTTS_LAUNCH_CHECK("gemv_partial_reduce_kernel");

@@ -326,6 +326,7 @@ __global__ void __launch_bounds__(32 * SOLVE_WARPS, 4)
 mlpg_solve_fwd_kernel(const float* __restrict__ in, int64_t in_bs, int in_ts, float* __restrict__ out, int64_t out_bs,
                       int out_ts, const float* __restrict__ table, gantts_streams_t st, SolveTaps taps, int B, int T,
                       int ncols, int ncg, int bpc) {
+  pdl_entry();
   extern __shared__ __align__(16) float smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const SolveItem it = solve_item(B, ncg, bpc);
@@ -454,6 +455,7 @@ mlpg_solve_bwd_kernel(const float* __restrict__ go, int64_t go_bs, int go_ts, fl
                       int gi_ts, const float* __restrict__ table, gantts_streams_t st, SolveTaps taps, int B, int T, int ncols,
                       int ncg, int bpc, int accumulate, __nv_bfloat16* __restrict__ phi, __nv_bfloat16* __restrict__ plo,
                       int ppitch) {
+  pdl_entry();
   extern __shared__ __align__(16) float smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const SolveItem it = solve_item(B, ncg, bpc);
@@ -758,7 +760,7 @@ extern "C" int gantts_mlpg_fwd(const float* in, int64_t in_bs, int64_t in_ts, fl
       int in_cols = 0;
       for (int s = 0; s < st->n; ++s) in_cols += st->sd[s] * (st->dyn[s] ? win->n : 1);
       prof_begin(PROF_MLPG_FWD, 4.0 * (double)B * T * (in_cols + ncols), as_stream(stream));
-      fn<<<g.blocks, 32 * SOLVE_WARPS, g.smem, as_stream(stream)>>>(in, in_bs, (int)in_ts, out, out_bs, (int)out_ts, table_dev, *st,
+      GANTTS_PDL_LAUNCH((fn), g.blocks, 32 * SOLVE_WARPS, g.smem, as_stream(stream), in, in_bs, (int)in_ts, out, out_bs, (int)out_ts, table_dev, *st,
                                                                   tp, B, T, ncols, g.ncg, g.bpc);
       prof_end(as_stream(stream));
       GANTTS_LAUNCH_CHECK("mlpg_solve_fwd_kernel");
@@ -809,7 +811,7 @@ static int mlpg_bwd_planes(const float* go, int64_t go_bs, int64_t go_ts, __nv_b
   int in_cols = 0;
   for (int s = 0; s < st->n; ++s) in_cols += st->sd[s] * (st->dyn[s] ? win->n : 1);
   prof_begin(PROF_MLPG_BWD, 4.0 * (double)B * T * (in_cols + ncols), as_stream(stream));
-  fn<<<g.blocks, 32 * SOLVE_WARPS, g.smem, as_stream(stream)>>>(go, go_bs, (int)go_ts, nullptr, 0, 0, table_dev, *st, tp, B, T, ncols,
+  GANTTS_PDL_LAUNCH((fn), g.blocks, 32 * SOLVE_WARPS, g.smem, as_stream(stream), go, go_bs, (int)go_ts, nullptr, 0, 0, table_dev, *st, tp, B, T, ncols,
                                                               g.ncg, g.bpc, 0, phi, plo, (int)ppitch);
   prof_end(as_stream(stream));
   GANTTS_LAUNCH_CHECK("mlpg_solve_bwd_kernel(planes)");
@@ -835,7 +837,7 @@ extern "C" int gantts_mlpg_bwd(const float* go, int64_t go_bs, int64_t go_ts, fl
       int in_cols = 0;
       for (int s = 0; s < st->n; ++s) in_cols += st->sd[s] * (st->dyn[s] ? win->n : 1);
       prof_begin(PROF_MLPG_BWD, 4.0 * (double)B * T * (in_cols + ncols), as_stream(stream));
-      fn<<<g.blocks, 32 * SOLVE_WARPS, g.smem, as_stream(stream)>>>(go, go_bs, (int)go_ts, gi, gi_bs, (int)gi_ts, table_dev, *st, tp, B, T,
+      GANTTS_PDL_LAUNCH((fn), g.blocks, 32 * SOLVE_WARPS, g.smem, as_stream(stream), go, go_bs, (int)go_ts, gi, gi_bs, (int)gi_ts, table_dev, *st, tp, B, T,
                                                                   ncols, g.ncg, g.bpc, accumulate, nullptr, nullptr, 0);
       prof_end(as_stream(stream));
       GANTTS_LAUNCH_CHECK("mlpg_solve_bwd_kernel");

@@ -28,6 +28,7 @@ __device__ __forceinline__ int find_tensor(const TensorList& tl, int64_t i) {
 
 __global__ void __launch_bounds__(OPT_THREADS)
 sumsq_partial_kernel(TensorList tl, float* partial) {
+  pdl_entry();
   __shared__ float sm[32];
   float v[1] = {0.f};
   const int64_t total = tl.off[tl.n];
