@@ -60,13 +60,20 @@ def scaling(b):
     if "" not in b or not any(k in b for k in ("_n2", "_n4", "_n8")):
         return
     base = b[""]
+    # the N > 1 runs were made on the build of commit c21373d (before PDL was extended to the streaming kernels); its own
+    # N = 1 line is kept as <tag>_bench_scaling_n1.json so that the efficiencies compare like with like
+    sb = os.path.join(OUT, "%s_bench_scaling_n1.json" % TAG)
+    base_file = "%s_bench.json" % TAG
+    if os.path.exists(sb):
+        base = json.load(open(sb))
+        base_file = "%s_bench_scaling_n1.json (build c21373d)" % TAG
     lines = ["# Weak scaling on one B200 node, %s (`bench.py --gpus N` under torchrun, one rank per GPU, B=32 x T=1000 per GPU)" % TAG, "",
              "value = total frames of all ranks / max-over-ranks CUDA-event time, median of >= 3 repeats after 12 untimed all-reduces of "
              "both gradient buffers.  Exchange per step: SUM all-reduce of the D buffer (0.6 MB) after phase 1 and of the G buffer "
              "(3.4 MB) after phase 2 of `gantts_gan_step`; `allreduce` = the two all-reduces timed alone, back to back.", "",
              "| N | ms/step | frames/s (device-resident) | vs N=1 (efficiency) | e2e ms/step | all-reduce pair alone us | file |",
              "|---|---|---|---|---|---|---|",
-             "| 1 | %.4f | %.2f M | 1.00 | %.3f | - | %s_bench.json |" % (base["ms_per_step"], base["value"] / 1e6, base["e2e"]["ms_per_step"], TAG)]
+             "| 1 | %.4f | %.2f M | 1.00 | %.3f | - | %s |" % (base["ms_per_step"], base["value"] / 1e6, base["e2e"]["ms_per_step"], base_file)]
     for k, n in (("_n2", 2), ("_n4", 4), ("_n8", 8)):
         if k in b:
             d = b[k]
@@ -74,14 +81,24 @@ def scaling(b):
             lines.append("| %d | %.4f | %.2f M | %.2f (%.0f %%) | %.3f | %s | %s_bench%s.json |" % (
                 n, d["ms_per_step"], d["value"] / 1e6, d["value"] / base["value"], 100.0 * d["value"] / base["value"] / n,
                 d["e2e"]["ms_per_step"], ("%.0f" % ar["us_per_step_pair"]) if ar else "-", TAG, k))
+    if os.path.exists(sb):
+        cur = b[""]
+        lines += ["", "All three rows: build c21373d.  The final build (programmatic dependent launch extended to the streaming kernels) runs "
+                  "N = 1 at %.4f ms/step = %.2f M frames/s (%s_bench.json); the N > 1 rows were not re-measured on it (GPU budget)."
+                  % (cur["ms_per_step"], cur["value"] / 1e6, TAG)]
     c5, c5n = last_json(os.path.join(GO, "bench_%s_cfg5.json" % TAG)), last_json(os.path.join(GO, "bench_%s_cfg5_n8.json" % TAG))
     if c5 and c5n:
         json.dump(c5n, open(os.path.join(OUT, "%s_bench_cfg5_n8.json" % TAG), "w"), indent=1)
+        sb5 = os.path.join(OUT, "%s_bench_cfg5_scaling_n1.json" % TAG)
+        note5 = ""
+        if os.path.exists(sb5):
+            cur5, c5 = c5, json.load(open(sb5))
+            note5 = "  (Both on build c21373d; the final build runs cfg5 at %.1f ms/step on one GPU.)" % cur5["ms_per_step"]
         lines += ["", "cfg5 (BASELINE configs[4]: TTS acoustic LSTMRNN + GAN + MGE, B=64 x T=1500 per GPU, `GanTrainer`, gradient all-reduce of "
-                  "the 17 M-parameter generator and the discriminator per step): 1 GPU %.1f ms/step = %.1f k frames/s (%s_bench_cfg5.json); "
+                  "the 17 M-parameter generator and the discriminator per step): 1 GPU %.1f ms/step = %.1f k frames/s (%s_bench_cfg5*.json); "
                   "**8 GPUs %.1f ms/step = %.2f M frames/s = %.2fx (%.0f %%)** (%s_bench_cfg5_n8.json)." % (
                       c5["ms_per_step"], c5["value"] / 1e3, TAG, c5n["ms_per_step"], c5n["value"] / 1e6, c5n["value"] / c5["value"],
-                      100.0 * c5n["value"] / c5["value"] / 8, TAG)]
+                      100.0 * c5n["value"] / c5["value"] / 8, TAG) + note5]
     open(os.path.join(OUT, "%s_scaling.md" % TAG), "w").write("\n".join(lines) + "\n")
 
 
