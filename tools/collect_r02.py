@@ -60,13 +60,13 @@ def scaling(b):
     if "" not in b or not any(k in b for k in ("_n2", "_n4", "_n8")):
         return
     base = b[""]
-    # the N > 1 runs were made on the build of commit c21373d (before PDL was extended to the streaming kernels); its own
-    # N = 1 line is kept as <tag>_bench_scaling_n1.json so that the efficiencies compare like with like
+    # the N > 1 runs use --steps 50 --warmup 10; the N = 1 line with the same arguments is kept as
+    # <tag>_bench_scaling_n1.json (the default 100-step run of <tag>_bench.json reaches the software power cap)
     sb = os.path.join(OUT, "%s_bench_scaling_n1.json" % TAG)
     base_file = "%s_bench.json" % TAG
     if os.path.exists(sb):
         base = json.load(open(sb))
-        base_file = "%s_bench_scaling_n1.json (build c21373d)" % TAG
+        base_file = "%s_bench_scaling_n1.json (--steps 50 --warmup 10, like the rows below)" % TAG
     lines = ["# Weak scaling on one B200 node, %s (`bench.py --gpus N` under torchrun, one rank per GPU, B=32 x T=1000 per GPU)" % TAG, "",
              "value = total frames of all ranks / max-over-ranks CUDA-event time, median of >= 3 repeats after 12 untimed all-reduces of "
              "both gradient buffers.  Exchange per step: SUM all-reduce of the D buffer (0.6 MB) after phase 1 and of the G buffer "
@@ -81,11 +81,6 @@ def scaling(b):
             lines.append("| %d | %.4f | %.2f M | %.2f (%.0f %%) | %.3f | %s | %s_bench%s.json |" % (
                 n, d["ms_per_step"], d["value"] / 1e6, d["value"] / base["value"], 100.0 * d["value"] / base["value"] / n,
                 d["e2e"]["ms_per_step"], ("%.0f" % ar["us_per_step_pair"]) if ar else "-", TAG, k))
-    if os.path.exists(sb):
-        cur = b[""]
-        lines += ["", "All three rows: build c21373d.  The final build (programmatic dependent launch extended to the streaming kernels) runs "
-                  "N = 1 at %.4f ms/step = %.2f M frames/s (%s_bench.json); the N > 1 rows were not re-measured on it (GPU budget)."
-                  % (cur["ms_per_step"], cur["value"] / 1e6, TAG)]
     c5, c5n = last_json(os.path.join(GO, "bench_%s_cfg5.json" % TAG)), last_json(os.path.join(GO, "bench_%s_cfg5_n8.json" % TAG))
     if c5 and c5n:
         json.dump(c5n, open(os.path.join(OUT, "%s_bench_cfg5_n8.json" % TAG), "w"), indent=1)
