@@ -141,6 +141,30 @@ def test_gan_trainer_cfg2_full_size_train_mode_injected_masks(dev):
     assert max(errs.values()) < 1e-4, errs
 
 
+@pytest.mark.parametrize("rows,cols,p", [(257, 256, 0.5), (64, 187, 0.2), (33, 58, 0.5), (5, 3, 0.9)])
+def test_dropout_mask_matches_numpy_mirror(dev, rows, cols, p):
+    """gantts_dropout (the kernel the injected-mask parity tests regenerate masks with) against tests/dropout_mirror.py, the
+    numpy statement of csrc/common.cuh's counter hash: bit-exact, including widths that are not multiples of 4; and the
+    tcgen05 epilogue applies the same mask (a Linear layer with zero weights and bias 1 outputs exactly the multiplier)."""
+    import dropout_mirror as dm
+    from gantts_b200 import ops, _lib
+    seed = 0x1234567 * (rows + cols)
+    keep = dm.keep_mask(seed, rows, cols, p)
+    scale = 1.0 / (1.0 - p)
+
+    def check(got, what):
+        assert np.array_equal(got != 0, keep), what                         # the mask: bit-exact
+        assert np.allclose(got[keep], scale, rtol=1e-6, atol=0), what       # the multiplier 1 / (1 - p)
+    check(npy(ops.dropout_mask(rows, cols, p, seed, dev)), "gantts_dropout")
+    if cols >= 16:
+        W = torch.zeros(cols, 16, device=dev)
+        b = torch.ones(cols, device=dev)
+        x = torch.zeros(rows, 16, device=dev)
+        for engine in ("simt", "tc"):
+            y = ops.linear_act(x, W, b, act=_lib.ACT_LEAKY_DROPOUT, p=p, training=True, engine=engine, seed=seed)
+            check(npy(y), engine)
+
+
 @pytest.mark.parametrize("mse_w,mge_w", [(0.0, 1.0), (1.0, 0.0)])
 def test_fused_step_without_discriminator(dev, mse_w, mge_w):
     """BASELINE configs[3] (TTS acoustic MLP + MGE loss, no adversarial term) and the MSE-only objective of configs[0] on the

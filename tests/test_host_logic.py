@@ -53,6 +53,51 @@ def test_mlpg_table_matches_dense_inverse(lib):
                 assert abs(tab[t, j] - exp) < 2e-7
 
 
+def test_mlpg_table_cholesky_rows_solve_the_normal_equations():
+    """Columns 52..59 of the table = rows of the banded Cholesky factor L of P = W^T W (1/L_tt, L[t][t-1], L[t][t-2] and the
+    transposed entries L[t+1][t], L[t+2][t]).  The substitution the round-2 MLPG kernels run (forward with the first three,
+    backward with the transposed pair), evaluated here in numpy from the library's own table, solves P y = b -- on the whole
+    sequence and, with the kernels' 28-frame warm-up from a zero state, on a 32-frame chunk in the middle."""
+    from gantts_b200 import ops
+    rng = np.random.default_rng(1)
+    for wins, T in ((WINDOWS, 200), (WINDOWS[:2], 77), (WINDOWS, 5), (WINDOWS[:1], 9)):
+        tab = ops.mlpg_table_full_host(wins, T).astype(np.float64)
+        P = nnp.normal_matrix(wins, T)
+        L = np.zeros((T, T))
+        for t in range(T):
+            L[t, t] = 1.0 / tab[t, 52]
+            if t >= 1:
+                L[t, t - 1] = tab[t, 53]
+            if t >= 2:
+                L[t, t - 2] = tab[t, 54]
+            if t + 1 < T:
+                assert abs(tab[t, 56] - tab[t + 1, 53]) < 1e-12          # L[t+1][t] stored twice
+            if t + 2 < T:
+                assert abs(tab[t, 57] - tab[t + 2, 54]) < 1e-12
+        assert np.abs(L @ L.T - P).max() < 2e-6 * np.abs(P).max()
+
+        def solve(b, s, e):
+            """forward then backward substitution over rows [s, e) from a zero state, table rows as the kernels read them"""
+            z = np.zeros(T)
+            z1 = z2 = 0.0
+            for t in range(s, e):
+                z[t] = (b[t] - tab[t, 53] * z1 - tab[t, 54] * z2) * tab[t, 52]
+                z2, z1 = z1, z[t]
+            y = np.zeros(T)
+            y1 = y2 = 0.0
+            for t in range(e - 1, s - 1, -1):
+                y[t] = (z[t] - tab[t, 56] * y1 - tab[t, 57] * y2) * tab[t, 52]
+                y2, y1 = y1, y[t]
+            return y
+        b = rng.standard_normal(T)
+        ref = np.linalg.solve(P, b)
+        assert np.abs(solve(b, 0, T) - ref).max() < 5e-6 * np.abs(ref).max()
+        if T >= 120:
+            t0, t1, sw = 80, 112, 28
+            y = solve(b, t0 - sw, t1 + sw)
+            assert np.abs(y[t0:t1] - ref[t0:t1]).max() < 5e-6 * np.abs(ref).max()
+
+
 def test_mlpg_table_fir_equals_dense_R():
     """Stencil + truncated FIR (the CUDA algorithm, evaluated here in numpy from the library's own
     table) reproduces the reference's dense R matmul."""
@@ -172,3 +217,25 @@ def test_distortion_struct_matches_header():
     body = hdr[hdr.index("typedef struct {\n  int mcd_start"):hdr.index("} gantts_distortion_cols_t;")]
     names = [tok.strip(" ;") for line in body.splitlines()[1:] for tok in line.replace("int ", "").split(",") if tok.strip(" ;")]
     assert names == [f for f, _ in _lib.DistortionColsT._fields_]
+
+
+def test_dropout_hash_statistics():
+    """The counter-hash keep mask (tests/dropout_mirror.py = csrc/common.cuh bit for bit; the GPU suite pins the kernels to
+    the mirror): keep rate, independence of the four fields of a quad / of neighbouring quads / of neighbouring rows, and
+    binomial dispersion of the per-column and per-row keep rates."""
+    import dropout_mirror as dm
+    rows, n = 8192, 256
+    for seed, p in ((12345678901234567, 0.5), (4242 * 4 + 1, 0.2), (99, 0.5)):
+        m = dm.keep_mask(seed, rows, n, p).astype(np.float64)
+        assert abs(m.mean() - (1.0 - p)) < 2e-3
+        z = m - m.mean()
+
+        def corr(a, b):
+            return float((a * b).mean() / np.sqrt((a * a).mean() * (b * b).mean()))
+        pairs = [(z[:, 0::4], z[:, 1::4]), (z[:, 0::4], z[:, 2::4]), (z[:, 0::4], z[:, 3::4]), (z[:, 1::4], z[:, 2::4]),
+                 (z[:, 2::4], z[:, 3::4]), (z[:, :-4], z[:, 4:]), (z[:-1], z[1:])]
+        assert max(abs(corr(a, b)) for a, b in pairs) < 8e-3          # 1/sqrt(samples) = 1.4e-3
+        q = p * (1.0 - p)
+        assert abs(m.mean(0).std() / np.sqrt(q / rows) - 1.0) < 0.25
+        assert abs(m.mean(1).std() / np.sqrt(q / n) - 1.0) < 0.1
+    assert not dm.keep_mask(7, 64, 64, 1.0).any() and dm.keep_mask(7, 64, 64, 0.0).all()
