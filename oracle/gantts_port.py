@@ -197,6 +197,30 @@ def adagrad_step(params, grads, state_sums, lr=0.01, weight_decay=1e-7, eps=1e-1
             p.addcdiv_(g, s.sqrt() + eps, value=-lr)
 
 
+class AdamStepper(object):
+    """torch.optim.Adam (amsgrad off) as configured by reference hparams.py:125-130 for the duration model
+    (lr 1e-3, betas (0.5, 0.9), weight_decay 0, eps 1e-8) and stepped at train.py:276,318:
+    g' = g + wd p; m = b1 m + (1 - b1) g'; v = b2 v + (1 - b2) g'^2;
+    p -= lr / (1 - b1^t) * m / (sqrt(v) / sqrt(1 - b2^t) + eps).  Callable as ``stepper(params, grads)``;
+    pass it to ``gan_step(..., d_opt=..., g_opt=...)`` in place of the default Adagrad."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        self.lr, self.b1, self.b2, self.eps, self.wd = float(lr), float(betas[0]), float(betas[1]), float(eps), float(weight_decay)
+        self.m = [torch.zeros_like(p) for p in params]
+        self.v = [torch.zeros_like(p) for p in params]
+        self.t = 0
+
+    def __call__(self, params, grads):
+        self.t += 1
+        c1, c2 = 1.0 - self.b1 ** self.t, 1.0 - self.b2 ** self.t
+        with torch.no_grad():
+            for p, g, m, v in zip(params, grads, self.m, self.v):
+                g = g + self.wd * p
+                m.mul_(self.b1).add_(g, alpha=1.0 - self.b1)
+                v.mul_(self.b2).addcmul_(g, g, value=1.0 - self.b2)
+                p.addcdiv_(m, v.sqrt() / math.sqrt(c2) + self.eps, value=-self.lr / c1)
+
+
 class GanStepState(object):
     """Weights + Adagrad accumulators for one MLP-G / MLP-D pair (plain tensors)."""
 
@@ -229,7 +253,7 @@ def apply_generator(model_out, x, R, hp, include_parameter_generation=False):
 
 def gan_step(g_forward, g_params, g_sum, d_layers, d_sum, x, y, lengths, R, hp, w_d=1.0, mse_w=0.0,
              mge_w=1.0, adv_w=1.0, dropout_d=0.0, training=True, lr=0.01, weight_decay=1e-7, update=True,
-             d_masks=None):
+             d_masks=None, d_opt=None, g_opt=None):
     """One mini-batch of the reference train_loop body (train.py:528-580) for ANY generator:
     ``g_forward()`` -> ``(y_hat, y_hat_static)`` is the result of ``apply_generator`` (train.py:336-355)
     with autograd history on ``g_params``; ``d_layers`` is the MLP discriminator ``[(W, b), ...]`` or
@@ -272,7 +296,10 @@ def gan_step(g_forward, g_params, g_sum, d_layers, d_sum, x, y, lengths, R, hp, 
             loss_d.backward(retain_graph=True)
             dg = [p.grad for p in d_params]
             out["d_grad_norm"] = float(clip_grad_norm(dg, 1.0))
-            adagrad_step(d_params, dg, d_sum, lr, weight_decay)
+            if d_opt is not None:
+                d_opt(d_params, dg)                      # e.g. AdamStepper (hparams.py:125-130)
+            else:
+                adagrad_step(d_params, dg, d_sum, lr, weight_decay)
         out.update(loss_d=loss_d.item(), loss_fake_d=loss_fake.item(), loss_real_d=loss_real.item())
     # update_generator, train.py:282-320
     loss_mge = masked_mse(y_hat_static, y_static, mask=mask)
@@ -292,7 +319,10 @@ def gan_step(g_forward, g_params, g_sum, d_layers, d_sum, x, y, lengths, R, hp, 
         g_params = list(g_params)
         gg = [p.grad if p.grad is not None else torch.zeros_like(p) for p in g_params]
         out["g_grad_norm"] = float(clip_grad_norm(gg, 1.0))
-        adagrad_step(g_params, gg, g_sum, lr, weight_decay)
+        if g_opt is not None:
+            g_opt(g_params, gg)
+        else:
+            adagrad_step(g_params, gg, g_sum, lr, weight_decay)
     out.update(loss_mse=loss_mse.item(), loss_mge=loss_mge.item(), loss_adv=float(loss_adv.detach()),
                loss_g=float(loss_g.detach()))
     return out, y_hat.detach(), y_hat_static.detach()
@@ -300,7 +330,7 @@ def gan_step(g_forward, g_params, g_sum, d_layers, d_sum, x, y, lengths, R, hp, 
 
 def gan_step_mlp(state, x, y, lengths, R, hp, w_d=1.0, mse_w=0.0, mge_w=1.0, adv_w=1.0,
                  dropout_g=0.0, dropout_d=0.0, training=True, lr=0.01, weight_decay=1e-7,
-                 update=True, masks=None):
+                 update=True, masks=None, d_opt=None, g_opt=None):
     """``gan_step`` for an MLP generator (reference ``MLP`` class, models.py:121-141) held in a
     ``GanStepState``.  ``masks`` = {"g": [...], "real": [...], "fake": [...], "adv": [...]} injects the
     dropout multipliers of the generator forward and of the three discriminator forwards."""
@@ -312,7 +342,8 @@ def gan_step_mlp(state, x, y, lengths, R, hp, w_d=1.0, mse_w=0.0, mge_w=1.0, adv
 
     return gan_step(g_forward, state.g_params(), state.g_sum, state.d if w_d > 0 else None, state.d_sum,
                     x, y, lengths, R, hp, w_d=w_d, mse_w=mse_w, mge_w=mge_w, adv_w=adv_w, dropout_d=dropout_d,
-                    training=training, lr=lr, weight_decay=weight_decay, update=update, d_masks=masks)
+                    training=training, lr=lr, weight_decay=weight_decay, update=update, d_masks=masks,
+                    d_opt=d_opt, g_opt=g_opt)
 
 
 class GeneratorOracle(object):

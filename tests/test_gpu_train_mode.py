@@ -141,6 +141,84 @@ def test_gan_trainer_cfg2_full_size_train_mode_injected_masks(dev):
     assert max(errs.values()) < 1e-4, errs
 
 
+DUR_HP = dict(stream_sizes=[5], has_dynamic_features=[False], adversarial_streams=[True], mask_nth_mgc_for_adv_loss=0,
+              num_windows=1, discriminator_linguistic_condition=False)
+
+
+def _duration_models(dev, p=0.0):
+    import gantts_b200
+    torch.manual_seed(5)
+    mg = gantts_b200.models.MLP(20, 5, 2, 64, dropout=p, last_sigmoid=False)
+    md = gantts_b200.models.MLP(5, 1, 2, 32, dropout=p, last_sigmoid=True)
+    names = ["layers.0", "layers.1", "last_linear"]
+    state = gp.GanStepState(layers_of(mg, names), layers_of(md, names))
+    return mg.to(dev).train(), md.to(dev).train(), state
+
+
+def _duration_hp():
+    from gantts_b200 import step as gstep
+    return gstep.HParams(windows=[(0, 0, np.array([1.0]))], stream_sizes=[5], has_dynamic_features=[False],
+                         adversarial_streams=[True], mask_nth_mgc_for_adv_loss=0, discriminator_linguistic_condition=False)
+
+
+def test_gan_trainer_duration_config_adam_and_no_R(dev):
+    """The duration model's configuration (reference hparams.py:98-130): static-only stream (has_dynamic_features = [False]
+    => train.py:510-515 passes R = None and multi_stream_mlpg is the identity), adversarial loss on the whole stream, Adam
+    (lr 1e-3, betas (0.5, 0.9)) for both models.  GanTrainer with optimizer="Adam" against the oracle stepping with
+    AdamStepper: losses, both gradient norms and the post-step weights of two consecutive steps (the oracle is re-synchronised
+    to the product's weights and moments before step 2: a first Adam step is lr * sign(g), ill-conditioned where g ~ 0)."""
+    from gantts_b200 import step as gstep
+    B, T = 6, 50
+    mg, md, state = _duration_models(dev)
+    okw = dict(lr=1e-3, betas=(0.5, 0.9), weight_decay=0.0, eps=1e-8)
+    tr = gstep.GanTrainer(mg, md, _duration_hp(), w_d=1.0, mse_w=1.0, mge_w=0.0, optimizer="Adam", optimizer_params=okw)
+    g_opt = gp.AdamStepper(state.g_params(), **okw)
+    d_opt = gp.AdamStepper(state.d_params(), **okw)
+    for it in range(2):
+        lens = ragged_lengths(B, T, 30 + it)
+        x, y = make_batch(B, T, 20, 5, lens, 200 + it)
+        out, yh, ys = tr.step(x.to(dev), y.to(dev), lens, None)
+        ref, yh_ref, ys_ref = gp.gan_step_mlp(state, x, y, lens, None, DUR_HP, w_d=1.0, mse_w=1.0, mge_w=0.0, d_opt=d_opt,
+                                              g_opt=g_opt)
+        errs = loss_errors(out, ref, ("loss_d", "loss_fake_d", "loss_real_d", "loss_mse", "loss_mge", "loss_adv", "loss_g"))
+        errs["y_hat"] = rel_err(npy(yh), yh_ref.numpy())
+        errs["g_grad_norm"] = abs(float(tr.opt_g.grad_norm()) - ref["g_grad_norm"]) / ref["g_grad_norm"]
+        errs["d_grad_norm"] = abs(float(tr.opt_d.grad_norm()) - ref["d_grad_norm"]) / ref["d_grad_norm"]
+        assert max(errs.values()) < 1e-4, (it, errs)
+        assert torch.equal(ys, yh)                                       # static-only: MLPG is the identity
+        for mod, params in ((mg, state.g_params()), (md, state.d_params())):
+            for q, r in zip(mod.parameters(), params):
+                dW = np.abs(npy(q) - r.detach().numpy())
+                assert np.median(dW) < 2e-6 and dW.max() <= 2.01e-3, (it, np.median(dW), dW.max())
+        # re-synchronise the oracle: weights and Adam moments
+        with torch.no_grad():
+            for mod, params, opt, st in ((mg, state.g_params(), tr.opt_g, g_opt), (md, state.d_params(), tr.opt_d, d_opt)):
+                sd = opt.state_dict()["state"]
+                for i, (q, r) in enumerate(zip(mod.parameters(), params)):
+                    r.copy_(q.detach().cpu())
+                    st.m[i].copy_(sd[i]["exp_avg"].cpu())
+                    st.v[i].copy_(sd[i]["exp_avg_sq"].cpu())
+
+
+def test_fused_step_static_only_streams(dev):
+    """The same static-only configuration on the fused entry point (Adagrad): no stream has dynamic features, MLPG
+    degenerates to a copy (reference train.py:510-515: R = None), the discriminator sees the whole stream."""
+    from gantts_b200 import fused
+    B, T = 6, 50
+    mg, md, state = _duration_models(dev)
+    lens = ragged_lengths(B, T, 41)
+    x, y = make_batch(B, T, 20, 5, lens, 300)
+    fs = fused.FusedGanStep(mg, md, _duration_hp(), B, T, w_d=1.0, mse_w=1.0, mge_w=1.0, seed=3)
+    fs.step(x.to(dev), y.to(dev), torch.LongTensor(lens).to(dev), frames=sum(lens))
+    got = fs.loss_dict()
+    ref, yh_ref, ys_ref = gp.gan_step_mlp(state, x, y, lens, None, DUR_HP, w_d=1.0, mse_w=1.0, mge_w=1.0)
+    errs = loss_errors(got, ref, LOSS_KEYS + ("d_grad_norm", "g_grad_norm"))
+    errs["y_hat"] = rel_err(npy(fs.y_hat), yh_ref.numpy())
+    errs["y_hat_static"] = rel_err(npy(fs.y_hat_static), ys_ref.numpy())
+    assert max(errs.values()) < 1e-4, errs
+    assert torch.equal(fs.y_hat, fs.y_hat_static)
+
+
 @pytest.mark.parametrize("rows,cols,p", [(257, 256, 0.5), (64, 187, 0.2), (33, 58, 0.5), (5, 3, 0.9)])
 def test_dropout_mask_matches_numpy_mirror(dev, rows, cols, p):
     """gantts_dropout (the kernel the injected-mask parity tests regenerate masks with) against tests/dropout_mirror.py, the
@@ -732,3 +810,32 @@ def test_mlpg_both_kernel_families_vs_dense_R(dev, monkeypatch, mode, B, Tn):
     assert rel_err(npy(yd), npy(yr)) < 5e-6
     assert rel_err(npy(xd.grad), npy(xr.grad)) < 5e-6
     assert torch.equal(yd[:, :, 61].cpu(), x[:, :, 183])          # static stream copied bit-exactly
+
+
+@pytest.mark.parametrize("mode", ["0", "3"])
+@pytest.mark.parametrize("case", ["two_windows", "dense_delta"])
+def test_mlpg_generic_window_patterns(dev, monkeypatch, mode, case):
+    """Window sets that do NOT have the sparsity pattern the substitution kernels are specialised for (`STD3`): static +
+    delta only, and three windows whose delta window has a non-zero centre tap -- the generic path of both kernel families,
+    forward and backward, against the dense R matmul."""
+    from gantts_b200 import ops
+    monkeypatch.setenv("GANTTS_B200_MLPG_SOLVE", mode)
+    if case == "two_windows":
+        wins = WINDOWS[:2]
+    else:
+        wins = [WINDOWS[0], (1, 1, np.array([-0.4, 0.1, 0.5])), WINDOWS[2]]
+    nw, sd, B, Tn = len(wins), 7, 3, 203
+    torch.manual_seed(11)
+    x = torch.randn(B, Tn, nw * sd + 2)                 # one dynamic stream of 7 static dims + a static stream of 2
+    g = torch.randn(B, Tn, sd + 2)
+    R = torch.from_numpy(nnp.unit_variance_mlpg_matrix(wins, Tn))
+    xr = x.clone().requires_grad_(True)
+    yr = gp.multi_stream_mlpg(xr, R, (nw * sd, 2), (True, False), (True, True))
+    yr.backward(g)
+    entries = [(0, sd, True, 0), (nw * sd, 2, False, sd)]
+    xd = x.to(dev).requires_grad_(True)
+    yd = ops.mlpg(xd, [(l, u, tuple(float(v) for v in c)) for l, u, c in wins], entries, sd + 2)
+    yd.backward(g.to(dev))
+    assert rel_err(npy(yd), npy(yr)) < 5e-6
+    assert rel_err(npy(xd.grad), npy(xr.grad)) < 5e-6
+

@@ -266,3 +266,25 @@ def test_metrics_restatement_hand_values_and_agrees_with_the_shim():
     mgc_h = yh[:, :, 1:60] * Ys[1:60] + Ym[1:60]
     assert abs(d["mcd"] - M.melcd(mgc, mgc_h, [6, 4])) < 1e-12
     assert set(d) == {"mcd", "bap_mcd", "f0_rmse", "vuv_err"}
+
+
+def test_adam_stepper_matches_torch_optim_adam():
+    """oracle AdamStepper (the duration model's optimiser, reference hparams.py:125-130: Adam, lr 1e-3, betas (0.5, 0.9),
+    weight_decay 0) against torch.optim.Adam over several steps, with and without weight decay."""
+    import torch
+    from oracle import gantts_port as gp
+    for wd in (0.0, 1e-3):
+        torch.manual_seed(0)
+        ps = [torch.randn(7, 5), torch.randn(5)]
+        a = [p.clone().requires_grad_(True) for p in ps]
+        b = [p.clone() for p in ps]
+        opt = torch.optim.Adam(a, lr=1e-3, betas=(0.5, 0.9), eps=1e-8, weight_decay=wd)
+        st = gp.AdamStepper(b, lr=1e-3, betas=(0.5, 0.9), eps=1e-8, weight_decay=wd)
+        for k in range(5):
+            gs = [torch.randn_like(p) * (k + 1) for p in ps]
+            for p, g in zip(a, gs):
+                p.grad = g.clone()
+            opt.step()
+            st(b, [g.clone() for g in gs])
+            for p, q in zip(a, b):
+                assert float((p.detach() - q).abs().max()) < 2e-7
