@@ -77,8 +77,14 @@ class GanStepT(ctypes.Structure):
                 ("lr_g", ctypes.c_float), ("lr_d", ctypes.c_float), ("wd_g", ctypes.c_float),
                 ("wd_d", ctypes.c_float), ("eps", ctypes.c_float), ("max_norm", ctypes.c_float),
                 ("w_d", ctypes.c_float), ("mse_w", ctypes.c_float), ("mge_w", ctypes.c_float),
-                ("adv_w", ctypes.c_float)]
+                ("adv_w", ctypes.c_float),
+                ("optimizer", ctypes.c_int), ("beta1", ctypes.c_float), ("beta2", ctypes.c_float),
+                ("opt_step", ctypes.c_int64),
+                ("g_sqW", ctypes.c_void_p * MAX_LAYERS), ("g_sqb", ctypes.c_void_p * MAX_LAYERS),
+                ("d_sqW", ctypes.c_void_p * MAX_LAYERS), ("d_sqb", ctypes.c_void_p * MAX_LAYERS)]
 
+
+OPT_ADAGRAD, OPT_ADAM = 0, 1
 
 _lib = None
 

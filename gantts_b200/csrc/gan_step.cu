@@ -235,6 +235,42 @@ clip_adagrad_partials_kernel(TensorList tl, const float* __restrict__ partial, i
   }
 }
 
+// The same with torch.optim.Adam (amsgrad off; reference hparams.py:125-130): tl.s = exp_avg, tl.s2 = exp_avg_sq;
+// step_size = lr / (1 - beta1^t), inv_sqrt_bc2 = 1 / sqrt(1 - beta2^t) come from the host.
+__global__ void __launch_bounds__(OPT_THREADS)
+clip_adam_partials_kernel(TensorList tl, const float* __restrict__ partial, int npartial, float* __restrict__ sumsq_out,
+                          float max_norm, float b1, float b2, float wd, float eps, float step_size, float inv_sqrt_bc2) {
+  pdl_entry();
+  __shared__ float sm[32];
+  __shared__ float total_s;
+  float v[1] = {0.f};
+  for (int i = threadIdx.x; i < npartial; i += OPT_THREADS) v[0] += partial[i];
+  block_sum<1>(v, sm);
+  if (threadIdx.x == 0) {
+    total_s = v[0];
+    if (blockIdx.x == 0) sumsq_out[0] = v[0];
+  }
+  __syncthreads();
+  const float total_norm = sqrtf(total_s);
+  float coef = max_norm / (total_norm + 1e-6f);
+  coef = coef < 1.f ? coef : 1.f;
+  const int64_t total = tl.off[tl.n];
+  for (int64_t i = (int64_t)blockIdx.x * OPT_THREADS + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * OPT_THREADS) {
+    int k = find_tensor(tl, i);
+    int64_t j = i - tl.off[k];
+    float g = tl.g[k][j] * coef;
+    tl.g[k][j] = g;
+    const float p = tl.p[k][j];
+    g = fmaf(wd, p, g);
+    const float m = b1 * tl.s[k][j] + (1.f - b1) * g;
+    const float q = b2 * tl.s2[k][j] + (1.f - b2) * g * g;
+    tl.s[k][j] = m;
+    tl.s2[k][j] = q;
+    tl.p[k][j] = p - step_size * m / (sqrtf(q) * inv_sqrt_bc2 + eps);
+  }
+}
+
 // losses[0..11] = loss_d, loss_fake_d, loss_real_d, loss_mse, loss_mge, loss_adv, loss_g,
 //                 real_correct, fake_correct, frames(local sum of mask), d_grad_norm, g_grad_norm
 __global__ void __launch_bounds__(RED_THREADS)
@@ -287,6 +323,7 @@ struct ParamList {
   float* p[2 * GANTTS_MAX_LAYERS];
   float* g[2 * GANTTS_MAX_LAYERS];
   float* s[2 * GANTTS_MAX_LAYERS];
+  float* s2[2 * GANTTS_MAX_LAYERS];                     // Adam: exp_avg_sq (null for Adagrad)
   int64_t sizes[2 * GANTTS_MAX_LAYERS];
   float* gW[GANTTS_MAX_LAYERS];
   float* gb[GANTTS_MAX_LAYERS];
@@ -352,7 +389,8 @@ static void layout(const gantts_gan_step_t* c, char* base, StepLayout* L) {
   L->total = (size_t)(cur - base) + 256;
 }
 
-static void param_list(const gantts_mlp_t& m, float* const* sumW, float* const* sumb, float* flat, ParamList* pl) {
+static void param_list(const gantts_mlp_t& m, float* const* sumW, float* const* sumb, float* const* sqW, float* const* sqb,
+                       float* flat, ParamList* pl) {
   pl->n = 0;
   pl->total = 0;
   float* cur = flat;
@@ -362,12 +400,14 @@ static void param_list(const gantts_mlp_t& m, float* const* sumW, float* const* 
     pl->p[pl->n] = const_cast<float*>(m.W[l]);
     pl->g[pl->n] = cur;
     pl->s[pl->n] = sumW[l];
+    pl->s2[pl->n] = sqW[l];
     pl->sizes[pl->n++] = nw;
     cur += nw;
     pl->gb[l] = cur;
     pl->p[pl->n] = const_cast<float*>(m.b[l]);
     pl->g[pl->n] = cur;
     pl->s[pl->n] = sumb[l];
+    pl->s2[pl->n] = sqb[l];
     pl->sizes[pl->n++] = nb;
     cur += nb;
   }
@@ -397,23 +437,38 @@ static int launch_sse(const float* a, int64_t a_rs, const float* b, int64_t b_rs
   return GANTTS_OK;
 }
 
-// clip_grad_norm_ + Adagrad over one model's parameter list: two launches (partials, update), no finish kernel
-static int clip_adagrad_model(const ParamList& pl, float* partial, float* sumsq_out, float max_norm, float lr, float wd,
-                              float eps, cudaStream_t st) {
+// clip_grad_norm_ + optimiser step over one model's parameter list: two launches (partials, update), no finish kernel
+static int clip_opt_model(const gantts_gan_step_t* c, const ParamList& pl, float* partial, float* sumsq_out, float lr, float wd,
+                          cudaStream_t st) {
   TensorList tl;
-  int rc = fill(tl, pl.p, pl.g, pl.s, nullptr, pl.sizes, 0, pl.n);
+  const bool adam = c->optimizer == GANTTS_OPT_ADAM;
+  int rc = fill(tl, pl.p, pl.g, pl.s, adam ? pl.s2 : nullptr, pl.sizes, 0, pl.n);
   if (rc) return rc;
   const int nb = blocks_for(tl.off[tl.n], OPT_MAX_BLOCKS);
   GANTTS_PDL_LAUNCH((sumsq_partial_kernel), nb, OPT_THREADS, 0, st, tl, partial);
   GANTTS_LAUNCH_CHECK("sumsq_partial_kernel");
-  GANTTS_PDL_LAUNCH((clip_adagrad_partials_kernel), nb, OPT_THREADS, 0, st, tl, partial, nb, sumsq_out, max_norm, lr, wd, eps);
-  GANTTS_LAUNCH_CHECK("clip_adagrad_partials_kernel");
+  if (adam) {
+    for (int i = 0; i < pl.n; ++i) GANTTS_CHECK_ARG(pl.s[i] && pl.s2[i], "gan_step: Adam needs exp_avg and exp_avg_sq for every tensor");
+    GANTTS_CHECK_ARG(c->opt_step >= 1, "gan_step: Adam needs opt_step >= 1 (the number of the step being taken)");
+    const double t = (double)c->opt_step;
+    const float step_size = (float)((double)lr / (1.0 - pow((double)c->beta1, t)));
+    const float inv_sqrt_bc2 = (float)(1.0 / sqrt(1.0 - pow((double)c->beta2, t)));
+    GANTTS_PDL_LAUNCH((clip_adam_partials_kernel), nb, OPT_THREADS, 0, st, tl, partial, nb, sumsq_out, c->max_norm, c->beta1, c->beta2,
+                      wd, c->eps, step_size, inv_sqrt_bc2);
+    GANTTS_LAUNCH_CHECK("clip_adam_partials_kernel");
+  } else {
+    GANTTS_PDL_LAUNCH((clip_adagrad_partials_kernel), nb, OPT_THREADS, 0, st, tl, partial, nb, sumsq_out, c->max_norm, lr, wd, c->eps);
+    GANTTS_LAUNCH_CHECK("clip_adagrad_partials_kernel");
+  }
   return GANTTS_OK;
 }
 
 static int check_step(const gantts_gan_step_t* c) {
   GANTTS_CHECK_ARG(c, "gan_step: null config");
   GANTTS_CHECK_ARG(c->B >= 1 && c->T >= 1, "gan_step: bad batch shape");
+  GANTTS_CHECK_ARG(c->optimizer == GANTTS_OPT_ADAGRAD || c->optimizer == GANTTS_OPT_ADAM, "gan_step: unknown optimizer %d", c->optimizer);
+  if (c->optimizer == GANTTS_OPT_ADAM)
+    GANTTS_CHECK_ARG(c->beta1 >= 0.f && c->beta1 < 1.f && c->beta2 >= 0.f && c->beta2 < 1.f, "gan_step: Adam betas out of range");
   GANTTS_CHECK_ARG(c->g.num_layers >= 1 && c->g.num_layers <= GANTTS_MAX_LAYERS, "gan_step: bad generator");
   GANTTS_CHECK_ARG(c->n_static >= 1 && c->n_static <= GANTTS_MAX_COLS, "gan_step: bad n_static");
   GANTTS_CHECK_ARG(c->n_static_cols == c->n_static, "gan_step: static column list must have n_static entries");
@@ -481,8 +536,8 @@ extern "C" int gantts_gan_step(const gantts_gan_step_t* c, int phases, const flo
   const int cond_w = (has_d && c->d_conditioned) ? d_in : 0;
   const int nA = dD - cond_w;
   ParamList pg, pd;
-  param_list(c->g, c->g_sumW, c->g_sumb, L.g_grads, &pg);
-  if (has_d) param_list(c->d, c->d_sumW, c->d_sumb, L.d_grads, &pd);
+  param_list(c->g, c->g_sumW, c->g_sumb, c->g_sqW, c->g_sqb, L.g_grads, &pg);
+  if (has_d) param_list(c->d, c->d_sumW, c->d_sumb, c->d_sqW, c->d_sqb, L.d_grads, &pd);
   ColList static_cols, adv_cols;
   static_cols.n = c->n_static_cols;
   for (int i = 0; i < c->n_static_cols; ++i) static_cols.c[i] = c->static_cols[i];
@@ -624,7 +679,7 @@ extern "C" int gantts_gan_step(const gantts_gan_step_t* c, int phases, const flo
     NvtxRange r2("gantts_gan_step/phase2: D step, adv D fwd+bwd, MLPG bwd, G bwd");
     if (has_d) {
       // ---- clip_grad_norm_ + Adagrad on D (train.py:275-276)
-      if ((rc = clip_adagrad_model(pd, L.opt_partial, L.scal + S_DSUMSQ, c->max_norm, c->lr_d, c->wd_d, c->eps, st)))
+      if ((rc = clip_opt_model(c, pd, L.opt_partial, L.scal + S_DSUMSQ, c->lr_d, c->wd_d, st)))
         return rc;
     }
     // ---- update_generator (train.py:282-320); the MGE term was evaluated in phase 1
@@ -685,7 +740,7 @@ extern "C" int gantts_gan_step(const gantts_gan_step_t* c, int phases, const flo
   if (phases & 4) {
     NvtxRange r4("gantts_gan_step/phase4: G step, losses");
     // ---- clip_grad_norm_ + Adagrad on G (train.py:317-318), then the loss scalars
-    if ((rc = clip_adagrad_model(pg, L.opt_partial, L.scal + S_GSUMSQ, c->max_norm, c->lr_g, c->wd_g, c->eps, st)))
+    if ((rc = clip_opt_model(c, pg, L.opt_partial, L.scal + S_GSUMSQ, c->lr_g, c->wd_g, st)))
       return rc;
     if (has_d) cnt.n[R_REAL] = cnt.n[R_FAKE] = bce_blocks(M);
     if (has_adv) cnt.n[R_ADV] = bce_blocks(M);

@@ -40,8 +40,19 @@ def _fill_mlp(desc, model, p, last_act):
 
 class FusedGanStep(object):
     def __init__(self, model_g, model_d, hp, B, T, w_d=1.0, mse_w=0.0, mge_w=1.0, lr=0.01, weight_decay=1e-7,
-                 max_norm=1.0, process_group=None, seed=None):
+                 max_norm=1.0, process_group=None, seed=None, optimizer="Adagrad", optimizer_params=None):
+        """``optimizer`` / ``optimizer_params`` mirror ``getattr(optim, hp.optimizer_g)(params, **hp.optimizer_g_params)``
+        of reference train.py:784-789 (one setting for both models): "Adagrad" (lr, weight_decay, eps; the defaults
+        are hparams.py:201-206) or "Adam" (lr, betas, eps, weight_decay; hparams.py:125-130)."""
         lib = _lib.load()
+        if optimizer not in ("Adagrad", "Adam"):
+            raise RuntimeError("FusedGanStep: no native optimiser %r (Adagrad and Adam are the ones hparams.py uses)" % optimizer)
+        self.optimizer = optimizer
+        okw = dict(optimizer_params or {})
+        if optimizer == "Adam":
+            lr, weight_decay = okw.get("lr", 1e-3), okw.get("weight_decay", 0.0)
+        else:
+            lr, weight_decay = okw.get("lr", lr), okw.get("weight_decay", weight_decay)
         self.g, self.d, self.hp, self.pg = model_g, model_d, hp, process_group
         self.B, self.T = int(B), int(T)
         dev = next(model_g.parameters()).device
@@ -54,12 +65,17 @@ class FusedGanStep(object):
         self._d_layers = _fill_mlp(c.d, model_d, model_d.dropout_p, _lib.ACT_SIGMOID)
         if model_g.last_sigmoid or not model_d.last_sigmoid:
             raise RuntimeError("FusedGanStep: generator must be linear-output, discriminator sigmoid-output")
-        self._sums = []
-        for layers, sw, sb in ((self._g_layers, c.g_sumW, c.g_sumb), (self._d_layers, c.d_sumW, c.d_sumb)):
+        self._sums, self._sqs = [], []      # Adagrad: state_sum | Adam: exp_avg, exp_avg_sq (model.parameters() order)
+        for layers, sw, sb, qw, qb in ((self._g_layers, c.g_sumW, c.g_sumb, c.g_sqW, c.g_sqb),
+                                       (self._d_layers, c.d_sumW, c.d_sumb, c.d_sqW, c.d_sqb)):
             for i, l in enumerate(layers):
                 a, b = torch.zeros_like(l.weight), torch.zeros_like(l.bias)
                 self._sums += [a, b]
                 sw[i], sb[i] = a.data_ptr(), b.data_ptr()
+                if optimizer == "Adam":
+                    a2, b2 = torch.zeros_like(l.weight), torch.zeros_like(l.bias)
+                    self._sqs += [a2, b2]
+                    qw[i], qb[i] = a2.data_ptr(), b2.data_ptr()
         nw = len(hp.windows)
         entries, n_static = multistream.mlpg_stream_entries(hp.stream_sizes, hp.has_dynamic_features,
                                                             [True] * len(hp.stream_sizes), nw)
@@ -82,7 +98,13 @@ class FusedGanStep(object):
         c.d_conditioned = 1 if hp.discriminator_linguistic_condition else 0
         c.lr_g = c.lr_d = float(lr)
         c.wd_g = c.wd_d = float(weight_decay)
-        c.eps, c.max_norm = 1e-10, float(max_norm)
+        c.max_norm = float(max_norm)
+        if optimizer == "Adam":
+            betas = okw.get("betas", (0.9, 0.999))
+            c.optimizer, c.beta1, c.beta2, c.eps = _lib.OPT_ADAM, float(betas[0]), float(betas[1]), float(okw.get("eps", 1e-8))
+        else:
+            c.optimizer, c.eps = _lib.OPT_ADAGRAD, float(okw.get("eps", 1e-10))
+        c.opt_step = 1
         c.w_d, c.mse_w, c.mge_w, c.adv_w = float(w_d), float(mse_w), float(mge_w), 1.0
         self.cfg = c
         nbytes = lib.gantts_gan_step_workspace_bytes(ctypes.byref(c))
@@ -153,6 +175,7 @@ class FusedGanStep(object):
         seed = (self._seed + self._step) & ((1 << 61) - 1)
         self.last_seed = seed
         self._step += 1
+        self.cfg.opt_step = self._step          # Adam's bias corrections: the number of the step being taken
         if world == 1:
             self._call(7, x, y, lengths, inv, seed)
         else:
@@ -179,29 +202,40 @@ class FusedGanStep(object):
     # ---- checkpoint / resume (reference train.py:162-171 save_checkpoint, :174-199 load_checkpoint round-trip
     # optimizer.state_dict(); the layout below is torch.optim.Adagrad's, one entry per parameter in
     # model.parameters() order, so the files are interchangeable with the reference's)
-    def _opt_state(self, model, sums, lr, wd):
-        n = len(sums)
-        return {"state": {i: {"step": torch.tensor(float(self._step)), "sum": s.detach().clone()}
-                          for i, s in enumerate(sums)},
+    def _opt_state(self, lo, hi, lr, wd):
+        n = hi - lo
+        step = torch.tensor(float(self._step))
+        if self.optimizer == "Adam":
+            return {"state": {i: {"step": step.clone(), "exp_avg": self._sums[lo + i].detach().clone(),
+                                  "exp_avg_sq": self._sqs[lo + i].detach().clone()} for i in range(n)},
+                    "param_groups": [{"lr": lr, "betas": (float(self.cfg.beta1), float(self.cfg.beta2)),
+                                      "eps": float(self.cfg.eps), "weight_decay": wd, "amsgrad": False, "maximize": False,
+                                      "foreach": None, "capturable": False, "differentiable": False, "fused": None,
+                                      "params": list(range(n))}]}
+        return {"state": {i: {"step": step.clone(), "sum": self._sums[lo + i].detach().clone()} for i in range(n)},
                 "param_groups": [{"lr": lr, "lr_decay": 0, "eps": float(self.cfg.eps), "weight_decay": wd,
                                   "initial_accumulator_value": 0, "foreach": None, "maximize": False,
                                   "differentiable": False, "fused": None, "params": list(range(n))}]}
 
     def state_dict(self):
-        ng = 2 * len(self._g_layers)
-        return {"optimizer_g": self._opt_state(self.g, self._sums[:ng], float(self.cfg.lr_g), float(self.cfg.wd_g)),
-                "optimizer_d": self._opt_state(self.d, self._sums[ng:], float(self.cfg.lr_d), float(self.cfg.wd_d)),
+        ng, n = 2 * len(self._g_layers), len(self._sums)
+        return {"optimizer_g": self._opt_state(0, ng, float(self.cfg.lr_g), float(self.cfg.wd_g)),
+                "optimizer_d": self._opt_state(ng, n, float(self.cfg.lr_d), float(self.cfg.wd_d)),
                 "step": self._step, "seed": self._seed}
 
     def load_state_dict(self, sd):
-        ng = 2 * len(self._g_layers)
-        for key, sums in (("optimizer_g", self._sums[:ng]), ("optimizer_d", self._sums[ng:])):
+        ng, n = 2 * len(self._g_layers), len(self._sums)
+        for key, lo, hi in (("optimizer_g", 0, ng), ("optimizer_d", ng, n)):
             st = sd[key]["state"]
-            for i, s in enumerate(sums):
+            for i in range(hi - lo):
                 e = st.get(i, st.get(str(i)))
                 if e is None:
                     raise RuntimeError("FusedGanStep.load_state_dict: %s has no state for parameter %d" % (key, i))
-                s.copy_(e["sum"])
+                if self.optimizer == "Adam":
+                    self._sums[lo + i].copy_(e["exp_avg"])
+                    self._sqs[lo + i].copy_(e["exp_avg_sq"])
+                else:
+                    self._sums[lo + i].copy_(e["sum"])
             grp = (sd[key].get("param_groups") or [{}])[0]
             if key == "optimizer_g":
                 self.cfg.lr_g = float(grp.get("lr", self.cfg.lr_g))

@@ -325,7 +325,20 @@ typedef struct {
                                               cat((x, y_adv), -1), d.dims[0] = g.dims[0] + n_adv */
   float lr_g, lr_d, wd_g, wd_d, eps, max_norm;
   float w_d, mse_w, mge_w, adv_w;
+  /* Optimiser of both models (reference train.py:784-789 getattr(optim, hp.optimizer_g)(...)): 0 = Adagrad
+   * (hparams.py:201-206; *_sum* = state_sum), 1 = Adam (hparams.py:125-130, the duration model: lr 1e-3,
+   * betas (0.5, 0.9), weight_decay 0, eps 1e-8, amsgrad off; *_sum* = exp_avg, *_sq* = exp_avg_sq, opt_step =
+   * number of the step being taken, 1 for the first -- the bias corrections are computed on the host). */
+  int optimizer;
+  float beta1, beta2;
+  int64_t opt_step;
+  float* g_sqW[GANTTS_MAX_LAYERS];
+  float* g_sqb[GANTTS_MAX_LAYERS];
+  float* d_sqW[GANTTS_MAX_LAYERS];
+  float* d_sqb[GANTTS_MAX_LAYERS];
 } gantts_gan_step_t;
+#define GANTTS_OPT_ADAGRAD 0
+#define GANTTS_OPT_ADAM 1
 
 /* Phase bits of gantts_gan_step.  GANTTS_STEP_EVAL = the "test" phase of reference train.py:481-486,
  * :273,:315 (model.eval(), phase != "train"): forwards and losses only -- dropout off, no backward, no

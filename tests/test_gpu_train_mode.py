@@ -200,6 +200,62 @@ def test_gan_trainer_duration_config_adam_and_no_R(dev):
                     st.v[i].copy_(sd[i]["exp_avg_sq"].cpu())
 
 
+def test_fused_step_adam(dev):
+    """gantts_gan_step with optimizer = Adam (reference hparams.py:125-130: lr 1e-3, betas (0.5, 0.9)) against the oracle
+    stepping with AdamStepper (pinned to torch.optim.Adam on the CPU): three consecutive steps -- losses, gradient norms,
+    post-step weights -- with the oracle re-synchronised to the product's weights and moments between steps (a first Adam
+    step is lr * sign(g)); and the state_dict is torch.optim.Adam's layout and round-trips."""
+    from gantts_b200 import fused, step as gstep
+    B, T = 4, 120
+    import gantts_b200
+    torch.manual_seed(9)
+    mg = gantts_b200.models.MLP(425, 187, 2, 128, dropout=0.0, last_sigmoid=False)
+    md = gantts_b200.models.MLP(58, 1, 2, 64, dropout=0.0, last_sigmoid=True)
+    names = ["layers.0", "layers.1", "last_linear"]
+    state = gp.GanStepState(layers_of(mg, names), layers_of(md, names))
+    mg, md = mg.to(dev).train(), md.to(dev).train()
+    okw = dict(lr=1e-3, betas=(0.5, 0.9), weight_decay=0.0, eps=1e-8)
+    fs = fused.FusedGanStep(mg, md, gstep.TTS_ACOUSTIC, B, T, w_d=1.0, mse_w=0.0, mge_w=1.0, seed=1, optimizer="Adam",
+                            optimizer_params=okw)
+    g_opt, d_opt = gp.AdamStepper(state.g_params(), **okw), gp.AdamStepper(state.d_params(), **okw)
+    R = torch.from_numpy(nnp.unit_variance_mlpg_matrix(WINDOWS, T))
+    for it in range(3):
+        lens = ragged_lengths(B, T, 50 + it)
+        x, y = make_batch(B, T, 425, 187, lens, 400 + it)
+        fs.step(x.to(dev), y.to(dev), torch.LongTensor(lens).to(dev), frames=sum(lens))
+        got = fs.loss_dict()
+        ref, yh_ref, ys_ref = gp.gan_step_mlp(state, x, y, lens, R, TTS_HP, d_opt=d_opt, g_opt=g_opt)
+        errs = loss_errors(got, ref, LOSS_KEYS + ("d_grad_norm", "g_grad_norm"))
+        errs["y_hat_static"] = rel_err(npy(fs.y_hat_static), ys_ref.numpy())
+        assert max(errs.values()) < 1e-4, (it, errs)
+        sd = fs.state_dict()
+        for mod, params, key, st in ((mg, state.g_params(), "optimizer_g", g_opt), (md, state.d_params(), "optimizer_d", d_opt)):
+            assert set(sd[key]["state"][0]) == {"step", "exp_avg", "exp_avg_sq"} and sd[key]["param_groups"][0]["betas"] == (0.5, 0.9)
+            for i, (q, r) in enumerate(zip(mod.parameters(), params)):
+                dW = np.abs(npy(q) - r.detach().numpy())
+                assert np.median(dW) < 2e-6 and dW.max() <= 4e-3, (it, key, i, np.median(dW), dW.max())
+                with torch.no_grad():                                    # re-synchronise the oracle
+                    r.copy_(q.detach().cpu())
+                    st.m[i].copy_(sd[key]["state"][i]["exp_avg"].cpu())
+                    st.v[i].copy_(sd[key]["state"][i]["exp_avg_sq"].cpu())
+    # resume: a second object loaded from the state_dict takes the same next step
+    snap = [q.detach().clone() for q in list(mg.parameters()) + list(md.parameters())]
+    sd = fs.state_dict()
+    lens = ragged_lengths(B, T, 60)
+    x, y = make_batch(B, T, 425, 187, lens, 500)
+    fs.step(x.to(dev), y.to(dev), torch.LongTensor(lens).to(dev), frames=sum(lens))
+    after = [q.detach().clone() for q in list(mg.parameters()) + list(md.parameters())]
+    with torch.no_grad():
+        for q, v in zip(list(mg.parameters()) + list(md.parameters()), snap):
+            q.copy_(v)
+    fs2 = fused.FusedGanStep(mg, md, gstep.TTS_ACOUSTIC, B, T, w_d=1.0, mse_w=0.0, mge_w=1.0, seed=77, optimizer="Adam",
+                             optimizer_params=okw)
+    fs2.load_state_dict(sd)
+    fs2.step(x.to(dev), y.to(dev), torch.LongTensor(lens).to(dev), frames=sum(lens))
+    for q, v in zip(list(mg.parameters()) + list(md.parameters()), after):
+        assert torch.equal(q.detach(), v)
+
+
 def test_fused_step_static_only_streams(dev):
     """The same static-only configuration on the fused entry point (Adagrad): no stream has dynamic features, MLPG
     degenerates to a copy (reference train.py:510-515: R = None), the discriminator sees the whole stream."""
