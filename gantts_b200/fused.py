@@ -101,6 +101,7 @@ class FusedGanStep(object):
         c.max_norm = float(max_norm)
         if optimizer == "Adam":
             betas = okw.get("betas", (0.9, 0.999))
+            self._betas = (float(betas[0]), float(betas[1]))          # as given (the C struct holds them as float32)
             c.optimizer, c.beta1, c.beta2, c.eps = _lib.OPT_ADAM, float(betas[0]), float(betas[1]), float(okw.get("eps", 1e-8))
         else:
             c.optimizer, c.eps = _lib.OPT_ADAGRAD, float(okw.get("eps", 1e-10))
@@ -208,7 +209,7 @@ class FusedGanStep(object):
         if self.optimizer == "Adam":
             return {"state": {i: {"step": step.clone(), "exp_avg": self._sums[lo + i].detach().clone(),
                                   "exp_avg_sq": self._sqs[lo + i].detach().clone()} for i in range(n)},
-                    "param_groups": [{"lr": lr, "betas": (float(self.cfg.beta1), float(self.cfg.beta2)),
+                    "param_groups": [{"lr": lr, "betas": self._betas,
                                       "eps": float(self.cfg.eps), "weight_decay": wd, "amsgrad": False, "maximize": False,
                                       "foreach": None, "capturable": False, "differentiable": False, "fused": None,
                                       "params": list(range(n))}]}
@@ -237,6 +238,9 @@ class FusedGanStep(object):
                 else:
                     self._sums[lo + i].copy_(e["sum"])
             grp = (sd[key].get("param_groups") or [{}])[0]
+            if self.optimizer == "Adam" and "betas" in grp:
+                self._betas = (float(grp["betas"][0]), float(grp["betas"][1]))
+                self.cfg.beta1, self.cfg.beta2 = self._betas
             if key == "optimizer_g":
                 self.cfg.lr_g = float(grp.get("lr", self.cfg.lr_g))
                 self.cfg.wd_g = float(grp.get("weight_decay", self.cfg.wd_g))

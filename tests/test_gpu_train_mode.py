@@ -230,7 +230,7 @@ def test_fused_step_adam(dev):
         assert max(errs.values()) < 1e-4, (it, errs)
         sd = fs.state_dict()
         for mod, params, key, st in ((mg, state.g_params(), "optimizer_g", g_opt), (md, state.d_params(), "optimizer_d", d_opt)):
-            assert set(sd[key]["state"][0]) == {"step", "exp_avg", "exp_avg_sq"} and sd[key]["param_groups"][0]["betas"] == (0.5, 0.9)
+            assert set(sd[key]["state"][0]) == {"step", "exp_avg", "exp_avg_sq"} and tuple(sd[key]["param_groups"][0]["betas"]) == (0.5, 0.9)
             for i, (q, r) in enumerate(zip(mod.parameters(), params)):
                 dW = np.abs(npy(q) - r.detach().numpy())
                 assert np.median(dW) < 2e-6 and dW.max() <= 4e-3, (it, key, i, np.median(dW), dW.max())
