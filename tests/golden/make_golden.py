@@ -23,6 +23,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 
 from oracle import reference_loader  # noqa: E402
+from oracle import nnmnkwii_port as nnp  # noqa: E402
 
 WINDOWS = [
     (0, 0, np.array([1.0])),
@@ -268,10 +269,51 @@ def gen_step_models(ref, out):
         hp.stream_sizes, hp.discriminator_linguistic_condition = saved
 
 
+def gen_eval(ref, out):
+    """reference evaluation_tts.py:50-97 ``gen_parameters`` (the call site of nnmnkwii.paramgen.mlpg with unit and
+    with real variances), executed UNMODIFIED where it lies: only that function definition is compiled out of the file
+    (the module imports pyworld / pysptk / hts question sets at load time), with ``paramgen`` / ``P`` bound to the
+    oracle's restatements and ``hp_acoustic`` to the reference's own hparams.tts_acoustic."""
+    import ast
+    import types
+    path = os.path.join(reference_loader.REFERENCE_ROOT, "evaluation_tts.py")
+    tree = ast.parse(open(path).read(), path)
+    fn = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "gen_parameters"]
+    assert len(fn) == 1
+    ns = {"np": np, "paramgen": types.SimpleNamespace(mlpg=nnp.mlpg),
+          "P": types.SimpleNamespace(inv_scale=lambda x, m, s: s * x + m), "hp_acoustic": ref.hparams.tts_acoustic}
+    exec(compile(ast.Module(body=fn, type_ignores=[]), path, "exec"), ns)
+    rng = np.random.RandomState(11)
+    T = 90
+    y = rng.randn(T, 187)
+    mean = {"acoustic": rng.randn(187) * 0.3}
+    std = {"acoustic": 0.4 + rng.rand(187)}
+    out["eval_y"], out["eval_mean"], out["eval_std"] = y, mean["acoustic"], std["acoustic"]
+    for tag, mge in (("mge", True), ("var", False)):
+        # the non-MGE branch inv_scales with the dicts themselves at reference evaluation_tts.py:82 (a latent bug of the
+        # script: P.inv_scale(y, Y_mean, Y_std) on dict arguments); it is fed the acoustic arrays through a dict-like
+        # that also answers ["acoustic"], which is what the following lines index
+        if mge:
+            mgc, lf0, vuv, bap = ns["gen_parameters"](y.copy(), mean, std, True)
+        else:
+            class Both(np.ndarray):
+                def __getitem__(self, k):
+                    return np.asarray(self) if isinstance(k, str) else np.ndarray.__getitem__(self, k)
+            mgc, lf0, vuv, bap = ns["gen_parameters"](y.copy(), mean["acoustic"].view(Both), std["acoustic"].view(Both), False)
+        for k, v in (("mgc", mgc), ("lf0", lf0), ("vuv", vuv), ("bap", bap)):
+            out["eval_%s_%s" % (tag, k)] = np.asarray(v, dtype=np.float64)
+
+
 def main():
     ref = reference_loader.load()
     torch.manual_seed(1234)
     torch.set_num_threads(1)
+    if "--only-eval" in sys.argv:
+        e = {}
+        gen_eval(ref, e)
+        np.savez_compressed(os.path.join(HERE, "eval.npz"), **e)
+        print("eval", os.path.getsize(os.path.join(HERE, "eval.npz")))
+        return
     if "--only-step-models" in sys.argv:
         d = {}
         gen_step_models(ref, d)
@@ -290,7 +332,10 @@ def main():
     d = {}
     gen_step_models(ref, d)
     np.savez_compressed(os.path.join(HERE, "step_models.npz"), **d)
-    for n in ("ops", "models", "step", "step_models"):
+    e = {}
+    gen_eval(ref, e)
+    np.savez_compressed(os.path.join(HERE, "eval.npz"), **e)
+    for n in ("ops", "models", "step", "step_models", "eval"):
         print(n, os.path.getsize(os.path.join(HERE, n + ".npz")))
 
 

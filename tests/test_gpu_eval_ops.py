@@ -135,3 +135,21 @@ def test_compat_paramgen_mlpg_numpy_api(dev):
         np.testing.assert_allclose(out, nnp.mlpg(mu, np.ones(9), WINDOWS), rtol=2e-5, atol=2e-6)
     finally:
         sys.path.remove(os.path.join(ROOT, "compat"))
+
+
+def test_evaluation_gen_parameters_on_cuda_paramgen(dev):
+    """The evaluation call site of MLPG (reference evaluation_tts.py:50-97, both branches) through the product's
+    nnmnkwii.paramgen.mlpg (compat shim -> gantts_mlpg_var on the GPU) and nnmnkwii.preprocessing.inv_scale, against the
+    outputs of the unmodified reference function (tests/golden/eval.npz)."""
+    if os.path.join(ROOT, "compat") not in sys.path:
+        sys.path.insert(1, os.path.join(ROOT, "compat"))
+    from nnmnkwii import paramgen, preprocessing
+    import evaltts_mirror
+    g = np.load(os.path.join(ROOT, "tests", "golden", "eval.npz"))
+    for tag, mge in (("mge", True), ("var", False)):
+        got = evaltts_mirror.gen_parameters(g["eval_y"].copy(), g["eval_mean"], g["eval_std"], mge, [180, 3, 1, 3], WINDOWS,
+                                            paramgen, preprocessing)
+        for k, v in zip(("mgc", "lf0", "vuv", "bap"), got):
+            want = g["eval_%s_%s" % (tag, k)]
+            assert np.abs(np.asarray(v, dtype=np.float64) - want).max() <= 2e-5 * np.abs(want).max(), (tag, k)
+

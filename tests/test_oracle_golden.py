@@ -288,3 +288,22 @@ def test_adam_stepper_matches_torch_optim_adam():
             st(b, [g.clone() for g in gs])
             for p, q in zip(a, b):
                 assert float((p.detach() - q).abs().max()) < 2e-7
+
+
+def test_evaluation_gen_parameters_mirror_matches_reference():
+    """tests/evaltts_mirror.gen_parameters (what the GPU suite drives the CUDA paramgen.mlpg through) against the outputs of the
+    UNMODIFIED reference evaluation_tts.py:50-97 (tests/golden/eval.npz, generated by make_golden.py::gen_eval), both
+    branches: MLPG with unit variance on normalised features, and with the real variances after inverse scaling."""
+    import os
+    import types
+    import evaltts_mirror
+    from conftest import WINDOWS
+    from oracle import nnmnkwii_port as nnp
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "eval.npz"))
+    P = types.SimpleNamespace(inv_scale=lambda x, m, s: s * x + m)
+    pg = types.SimpleNamespace(mlpg=nnp.mlpg)
+    for tag, mge in (("mge", True), ("var", False)):
+        got = evaltts_mirror.gen_parameters(g["eval_y"].copy(), g["eval_mean"], g["eval_std"], mge, [180, 3, 1, 3], WINDOWS, pg, P)
+        for k, v in zip(("mgc", "lf0", "vuv", "bap"), got):
+            assert np.abs(np.asarray(v) - g["eval_%s_%s" % (tag, k)]).max() < 1e-10, (tag, k)
+
