@@ -233,7 +233,7 @@ def cpu_reference_step_runner(w, sample_B, threads):
     return run, sample_B * w["T"], r_seconds
 
 
-def time_cpu_baseline(w, steps, warmup, full_batch):
+def time_cpu_baseline(w, steps, warmup, full_batch, time_budget_s=None):
     """Reference CPU arm.  torch's CPU kernels do not scale to every core of a large host on these shapes (128
     threads were 3x slower than 32 on the B200 box), so a one-step probe picks the fastest thread count among
     {16, 32, 64, all}.  `full_batch`: time the whole B-utterance batch (same config as the GPU arm); when one step of
@@ -260,6 +260,10 @@ def time_cpu_baseline(w, steps, warmup, full_batch):
         if best_dt is None or dt < best_dt:
             best, best_dt = c, dt
     torch.set_num_threads(best)
+    if time_budget_s is not None:
+        # the reference arm honours --steps / --warmup as far as the time budget allows (CPU steps take seconds each)
+        steps = max(2, min(steps, int(time_budget_s / max(best_dt, 1e-3))))
+        warmup = max(1, min(warmup, int(0.25 * time_budget_s / max(best_dt, 1e-3))))
     for _ in range(max(0, warmup - 1)):
         run()
     t0 = time.perf_counter()
@@ -273,7 +277,7 @@ def time_cpu_baseline(w, steps, warmup, full_batch):
                       "one-step probe" % (sample_B, w["B"], w["T"], steps, w["T"], r_s, frames / (dt + r_s),
                                           torch.__version__, cands, ncpu),
             "ms_per_step": dt * 1e3, "same_config_as_gpu_arm": sample_B == w["B"],
-            "value_with_R_build": frames / (dt + r_s)}
+            "value_with_R_build": frames / (dt + r_s), "steps_timed": steps, "warmup_run": warmup}
 
 
 def run_reference_arm(args):
@@ -281,16 +285,16 @@ def run_reference_arm(args):
     if rank != 0:
         return
     w = WORKLOADS[args.workload]
-    steps, warmup = max(2, min(args.steps, 4)), max(1, min(args.warmup, 2))
-    cb = time_cpu_baseline(w, steps, warmup, full_batch=True)
+    cb = time_cpu_baseline(w, max(2, args.steps), max(1, args.warmup), full_batch=True, time_budget_s=90.0)
+    steps, warmup = cb["steps_timed"], cb["warmup_run"]
     line = {"impl": "reference", "metric": "gan_step_frames_per_sec", "value": cb["value"], "unit": "frames/s",
             "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": cb["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(w, "cpu", args), "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
-            "note": "CPU steps take seconds each: the arm times %d steps after %d warm-up regardless of larger "
-                    "--steps/--warmup so that the run ends within minutes" % (steps, warmup)}
+            "note": "CPU steps take seconds each: the arm runs --steps/--warmup as far as a 90 s budget of timed work allows "
+                    "(here %d timed steps after %d warm-up) so that the run ends within minutes" % (steps, warmup)}
     emit_json_line(line)
 
 
