@@ -259,3 +259,22 @@ def test_dropout_hash_statistics():
         assert abs(m.mean(0).std() / np.sqrt(q / rows) - 1.0) < 0.25
         assert abs(m.mean(1).std() / np.sqrt(q / n) - 1.0) < 0.1
     assert not dm.keep_mask(7, 64, 64, 1.0).any() and dm.keep_mask(7, 64, 64, 0.0).all()
+
+
+def test_bench_algorithmic_work_matches_survey_8d():
+    """bench.py's roofline numerator: SURVEY.md 8(d) algorithmic MACs per padded frame of the de-duplicated GAN step --
+    cfg2 3 449 856 (= 3 F_G - k0 + 8 F_D - 256 d_in); cfg3 / cfg5: 3 x (LSTM stack 15.41 M / 16.42 M + hidden2out
+    181 248 / 191 488) minus the first layer's input-gradient product, plus the discriminator's share."""
+    import bench
+    assert bench.algorithmic_flops_per_frame(bench.WORKLOADS["cfg2"]) == 2.0 * 3449856
+    for name, lstm_macs, out_macs in (("cfg3", 15405056, 181248), ("cfg5", 16420864, 191488)):
+        w = bench.WORKLOADS[name]
+        H, F_L, inp = w["g_hidden"], 0, w["d_in"]
+        for _ in range(w["g_layers"]):
+            F_L += 2 * 4 * H * (inp + H)
+            inp = 2 * H
+        assert F_L == lstm_macs and 2 * H * w["d_out"] == out_macs
+        dd = w["d_dims"]
+        F_D = sum(a * b for a, b in zip(dd[:-1], dd[1:]))
+        want = 3 * (F_L + out_macs) - 2 * 4 * H * w["d_in"] + 2 * w.get("static_dim", 0) ** 2 + 8 * F_D - dd[1] * dd[0]
+        assert bench.algorithmic_flops_per_frame(w) == 2.0 * want
